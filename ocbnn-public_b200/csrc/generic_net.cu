@@ -1,0 +1,430 @@
+// generic_net.cu — K1 for arbitrary MLPs (credit [10,50,50,2] D=3202, recid [9,100,100,1] D=11201, deep toys):
+// ONE CTA PER WEIGHT VECTOR.  The particle's weights and its gradient accumulator stay resident in shared
+// memory (padded row-major), points are streamed through in tiles of TP, and every layer is a small
+// register-tiled fp32 GEMM (4x4 outputs per thread, float4 shared-memory operands):
+//     forward   Z_l[o][p]  = sum_d W_l[d][o] A_{l-1}[d][p] + b_l[o]
+//     backward  dW_l[d][o] += sum_p A_{l-1}[d][p] dZ_l[o][p] ;  dA_{l-1}[d][p] = sum_o W_l[d][o] dZ_l[o][p]
+// Activations are stored feature-major ([feature][point], row stride TP+4) so that the 4 points of a register
+// tile are one LDS.128 and consecutive feature rows fall in distinct banks.
+// Replaces forward (bnn/base.py:89-104) + autograd for the application-sized nets; fp32 SIMT on purpose:
+// the parity bar is 1e-5 and tcgen05 has no fp32 MMA.
+#include "heads.cuh"
+#include "small_net.cuh"
+
+namespace ocbnn {
+
+constexpr int kGenThreads = 256;
+constexpr int kMaxRt = 10;  // largest output width the runtime head dispatch handles
+
+struct GenLayout {
+    int nl;                          // weight layers
+    int s[OCBNN_MAX_LAYERS + 1];     // layer widths
+    int ws[OCBNN_MAX_LAYERS + 1];    // padded row stride of W_l / length of padded b_l  (index l = 1..nl)
+    int woff[OCBNN_MAX_LAYERS + 1];  // offset of W_l in the padded weight block
+    int boff[OCBNN_MAX_LAYERS + 1];  // offset of b_l
+    int coff[OCBNN_MAX_LAYERS + 1];  // offset of W_l in the compact (reference) layout
+    int wtot;                        // floats in the padded weight block
+    int arow[OCBNN_MAX_LAYERS + 1];  // first activation row of layer l (rows of length TS)
+    int rows_tot;                    // activation rows (A_0, then Z_l/A_l pairs)
+    int maxw;                        // widest padded layer (dZ ping-pong buffers)
+    int tp, ts;                      // points per tile, row stride
+    int act;
+    int d;                           // compact weight count
+};
+
+__host__ __device__ inline int pad4(int v) { return (v + 3) & ~3; }
+
+static GenLayout make_layout(const Problem& p, int tp) {
+    GenLayout L{};
+    L.nl = p.desc.n_layers;
+    for (int l = 0; l <= L.nl; ++l) L.s[l] = p.desc.layer_sizes[l];
+    int off = 0, coff = 0, rows = pad4(L.s[0]);
+    L.arow[0] = 0;
+    L.maxw = 4;
+    for (int l = 1; l <= L.nl; ++l) {
+        int w = pad4(L.s[l]);
+        if (w % 32 == 0) w += 4;
+        L.ws[l] = w;
+        L.woff[l] = off;
+        off += L.s[l - 1] * w;
+        L.boff[l] = off;
+        off += w;
+        L.coff[l] = coff;
+        coff += (L.s[l - 1] + 1) * L.s[l];
+        L.arow[l] = rows;          // Z_l rows [arow, arow+w) ; A_l rows [arow+w, arow+2w)
+        rows += 2 * w;
+        if (w > L.maxw) L.maxw = w;
+    }
+    L.wtot = off;
+    L.rows_tot = rows;
+    L.tp = tp;
+    L.ts = tp + 4;
+    L.act = p.desc.activation;
+    L.d = coff;
+    return L;
+}
+
+static size_t gen_smem_bytes(const GenLayout& L, int rs) {
+    size_t f = 2 * (size_t)L.wtot                 // weights + gradient
+               + (size_t)L.rows_tot * L.ts        // activations
+               + 2 * (size_t)L.maxw * L.ts        // dZ ping-pong
+               + (size_t)L.tp * rs                // staged records
+               + 64;                              // reduction scratch
+    return f * sizeof(float);
+}
+
+__device__ __forceinline__ float act_rt(int act, float z) {
+    if (act == OCBNN_ACT_RBF) return expf(-z * z);
+    if (act == OCBNN_ACT_RELU) return fmaxf(z, 0.f);
+    return z;
+}
+__device__ __forceinline__ float dact_rt(int act, float z, float a) {
+    if (act == OCBNN_ACT_RBF) return a * (-2.f * z);
+    if (act == OCBNN_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+    return 1.f;
+}
+
+// Z[o][p] = b[o] + sum_d W[d][o] A[d][p] ; Aout = act(Z) unless last
+__device__ __forceinline__ void gen_forward_layer(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ Ain,
+                                                  float* __restrict__ Z, float* __restrict__ Aout, int s_in, int ws, int tp, int ts, int act,
+                                                  bool last) {
+    const int npt = tp >> 2, ntile = (ws >> 2) * npt;
+    for (int tile = threadIdx.x; tile < ntile; tile += blockDim.x) {
+        const int pt = tile % npt, ot = tile / npt;
+        float4 bb = *reinterpret_cast<const float4*>(b + 4 * ot);
+        float acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[0][j] = bb.x; acc[1][j] = bb.y; acc[2][j] = bb.z; acc[3][j] = bb.w; }
+        const float* wp = W + 4 * ot;
+        const float* ap = Ain + 4 * pt;
+#pragma unroll 4
+        for (int d = 0; d < s_in; ++d) {
+            float4 w4 = *reinterpret_cast<const float4*>(wp + d * ws);
+            float4 a4 = *reinterpret_cast<const float4*>(ap + d * ts);
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[i], av[j], acc[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float* zr = Z + (4 * ot + i) * ts + 4 * pt;
+            *reinterpret_cast<float4*>(zr) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            if (!last) {
+                float* ar = Aout + (4 * ot + i) * ts + 4 * pt;
+                *reinterpret_cast<float4*>(ar) = make_float4(act_rt(act, acc[i][0]), act_rt(act, acc[i][1]), act_rt(act, acc[i][2]),
+                                                             act_rt(act, acc[i][3]));
+            }
+        }
+    }
+}
+
+// gW[d][o] += sum_p A[d][p] dZ[o][p] ; gb[o] += sum_p dZ[o][p].   Thread tile: rows d = dt + i*ND, o = ot + j*NO (interleaved,
+// so that the rows a warp touches at one step are consecutive -> distinct banks).
+__device__ __forceinline__ void gen_backward_weights(float* __restrict__ gW, float* __restrict__ gb, const float* __restrict__ Ain,
+                                                     const float* __restrict__ dZ, int s_in, int s_out, int ws, int tp, int ts) {
+    const int ND = (s_in + 3) >> 2, NO = ws >> 2, ntile = ND * NO;
+    for (int tile = threadIdx.x; tile < ntile; tile += blockDim.x) {
+        const int dt = tile % ND, ot = tile / ND;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int p = 0; p < tp; p += 4) {
+            float4 a4[4], z4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a4[i] = *reinterpret_cast<const float4*>(Ain + (dt + i * ND) * ts + p);   // pad rows are zero
+#pragma unroll
+            for (int j = 0; j < 4; ++j) z4[j] = *reinterpret_cast<const float4*>(dZ + (ot + j * NO) * ts + p);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[i][j] = fmaf(a4[i].x, z4[j].x, acc[i][j]);
+                    acc[i][j] = fmaf(a4[i].y, z4[j].y, acc[i][j]);
+                    acc[i][j] = fmaf(a4[i].z, z4[j].z, acc[i][j]);
+                    acc[i][j] = fmaf(a4[i].w, z4[j].w, acc[i][j]);
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int d = dt + i * ND;
+            if (d < s_in) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int o = ot + j * NO;
+                    if (o < s_out) gW[d * ws + o] += acc[i][j];
+                }
+            }
+        }
+    }
+    for (int o = threadIdx.x; o < s_out; o += blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < tp; ++p) s += dZ[o * ts + p];
+        gb[o] += s;
+    }
+}
+
+// dZprev[d][p] = (sum_o W[d][o] dZ[o][p]) * act'(Zprev[d][p])
+__device__ __forceinline__ void gen_backward_input(const float* __restrict__ W, const float* __restrict__ dZ, const float* __restrict__ Zprev,
+                                                   const float* __restrict__ Aprev, float* __restrict__ dZprev, int s_in, int ws, int wsp, int tp,
+                                                   int ts, int act) {
+    // wsp: padded width of the previous layer (rows of dZprev to produce, rows >= s_in are written as zero)
+    const int ND = wsp >> 2, npt = tp >> 2, ntile = ND * npt;
+    for (int tile = threadIdx.x; tile < ntile; tile += blockDim.x) {
+        const int dt = tile % ND, pt = tile / ND;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int o = 0; o < ws; o += 4) {
+            float4 w4[4], z4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int d = dt + i * ND;
+                w4[i] = d < s_in ? *reinterpret_cast<const float4*>(W + d * ws + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) z4[jj] = *reinterpret_cast<const float4*>(dZ + (o + jj) * ts + 4 * pt);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float wv[4] = {w4[i].x, w4[i].y, w4[i].z, w4[i].w};
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    acc[i][0] = fmaf(wv[jj], z4[jj].x, acc[i][0]);
+                    acc[i][1] = fmaf(wv[jj], z4[jj].y, acc[i][1]);
+                    acc[i][2] = fmaf(wv[jj], z4[jj].z, acc[i][2]);
+                    acc[i][3] = fmaf(wv[jj], z4[jj].w, acc[i][3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int d = dt + i * ND;
+            float4 zz = *reinterpret_cast<const float4*>(Zprev + d * ts + 4 * pt);
+            float4 aa = *reinterpret_cast<const float4*>(Aprev + d * ts + 4 * pt);
+            float4 r;
+            r.x = acc[i][0] * dact_rt(act, zz.x, aa.x);
+            r.y = acc[i][1] * dact_rt(act, zz.y, aa.y);
+            r.z = acc[i][2] * dact_rt(act, zz.z, aa.z);
+            r.w = acc[i][3] * dact_rt(act, zz.w, aa.w);
+            if (d >= s_in) r = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(dZprev + d * ts + 4 * pt) = r;
+        }
+    }
+}
+
+template <int SK>
+__device__ __forceinline__ float head_at_point(int kind, const float* Zlast, int ts, int p, const float* prm, const HeadConsts& hc, float wgt,
+                                               float* dZ) {
+    float f[SK], df[SK], val;
+#pragma unroll
+    for (int k = 0; k < SK; ++k) f[k] = Zlast[k * ts + p];
+    eval_head<SK>(kind, f, prm, hc, val, df);
+#pragma unroll
+    for (int k = 0; k < SK; ++k) dZ[k * ts + p] = wgt * df[k];
+    return wgt * val;
+}
+
+__device__ __forceinline__ float head_dispatch(int sk, int kind, const float* Zlast, int ts, int p, const float* prm, const HeadConsts& hc,
+                                               float wgt, float* dZ) {
+    switch (sk) {
+        case 1: return head_at_point<1>(kind, Zlast, ts, p, prm, hc, wgt, dZ);
+        case 2: return head_at_point<2>(kind, Zlast, ts, p, prm, hc, wgt, dZ);
+        case 3: return head_at_point<3>(kind, Zlast, ts, p, prm, hc, wgt, dZ);
+        case 4: return head_at_point<4>(kind, Zlast, ts, p, prm, hc, wgt, dZ);
+        case 5: return head_at_point<5>(kind, Zlast, ts, p, prm, hc, wgt, dZ);
+        case 6: return head_at_point<6>(kind, Zlast, ts, p, prm, hc, wgt, dZ);
+        case 7: return head_at_point<7>(kind, Zlast, ts, p, prm, hc, wgt, dZ);
+        case 8: return head_at_point<8>(kind, Zlast, ts, p, prm, hc, wgt, dZ);
+        case 9: return head_at_point<9>(kind, Zlast, ts, p, prm, hc, wgt, dZ);
+        default: return head_at_point<10>(kind, Zlast, ts, p, prm, hc, wgt, dZ);
+    }
+}
+
+__global__ void __launch_bounds__(kGenThreads)
+k_logpost_generic(EvalArgs a, GenLayout L, const float* __restrict__ w, long long m, float* __restrict__ out_lp, float* __restrict__ out_grad) {
+    extern __shared__ __align__(16) float smem[];
+    float* Ws = smem;
+    float* Gs = Ws + L.wtot;
+    float* Act = Gs + L.wtot;
+    float* dZa = Act + (size_t)L.rows_tot * L.ts;
+    float* dZb = dZa + (size_t)L.maxw * L.ts;
+    float* rec = dZb + (size_t)L.maxw * L.ts;
+    double* red = reinterpret_cast<double*>(rec + (((size_t)L.tp * a.rs + 1) & ~(size_t)1));
+
+    EvalCtx c = make_ctx(a, rec, nullptr, L.tp);
+    const int tp = L.tp, ts = L.ts, nl = L.nl, sk = L.s[nl];
+
+    for (long long chain = blockIdx.x; chain < m; chain += gridDim.x) {
+        __syncthreads();
+        // weights -> padded shared layout, gradient = 0, activations = 0 (pad rows must stay zero)
+        for (int i = threadIdx.x; i < L.wtot; i += blockDim.x) { Ws[i] = 0.f; Gs[i] = 0.f; }
+        for (int i = threadIdx.x; i < L.rows_tot * ts; i += blockDim.x) Act[i] = 0.f;
+        __syncthreads();
+        const float* wc = w + chain * L.d;
+        for (int l = 1; l <= nl; ++l) {
+            const int sin = L.s[l - 1], so = L.s[l], ws = L.ws[l];
+            for (int i = threadIdx.x; i < (sin + 1) * so; i += blockDim.x) {
+                int r = i / so, o = i - r * so;
+                float v = __ldg(wc + L.coff[l] + i);
+                if (r < sin) Ws[L.woff[l] + r * ws + o] = v; else Ws[L.boff[l] + o] = v;
+            }
+        }
+        double lp = 0.0;
+        for (int begin = 0; begin < c.npts; begin += tp) {
+            const int count = min(tp, c.npts - begin);
+            __syncthreads();
+            stage_points(rec, a, c.nb, c.mult, begin, count);
+            __syncthreads();
+            // A_0[d][p] = x ; points beyond count are zero with zero weight
+            for (int i = threadIdx.x; i < L.s[0] * tp; i += blockDim.x) {
+                int d = i / tp, p = i - d * tp;
+                Act[d * ts + p] = p < count ? rec[p * a.rs + d] : 0.f;
+            }
+            __syncthreads();
+            const float* Ain = Act;
+            for (int l = 1; l <= nl; ++l) {
+                float* Z = Act + (size_t)L.arow[l] * ts;
+                float* Aout = Z + (size_t)L.ws[l] * ts;
+                gen_forward_layer(Ws + L.woff[l], Ws + L.boff[l], Ain, Z, Aout, L.s[l - 1], L.ws[l], tp, ts, L.act, l == nl);
+                __syncthreads();
+                Ain = Aout;
+            }
+            // heads: dZ_K (weighted) and the value
+            float* dZ = dZa;
+            float* dZo = dZb;
+            {
+                const float* Zl = Act + (size_t)L.arow[nl] * ts;
+                for (int i = threadIdx.x; i < L.ws[nl] * ts; i += blockDim.x) dZ[i] = 0.f;
+                __syncthreads();
+                if (threadIdx.x < count) {
+                    const float* r = rec + threadIdx.x * a.rs;
+                    int kind = __float_as_int(r[a.s0]);
+                    lp += (double)head_dispatch(sk, kind, Zl, ts, threadIdx.x, r + a.s0 + 2, c.hc, r[a.s0 + 1], dZ);
+                }
+                __syncthreads();
+            }
+            for (int l = nl; l >= 1; --l) {
+                const float* Aprev = (l == 1) ? Act : Act + ((size_t)L.arow[l - 1] + L.ws[l - 1]) * ts;
+                gen_backward_weights(Gs + L.woff[l], Gs + L.boff[l], Aprev, dZ, L.s[l - 1], L.s[l], L.ws[l], tp, ts);
+                if (l > 1) {
+                    const float* Zprev = Act + (size_t)L.arow[l - 1] * ts;
+                    gen_backward_input(Ws + L.woff[l], dZ, Zprev, Aprev, dZo, L.s[l - 1], L.ws[l], L.ws[l - 1], tp, ts, L.act);
+                }
+                __syncthreads();
+                float* t = dZ; dZ = dZo; dZo = t;
+            }
+        }
+        // Gaussian prior, value reduction, compact gradient write-out
+        double pr = 0.0;
+        for (int l = 1; l <= nl; ++l) {
+            const int sin = L.s[l - 1], so = L.s[l], ws = L.ws[l];
+            for (int i = threadIdx.x; i < (sin + 1) * so; i += blockDim.x) {
+                int r = i / so, o = i - r * so;
+                int si = r < sin ? L.woff[l] + r * ws + o : L.boff[l] + o;
+                float2 mv = a.pri[L.coff[l] + i];
+                float diff = Ws[si] - mv.x, t = diff * mv.y;
+                pr += (double)(diff * t);
+                if (out_grad) out_grad[chain * L.d + L.coff[l] + i] = Gs[si] - t;
+            }
+        }
+        lp -= 0.5 * pr;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, off);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lp;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = c.lp_const;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+            if (out_lp) out_lp[chain] = (float)s;
+        }
+    }
+}
+
+// forward only: out[chain][p][k]
+__global__ void __launch_bounds__(kGenThreads)
+k_forward_generic(GenLayout L, const float* __restrict__ w, long long m, const float* __restrict__ x, long long npts, float* __restrict__ out) {
+    extern __shared__ __align__(16) float smem[];
+    float* Ws = smem;
+    float* Act = Ws + L.wtot;
+    const int tp = L.tp, ts = L.ts, nl = L.nl, sk = L.s[nl];
+    for (long long chain = blockIdx.x; chain < m; chain += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < L.wtot; i += blockDim.x) Ws[i] = 0.f;
+        for (int i = threadIdx.x; i < L.rows_tot * ts; i += blockDim.x) Act[i] = 0.f;
+        __syncthreads();
+        const float* wc = w + chain * L.d;
+        for (int l = 1; l <= nl; ++l) {
+            const int sin = L.s[l - 1], so = L.s[l], ws = L.ws[l];
+            for (int i = threadIdx.x; i < (sin + 1) * so; i += blockDim.x) {
+                int r = i / so, o = i - r * so;
+                float v = __ldg(wc + L.coff[l] + i);
+                if (r < sin) Ws[L.woff[l] + r * ws + o] = v; else Ws[L.boff[l] + o] = v;
+            }
+        }
+        for (long long begin = 0; begin < npts; begin += tp) {
+            const int count = (int)min((long long)tp, npts - begin);
+            __syncthreads();
+            for (int i = threadIdx.x; i < L.s[0] * tp; i += blockDim.x) {
+                int d = i / tp, p = i - d * tp;
+                Act[d * ts + p] = p < count ? __ldg(x + (begin + p) * L.s[0] + d) : 0.f;
+            }
+            __syncthreads();
+            const float* Ain = Act;
+            for (int l = 1; l <= nl; ++l) {
+                float* Z = Act + (size_t)L.arow[l] * ts;
+                float* Aout = Z + (size_t)L.ws[l] * ts;
+                gen_forward_layer(Ws + L.woff[l], Ws + L.boff[l], Ain, Z, Aout, L.s[l - 1], L.ws[l], tp, ts, L.act, l == nl);
+                __syncthreads();
+                Ain = Aout;
+            }
+            const float* Zl = Act + (size_t)L.arow[nl] * ts;
+            for (int i = threadIdx.x; i < count * sk; i += blockDim.x) {
+                int p = i / sk, k = i - p * sk;
+                out[(chain * npts + begin + p) * sk + k] = Zl[k * ts + p];
+            }
+        }
+    }
+}
+
+static int pick_tp(const Problem& p, GenLayout& L, bool with_grad) {
+    for (int tp : {32, 16, 8, 4}) {
+        L = make_layout(p, tp);
+        size_t need = with_grad ? gen_smem_bytes(L, p.rs) : sizeof(float) * ((size_t)L.wtot + (size_t)L.rows_tot * L.ts);
+        if ((long long)need <= (long long)p.max_smem_optin) return (int)need;
+    }
+    return -1;
+}
+
+int launch_logpost_generic(const Problem& p, const EvalArgs& a, const float* w, long long m, float* out_lp, float* out_grad,
+                           cudaStream_t st) {
+    OCBNN_REQUIRE(p.desc.layer_sizes[p.desc.n_layers] <= kMaxRt, OCBNN_EUNSUPPORTED, "output width %d > %d not supported",
+                  p.desc.layer_sizes[p.desc.n_layers], kMaxRt);
+    GenLayout L;
+    int sm = pick_tp(p, L, true);
+    OCBNN_REQUIRE(sm > 0, OCBNN_EUNSUPPORTED, "network with %d weights does not fit the shared-memory resident kernel", p.d);
+    OCBNN_CUDA(cudaFuncSetAttribute(k_logpost_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    int per_sm = (int)((long long)p.max_smem_optin / sm);
+    if (per_sm < 1) per_sm = 1;
+    long long grid = m < (long long)p.sm_count * per_sm * 4 ? m : (long long)p.sm_count * per_sm * 4;
+    k_logpost_generic<<<(unsigned)grid, kGenThreads, sm, st>>>(a, L, w, m, out_lp, out_grad);
+    OCBNN_LAUNCH_CHECK();
+    return OCBNN_OK;
+}
+
+int launch_forward_generic(const Problem& p, const float* w, long long m, const float* x, long long npts, float* out, cudaStream_t st) {
+    GenLayout L;
+    int sm = pick_tp(p, L, false);
+    OCBNN_REQUIRE(sm > 0, OCBNN_EUNSUPPORTED, "network with %d weights does not fit the shared-memory resident kernel", p.d);
+    OCBNN_CUDA(cudaFuncSetAttribute(k_forward_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    long long grid = m < (long long)p.sm_count * 4 ? m : (long long)p.sm_count * 4;
+    k_forward_generic<<<(unsigned)grid, kGenThreads, sm, st>>>(L, w, m, x, npts, out);
+    OCBNN_LAUNCH_CHECK();
+    return OCBNN_OK;
+}
+
+}  // namespace ocbnn

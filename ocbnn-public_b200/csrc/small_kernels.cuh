@@ -1,0 +1,290 @@
+// small_kernels.cuh — K1 (log-posterior + gradient), K2 (fused HMC trajectory + Metropolis-Hastings) and
+// K4 (fused SGLD steps) for the register-resident one-hidden-layer nets.  Included by one .cu per net shape.
+#pragma once
+#include "small_net.cuh"
+
+namespace ocbnn {
+
+constexpr int kSmallThreads = 128;
+
+__device__ __forceinline__ void load_pri(float2* pri_s, const EvalArgs& a, int d) {
+    for (int i = threadIdx.x; i < d; i += blockDim.x) pri_s[i] = a.pri[i];
+}
+
+// ---- K1 ------------------------------------------------------------------------------------------------
+template <class N, int G>
+__global__ void __launch_bounds__(kSmallThreads)
+k_logpost_small(EvalArgs a, const float* __restrict__ w, long long m, float* __restrict__ out_lp, float* __restrict__ out_grad,
+                int tile_cap) {
+    extern __shared__ __align__(16) float smem[];
+    float2* pri_s = reinterpret_cast<float2*>(smem);
+    float* tab = smem + 2 * ((N::D + 1) & ~1);
+    EvalCtx c = make_ctx(a, tab, pri_s, tile_cap);
+    load_pri(pri_s, a, N::D);
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    const bool active = gid < m;
+    const long long chain = active ? gid : m - 1;
+    float wv[N::D], g[N::D];
+#pragma unroll
+    for (int i = 0; i < N::D; ++i) wv[i] = __ldg(w + chain * N::D + i);
+    float lp;
+    evaluate<N, G>(a, c, /*restage=*/true, wv, g, lp, lane);
+    if (active && lane == 0) {
+        if (out_lp) out_lp[chain] = lp;
+        if (out_grad) {
+#pragma unroll
+            for (int i = 0; i < N::D; ++i) out_grad[chain * N::D + i] = g[i];
+        }
+    }
+}
+
+// ---- K2 ------------------------------------------------------------------------------------------------
+// One HMC iteration (bnn/inference.py:39-78):  p ~ injected;  U0,K0;  p -= eps/2 dU;  L x { q += eps p ; [l<L] p -= eps dU };
+// p -= eps/2 dU;  U1,K1;  accept iff u < exp(U0 - U1 + K0 - K1)  (fp32 exp, float64 compare, strict <).
+// dU = -grad log posterior, so "p -= c*dU" is "p += c*g" with identical rounding (fl(c*g) then one add).
+// The value+gradient at q_L is reused as U0/grad of the next iteration (the reference recomputes both).
+template <class N, int G>
+__global__ void __launch_bounds__(kSmallThreads)
+k_hmc_small(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, const double* __restrict__ u, long long m, int n_it,
+            float eps, float eps_half, int L, int restore, uint8_t* __restrict__ out_acc, float* __restrict__ out_h,
+            int* __restrict__ out_flags, float* __restrict__ out_samples, int thin, int tile_cap) {
+    extern __shared__ __align__(16) float smem[];
+    float2* pri_s = reinterpret_cast<float2*>(smem);
+    float* tab = smem + 2 * ((N::D + 1) & ~1);
+    EvalCtx c = make_ctx(a, tab, pri_s, tile_cap);
+    load_pri(pri_s, a, N::D);
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    const bool active = gid < m;
+    const long long chain = active ? gid : m - 1;
+    const bool writer = active && lane == 0;
+
+    float q[N::D], p[N::D], g[N::D];
+#pragma unroll
+    for (int i = 0; i < N::D; ++i) q[i] = q_io[chain * N::D + i];
+    float lp;
+    evaluate<N, G>(a, c, /*restage=*/true, q, g, lp, lane);   // stages the (fixed) point set once
+    int nan_flag = 0;
+    bool need_eval = false;
+
+    for (int it = 0; it < n_it; ++it) {
+        if (__any_sync(0xffffffffu, need_eval)) evaluate<N, G>(a, c, false, q, g, lp, lane);
+        need_eval = false;
+        const float* pin = p0 + ((long long)it * m + chain) * N::D;
+        double ksum = 0.0;
+#pragma unroll
+        for (int i = 0; i < N::D; ++i) {
+            p[i] = __ldg(pin + i);
+            ksum += (double)(p[i] * p[i]);
+        }
+        const float U0 = -lp;
+        const float K0 = 0.5f * (float)ksum;
+        if (restore && writer) {   // keep q0 for a possible restore (scratch: this iteration's slot of out_samples is not used yet)
+#pragma unroll
+            for (int i = 0; i < N::D; ++i) q_io[chain * N::D + i] = q[i];
+        }
+#pragma unroll
+        for (int i = 0; i < N::D; ++i) p[i] = __fadd_rn(p[i], __fmul_rn(eps_half, g[i]));
+        for (int l = 1; l <= L; ++l) {
+#pragma unroll
+            for (int i = 0; i < N::D; ++i) q[i] = __fadd_rn(q[i], __fmul_rn(eps, p[i]));
+            evaluate<N, G>(a, c, false, q, g, lp, lane);
+            const float e = (l < L) ? eps : eps_half;
+#pragma unroll
+            for (int i = 0; i < N::D; ++i) p[i] = __fadd_rn(p[i], __fmul_rn(e, g[i]));
+        }
+        bool isn = false;
+        ksum = 0.0;
+#pragma unroll
+        for (int i = 0; i < N::D; ++i) {
+            isn |= isnan(q[i]);
+            ksum += (double)(p[i] * p[i]);
+        }
+        nan_flag |= isn ? 1 : 0;
+        const float U1 = -lp;
+        const float K1 = 0.5f * (float)ksum;
+        const float dH = __fsub_rn(__fadd_rn(__fsub_rn(U0, U1), K0), K1);
+        const double alpha = (double)expf(dH);
+        const double ui = __ldg(u + (long long)it * m + chain);
+        const bool acc = ui < alpha;
+        if (writer) {
+            if (out_acc) out_acc[(long long)it * m + chain] = acc ? 1 : 0;
+            if (out_h) reinterpret_cast<float4*>(out_h)[(long long)it * m + chain] = make_float4(U0, K0, U1, K1);
+        }
+        if (restore && !acc) {
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < N::D; ++i) q[i] = q_io[chain * N::D + i];
+            need_eval = true;
+        }
+        if (out_samples && thin > 0 && ((it + 1) % thin == 0) && writer) {
+            float* dst = out_samples + ((long long)((it + 1) / thin - 1) * m + chain) * N::D;
+#pragma unroll
+            for (int i = 0; i < N::D; ++i) dst[i] = q[i];
+        }
+    }
+    if (writer) {
+#pragma unroll
+        for (int i = 0; i < N::D; ++i) q_io[chain * N::D + i] = q[i];
+        if (out_flags) out_flags[chain] = nan_flag;
+    }
+}
+
+// ---- K4 ------------------------------------------------------------------------------------------------
+// SGLD (bnn/inference.py:304-340): upd = (grad log prior + grad log lik) * (eps_t/2) + noise_t ; w += upd.
+template <class N, int G>
+__global__ void __launch_bounds__(kSmallThreads)
+k_sgld_small(EvalArgs a, float* __restrict__ w_io, const float* __restrict__ noise, const float* __restrict__ half_eps,
+             const int* __restrict__ offsets, long long m, int t_steps, float* __restrict__ out_samples, int thin, int tile_cap) {
+    extern __shared__ __align__(16) float smem[];
+    float2* pri_s = reinterpret_cast<float2*>(smem);
+    float* tab = smem + 2 * ((N::D + 1) & ~1);
+    load_pri(pri_s, a, N::D);
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    const bool active = gid < m;
+    const long long chain = active ? gid : m - 1;
+    const bool writer = active && lane == 0;
+    float w[N::D], g[N::D];
+#pragma unroll
+    for (int i = 0; i < N::D; ++i) w[i] = w_io[chain * N::D + i];
+    const bool batched = a.batch_stride > 1;
+    EvalCtx c = make_ctx(a, tab, pri_s, tile_cap);
+    for (int t = 0; t < t_steps; ++t) {
+        if (batched) {
+            a.batch_offset = offsets[t];
+            c = make_ctx(a, tab, pri_s, tile_cap);
+        }
+        float lp;
+        evaluate<N, G>(a, c, /*restage=*/batched || t == 0, w, g, lp, lane);
+        const float he = half_eps[t];
+        const float* nz = noise + ((long long)t * m + chain) * N::D;
+#pragma unroll
+        for (int i = 0; i < N::D; ++i) {
+            float upd = __fadd_rn(__fmul_rn(g[i], he), __ldg(nz + i));
+            w[i] = __fadd_rn(w[i], upd);
+        }
+        if (out_samples && thin > 0 && ((t + 1) % thin == 0) && writer) {
+            float* dst = out_samples + ((long long)((t + 1) / thin - 1) * m + chain) * N::D;
+#pragma unroll
+            for (int i = 0; i < N::D; ++i) dst[i] = w[i];
+        }
+    }
+    if (writer) {
+#pragma unroll
+        for (int i = 0; i < N::D; ++i) w_io[chain * N::D + i] = w[i];
+    }
+}
+
+// ---- forward (predict) -----------------------------------------------------------------------------------
+template <class N>
+__global__ void __launch_bounds__(kSmallThreads)
+k_forward_small(const float* __restrict__ w, long long m, const float* __restrict__ x, long long npts, float* __restrict__ out) {
+    const long long chain = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= m) return;
+    float wv[N::D];
+#pragma unroll
+    for (int i = 0; i < N::D; ++i) wv[i] = __ldg(w + chain * N::D + i);
+    for (long long j = 0; j < npts; ++j) {
+        float xv[N::S0], f[N::SK];
+#pragma unroll
+        for (int d = 0; d < N::S0; ++d) xv[d] = __ldg(x + j * N::S0 + d);
+        point_forward<N>(wv, xv, f);
+#pragma unroll
+        for (int k = 0; k < N::SK; ++k) out[(chain * npts + j) * N::SK + k] = f[k];
+    }
+}
+
+// ---- host-side launchers for one net shape ---------------------------------------------------------------
+template <class N>
+struct SmallLaunch {
+    static size_t smem_bytes(const Problem& p, int npts, int& tile_cap) {
+        size_t fixed = sizeof(float) * 2 * ((N::D + 1) & ~1);
+        int cap = (int)((kMaxSmemTable - fixed) / (sizeof(float) * p.rs));
+        tile_cap = npts < cap ? (npts > 0 ? npts : 1) : cap;
+        return fixed + sizeof(float) * (size_t)tile_cap * p.rs;
+    }
+    static int npts(const EvalArgs& a) {
+        return (a.with_data ? batch_count(a.n_train, 0, a.batch_stride) : 0) + a.n_cpoints;   // largest batch: offset 0
+    }
+
+    template <int G>
+    static int logpost(const Problem& p, const EvalArgs& a, const float* w, long long m, float* lp, float* grad, cudaStream_t st) {
+        int tile_cap;
+        size_t sm = smem_bytes(p, npts(a), tile_cap);
+        auto k = k_logpost_small<N, G>;
+        OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        long long blocks = (m * G + kSmallThreads - 1) / kSmallThreads;
+        k<<<(unsigned)blocks, kSmallThreads, sm, st>>>(a, w, m, lp, grad, tile_cap);
+        OCBNN_LAUNCH_CHECK();
+        return OCBNN_OK;
+    }
+    template <int G>
+    static int hmc(const Problem& p, const EvalArgs& a, float* q, const float* p0, const double* u, long long m, int n_it, float eps,
+                   float eps_half, int L, int restore, uint8_t* acc, float* h, int* flags, float* samples, int thin, cudaStream_t st) {
+        int tile_cap;
+        size_t sm = smem_bytes(p, npts(a), tile_cap);
+        auto k = k_hmc_small<N, G>;
+        OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        long long blocks = (m * G + kSmallThreads - 1) / kSmallThreads;
+        k<<<(unsigned)blocks, kSmallThreads, sm, st>>>(a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin,
+                                                       tile_cap);
+        OCBNN_LAUNCH_CHECK();
+        return OCBNN_OK;
+    }
+    template <int G>
+    static int sgld(const Problem& p, const EvalArgs& a, float* w, const float* noise, const float* he, const int* offs, long long m,
+                    int t_steps, float* samples, int thin, cudaStream_t st) {
+        int tile_cap;
+        size_t sm = smem_bytes(p, npts(a), tile_cap);
+        auto k = k_sgld_small<N, G>;
+        OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        long long blocks = (m * G + kSmallThreads - 1) / kSmallThreads;
+        k<<<(unsigned)blocks, kSmallThreads, sm, st>>>(a, w, noise, he, offs, m, t_steps, samples, thin, tile_cap);
+        OCBNN_LAUNCH_CHECK();
+        return OCBNN_OK;
+    }
+    static int forward(const float* w, long long m, const float* x, long long np, float* out, cudaStream_t st) {
+        long long blocks = (m + kSmallThreads - 1) / kSmallThreads;
+        k_forward_small<N><<<(unsigned)blocks, kSmallThreads, 0, st>>>(w, m, x, np, out);
+        OCBNN_LAUNCH_CHECK();
+        return OCBNN_OK;
+    }
+};
+
+}  // namespace ocbnn
+
+#define OCBNN_LANE_CASES(EXPR)                                                                   \
+    switch (lanes) {                                                                             \
+        case 1: { constexpr int G = 1; return EXPR; }                                            \
+        case 2: { constexpr int G = 2; return EXPR; }                                            \
+        case 4: { constexpr int G = 4; return EXPR; }                                            \
+        case 8: { constexpr int G = 8; return EXPR; }                                            \
+        case 16: { constexpr int G = 16; return EXPR; }                                          \
+        case 32: { constexpr int G = 32; return EXPR; }                                          \
+        default: set_error("lanes must be 1,2,4,8,16 or 32 (got %d)", lanes); return OCBNN_EINVAL; \
+    }
+
+// Defines the non-template entry points of one net shape (collected in the table of small_dispatch.cu).
+#define OCBNN_DEFINE_SMALL_NET(NAME, S0, H, SK, ACT)                                                                          \
+    namespace ocbnn {                                                                                                         \
+    using NAME##_N = Net1<S0, H, SK, ACT>;                                                                                    \
+    int NAME##_logpost(const Problem& p, const EvalArgs& a, const float* w, long long m, float* lp, float* grad, int lanes,    \
+                       cudaStream_t st) {                                                                                     \
+        OCBNN_LANE_CASES((SmallLaunch<NAME##_N>::template logpost<G>(p, a, w, m, lp, grad, st)))                             \
+    }                                                                                                                         \
+    int NAME##_hmc(const Problem& p, const EvalArgs& a, float* q, const float* p0, const double* u, long long m, int n_it,     \
+                   float eps, float eps_half, int L, int restore, uint8_t* acc, float* h, int* flags, float* samples,          \
+                   int thin, int lanes, cudaStream_t st) {                                                                    \
+        OCBNN_LANE_CASES((SmallLaunch<NAME##_N>::template hmc<G>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h,  \
+                                                                  flags, samples, thin, st)))                                 \
+    }                                                                                                                         \
+    int NAME##_sgld(const Problem& p, const EvalArgs& a, float* w, const float* noise, const float* he, const int* offs,       \
+                    long long m, int t_steps, float* samples, int thin, int lanes, cudaStream_t st) {                         \
+        OCBNN_LANE_CASES((SmallLaunch<NAME##_N>::template sgld<G>(p, a, w, noise, he, offs, m, t_steps, samples, thin, st)))  \
+    }                                                                                                                         \
+    int NAME##_forward(const float* w, long long m, const float* x, long long np, float* out, cudaStream_t st) {              \
+        return SmallLaunch<NAME##_N>::forward(w, m, x, np, out, st);                                                          \
+    }                                                                                                                         \
+    }

@@ -1,0 +1,3 @@
+// Instantiation of the register-resident kernels for the [1,10,1] rbf net (repro toy shape).
+#include "small_kernels.cuh"
+OCBNN_DEFINE_SMALL_NET(net_reg1_10_1, 1, 10, 1, OCBNN_ACT_RBF)

@@ -1,0 +1,63 @@
+"""
+Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink on the GPU box, gloo in the CPU
+tests).  HMC/SGLD chains are independent (no data-path collective, only a final gather of the collected
+samples); SVGD all-gathers particles and gradients once per epoch and all-reduces the 2048-bin select
+histograms of the exact median; BBB all-reduces its (D,2) gradient.  With no process group everything is a
+no-op on one device.
+"""
+
+import torch
+import torch.distributed as dist
+
+
+def active():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def rank():
+    return dist.get_rank() if active() else 0
+
+
+def world():
+    return dist.get_world_size() if active() else 1
+
+
+def shard(n, r=None, w=None):
+    """Contiguous share [lo, hi) of n units for rank r of w (first n % w ranks get one extra)."""
+    r = rank() if r is None else r
+    w = world() if w is None else w
+    base, rem = divmod(n, w)
+    lo = r * base + min(r, rem)
+    return lo, lo + base + (1 if r < rem else 0)
+
+
+def all_sum_(t):
+    if active():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def all_sum(t):
+    t = t.clone()
+    all_sum_(t)
+    return t.item()
+
+
+def gather_cat(t, dim=0):
+    """Concatenate the ranks' shards of `t` along `dim` (shards may differ by one row)."""
+    if not active():
+        return t
+    w = world()
+    t = t.movedim(dim, 0).contiguous()
+    sizes = torch.zeros(w, dtype=torch.int64, device=t.device)
+    sizes[rank()] = t.shape[0]
+    dist.all_reduce(sizes)
+    sizes = [int(s) for s in sizes.cpu()]
+    mx = max(sizes)
+    if t.shape[0] < mx:
+        pad = torch.zeros((mx - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        t = torch.cat([t, pad], 0)
+    out = torch.empty((w * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t) if t.is_cuda else dist.all_gather(list(out.view((w, mx) + tuple(t.shape[1:])).unbind(0)), t)
+    parts = [out[r * mx:r * mx + sizes[r]] for r in range(w)]
+    return torch.cat(parts, 0).movedim(0, dim).contiguous()

@@ -1,0 +1,286 @@
+"""
+ctypes binding of libocbnn_b200.so (the C-ABI declared in include/ocbnn_b200.h).
+
+PyTorch is used for device memory, streams and torch.distributed only; every
+number on the hot path is produced by the hand-written sm_100a kernels behind
+this boundary.  There is NO CPU fallback: if the library is missing, or there is
+no B200, every compute call raises EngineError.
+"""
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libocbnn_b200.so")
+
+OCBNN_ABI_VERSION = 1
+OCBNN_MAX_LAYERS = 8
+ACT_IDENTITY, ACT_RBF, ACT_RELU = 0, 1, 2
+HEAD_LIK_GAUSS, HEAD_NEG_EXP, HEAD_POS_GAUSS, HEAD_DIRICHLET, HEAD_LIK_SOFTMAX, HEAD_LIK_BERNOULLI = range(6)
+
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int32)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class ocbnn_desc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("n_layers", C.c_int32),
+        ("layer_sizes", C.c_int32 * (OCBNN_MAX_LAYERS + 1)),
+        ("activation", C.c_int32),
+        ("lik_head", C.c_int32),
+        ("lik_scale", C.c_float),
+        ("lik_const", C.c_double),
+        ("prior_mean", C.c_float),
+        ("prior_std", C.c_float),
+        ("prior_mean_vec", _fp),
+        ("prior_std_vec", _fp),
+        ("prior_const", C.c_double),
+        ("n_train", C.c_int64),
+        ("x_train", _fp),
+        ("y_train", _fp),
+        ("y_width", C.c_int32),
+        ("n_cpoints", C.c_int32),
+        ("cx", _fp),
+        ("ckind", _ip),
+        ("cweight", _fp),
+        ("cparam_stride", C.c_int32),
+        ("cparam", _fp),
+        ("neg_tau0", C.c_float),
+        ("neg_tau1", C.c_float),
+        ("pos_inv_var", C.c_float),
+    ]
+
+
+_lib = None
+
+_SIGS = {
+    "ocbnn_last_error": (C.c_char_p, []),
+    "ocbnn_abi_version": (C.c_int, []),
+    "ocbnn_launch_count": (C.c_int64, []),
+    "ocbnn_problem_create": (C.c_int, [C.POINTER(ocbnn_desc), C.POINTER(C.c_void_p)]),
+    "ocbnn_problem_destroy": (C.c_int, [C.c_void_p]),
+    "ocbnn_problem_nweights": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "ocbnn_logpost_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_int32, C.c_void_p]),
+    "ocbnn_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ocbnn_hmc_iterate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int32,
+                                    C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                    C.c_void_p]),
+    "ocbnn_sgld_iterate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _fp, _ip, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "ocbnn_svgd_hist_pass": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "ocbnn_svgd_select_update": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ocbnn_svgd_bandwidth": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ocbnn_svgd_phi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                 C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ocbnn_svgd_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
+    "ocbnn_adagrad_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p]),
+    "ocbnn_bbb_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ocbnn_bbb_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ocbnn_hmc_iterate_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double,
+                                         C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
+}
+
+
+def lib():
+    """Load the CUDA extension; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(f"{LIB_PATH} is missing: build it with `python ocbnn-public_b200/build.py` "
+                              "(the engine has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        if L.ocbnn_abi_version() != OCBNN_ABI_VERSION:
+            raise EngineError("libocbnn_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return list(_SIGS)
+
+
+def check(rc):
+    if rc != 0:
+        raise EngineError(f"ocbnn engine error {rc}: {lib().ocbnn_last_error().decode()}")
+
+
+def launch_count():
+    return int(lib().ocbnn_launch_count())
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise EngineError("no CUDA device visible: the OC-BNN B200 engine has no CPU fallback")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t, name):
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+        raise EngineError(f"{name} must be a contiguous float32 CUDA tensor")
+    return t
+
+
+class DeviceProblem:
+    """Device-resident compiled problem (opaque ocbnn_problem handle)."""
+
+    def __init__(self, cp):
+        require_cuda()
+        L = lib()
+        self.cp = cp
+        d = ocbnn_desc()
+        d.abi_version = OCBNN_ABI_VERSION
+        d.n_layers = len(cp.layer_sizes) - 1
+        for i, s in enumerate(cp.layer_sizes):
+            d.layer_sizes[i] = int(s)
+        d.activation, d.lik_head = cp.activation, cp.lik_head
+        d.lik_scale, d.lik_const = cp.lik_scale, cp.lik_const
+        d.prior_mean, d.prior_std, d.prior_const = cp.prior_mean, cp.prior_std, cp.prior_const
+        keep = []
+
+        def fptr(a):
+            if a is None or a.size == 0:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            keep.append(a)
+            return a.ctypes.data_as(_fp)
+        d.prior_mean_vec, d.prior_std_vec = fptr(cp.prior_mean_vec), fptr(cp.prior_std_vec)
+        d.n_train = cp.X.shape[0]
+        d.x_train, d.y_train, d.y_width = fptr(cp.X), fptr(cp.Y), cp.Y.shape[1] if cp.Y.ndim == 2 else 1
+        d.n_cpoints = cp.cx.shape[0]
+        d.cx, d.cweight, d.cparam = fptr(cp.cx), fptr(cp.cweight), fptr(cp.cparam)
+        ck = np.ascontiguousarray(cp.ckind, dtype=np.int32)
+        keep.append(ck)
+        d.ckind = ck.ctypes.data_as(_ip) if ck.size else None
+        d.cparam_stride = cp.cparam.shape[1] if cp.cparam.ndim == 2 and cp.cparam.size else 0
+        d.neg_tau0, d.neg_tau1, d.pos_inv_var = cp.tau[0], cp.tau[1], cp.pos_inv_var
+        h = C.c_void_p()
+        check(L.ocbnn_problem_create(C.byref(d), C.byref(h)))
+        self._h = h
+        self.D = cp.nweights
+        self.sK = cp.layer_sizes[-1]
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ocbnn_problem_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- K1 -------------------------------------------------------------------------------------------
+    def logpost_grad(self, W, batch=(0, 1), with_data=True, want_lp=True, want_grad=True, lanes=0, out_lp=None, out_grad=None):
+        W = _f32(W, "W")
+        M = W.shape[0]
+        lp = (out_lp if out_lp is not None else torch.empty(M, device=W.device)) if want_lp else None
+        g = (out_grad if out_grad is not None else torch.empty_like(W)) if want_grad else None
+        check(lib().ocbnn_logpost_grad(self._h, _ptr(W), M, int(batch[0]), int(batch[1]), int(bool(with_data)), _ptr(lp), _ptr(g),
+                                       int(lanes), _stream()))
+        return lp, g
+
+    def forward(self, W, X):
+        W, X = _f32(W, "W"), _f32(X, "X")
+        out = torch.empty(W.shape[0], X.shape[0], self.sK, device=W.device)
+        check(lib().ocbnn_forward(self._h, _ptr(W), W.shape[0], _ptr(X), X.shape[0], _ptr(out), _stream()))
+        return out
+
+    # ---- K2 -------------------------------------------------------------------------------------------
+    def hmc_iterate(self, q, p0, u, eps, L, with_data=True, restore_on_reject=False, want_h=False, want_flags=True, samples=None,
+                    thin=0, lanes=0):
+        q, p0 = _f32(q, "q"), _f32(p0, "p0")
+        if u.dtype != torch.float64 or not u.is_cuda or not u.is_contiguous():
+            raise EngineError("u must be a contiguous float64 CUDA tensor")
+        n_it, M = p0.shape[0], q.shape[0]
+        acc = torch.empty(n_it, M, dtype=torch.uint8, device=q.device)
+        H = torch.empty(n_it, M, 4, device=q.device) if want_h else None
+        flags = torch.zeros(M, dtype=torch.int32, device=q.device) if want_flags else None
+        check(lib().ocbnn_hmc_iterate(self._h, _ptr(q), _ptr(p0), _ptr(u), M, n_it, float(eps), int(L), int(bool(with_data)),
+                                      int(bool(restore_on_reject)), _ptr(acc), _ptr(H), _ptr(flags), _ptr(samples), int(thin),
+                                      int(lanes), _stream()))
+        return acc, H, flags
+
+    # ---- K4 -------------------------------------------------------------------------------------------
+    def sgld_iterate(self, w, noise, half_eps, batch_offsets, batch_stride, with_data=True, samples=None, thin=0, lanes=0):
+        w, noise = _f32(w, "w"), _f32(noise, "noise")
+        T = noise.shape[0]
+        he = np.ascontiguousarray(half_eps, dtype=np.float32)
+        bo = np.ascontiguousarray(batch_offsets if batch_offsets is not None else np.zeros(T), dtype=np.int32)
+        check(lib().ocbnn_sgld_iterate(self._h, _ptr(w), _ptr(noise), he.ctypes.data_as(_fp), bo.ctypes.data_as(_ip),
+                                       int(batch_stride), w.shape[0], T, int(bool(with_data)), _ptr(samples), int(thin), int(lanes),
+                                       _stream()))
+
+
+# ---- K3 (problem independent) ------------------------------------------------------------------------------
+
+def svgd_workspace(n, d, device):
+    nbytes = int(lib().ocbnn_svgd_workspace_bytes(n, d))
+    return torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=device)
+
+
+def svgd_bandwidth(X, workspace, out_h=None):
+    X = _f32(X, "X")
+    h = out_h if out_h is not None else torch.empty(1, device=X.device)
+    check(lib().ocbnn_svgd_bandwidth(_ptr(X), X.shape[0], X.shape[1], _ptr(h), _ptr(workspace), workspace.numel() * 8, _stream()))
+    return h
+
+
+def svgd_hist_pass(X, row_start, row_step, n_rows, pass_, hist, state):
+    check(lib().ocbnn_svgd_hist_pass(_ptr(X), X.shape[0], X.shape[1], int(row_start), int(row_step), int(n_rows), int(pass_), _ptr(hist),
+                                     _ptr(state), _stream()))
+
+
+def svgd_select_update(pass_, hist, state, n, out_h):
+    check(lib().ocbnn_svgd_select_update(int(pass_), _ptr(hist), _ptr(state), int(n), _ptr(out_h), _stream()))
+
+
+def svgd_phi(X, G, h, row_begin, n_rows, workspace, use_tensor=-1, out=None):
+    X, G = _f32(X, "X"), _f32(G, "G")
+    phi = out if out is not None else torch.empty(n_rows, X.shape[1], device=X.device)
+    check(lib().ocbnn_svgd_phi(_ptr(X), _ptr(G), X.shape[0], X.shape[1], int(row_begin), int(n_rows), _ptr(h), _ptr(phi), int(use_tensor),
+                               _ptr(workspace), workspace.numel() * 8 if workspace is not None else 0, _stream()))
+    return phi
+
+
+def adagrad_step(x, acc, direction, lr, grad_sign):
+    check(lib().ocbnn_adagrad_step(_ptr(_f32(x, "x")), _ptr(_f32(acc, "acc")), _ptr(_f32(direction, "dir")), x.numel(), float(lr),
+                                   float(grad_sign), _stream()))
+
+
+def bbb_sample(q_params, eps):
+    w = torch.empty_like(eps)
+    check(lib().ocbnn_bbb_sample(_ptr(_f32(q_params, "q_params")), _ptr(_f32(eps, "eps")), eps.shape[0], eps.shape[1], _ptr(w), _stream()))
+    return w
+
+
+def bbb_reduce(q_params, eps, lp, grad, k_total, add_entropy=True):
+    D = eps.shape[1]
+    gq = torch.empty(D, 2, device=eps.device)
+    elbo = torch.empty(1, device=eps.device)
+    colstat = torch.empty(D, device=eps.device)
+    check(lib().ocbnn_bbb_reduce(_ptr(q_params), _ptr(eps), _ptr(_f32(lp, "lp")), _ptr(_f32(grad, "grad")), eps.shape[0], D, int(k_total),
+                                 int(bool(add_entropy)), _ptr(gq), _ptr(elbo), _ptr(colstat), _stream()))
+    return gq, elbo

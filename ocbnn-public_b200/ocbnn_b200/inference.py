@@ -1,0 +1,329 @@
+"""
+Inference mixins with the interface of the reference (bnn/inference.py:5-10): each provides
+`infer(verbose=True, with_data=True)`, which appends `(samples, name)` to `self.all_bayes_samples`
+(`samples`: float32 (infer_nsamples, nweights) on the host) and saves `history/{uid}_{sampler}{id}.pt`.
+
+The bodies are drivers only: random numbers are drawn by PyTorch / numpy (host generators in the reference's
+draw order by default, so that a seeded run consumes the same streams as the reference), everything else runs
+in the CUDA engine:
+  HMC   K2  fused trajectory + Metropolis-Hastings        (replaces inference.py:39-78)
+  SGLD  K4  fused Langevin steps                           (replaces inference.py:304-340)
+  SVGD  K1 + K3a/b/c  gradients, bandwidth, phi, Adagrad  (replaces inference.py:208-281)
+  BBB   K5 + K1  reparameterised ELBO gradient + Adagrad   (replaces inference.py:132-186)
+Chains / particles / Monte-Carlo samples shard over the ranks of torch.distributed when it is initialised
+(one process per GPU); SVGD all-gathers particles and gradients each epoch, BBB all-reduces its (D,2) gradient.
+"""
+
+import logging
+import math
+import time
+
+import numpy as np
+import torch
+from torch.distributions.normal import Normal
+
+from . import dist as D
+from . import engine as E
+from .compiler import batch_spec
+
+
+def _name(self, sampler):
+    return f"{sampler}_{'ocbnn' if self.use_ocbnn else 'baseline'}"
+
+
+def _batch_for(self, t):
+    """(offset, stride) of torch.arange(t % nbatches, N_train, nbatches) (inference.py:180,276,334)."""
+    nb = int(getattr(self, "nbatches", 0) or 0)
+    if nb <= 1:
+        return (0, 1)
+    return (t % nb, nb)
+
+
+def _raise_nan(self):
+    logging.error(f"[{self.uid}] NaNs encountered in current set of weights.")
+    raise Exception
+
+
+class HMCMixin:
+    """Hamiltonian Monte Carlo (inference.py:24-124), M chains at once."""
+
+    def _hmc_chunk(self):
+        # iterations per kernel launch: bounded by the momentum buffer (<= ~256 MB)
+        M = max(1, int(getattr(self, "nchains", 1) or 1))
+        return max(1, min(512, (64 << 20) // max(1, M * self.nweights)))
+
+    def _hmc_draw(self, n_it, M, dev):
+        """Momenta (n_it,M,D) ~ N(0,1) and uniforms (n_it,M) float64.  rng='host' reproduces the reference's streams:
+        one torch Normal(0,1).sample([D]) and one numpy uniform per iteration (inference.py:45,74)."""
+        Dw = self.nweights
+        if getattr(self, "rng", "host") == "device":
+            p0 = torch.randn(n_it, M, Dw, device=dev)
+            u = torch.rand(n_it, M, device=dev, dtype=torch.float64)
+            return p0, u
+        p0 = torch.empty(n_it, M, Dw)
+        u = np.empty((n_it, M))
+        for it in range(n_it):
+            for c in range(M):
+                p0[it, c] = Normal(0, 1).sample(torch.Size([Dw]))
+                u[it, c] = np.random.uniform()
+        return p0.to(dev), torch.from_numpy(u).to(dev)
+
+    def _hmc_state(self, M, dev):
+        """Chain 0 continues from self.weights (like the reference); further chains continue from the previous
+        infer() when available, else start from N(0, sigma_w)."""
+        prev = getattr(self, "chain_states", None)
+        q = torch.empty(M, self.nweights)
+        q[0] = self.weights.data
+        for c in range(1, M):
+            q[c] = prev[c] if prev is not None and prev.shape[0] > c else Normal(0, self.sigma_w).sample(torch.Size([self.nweights]))
+        return q.to(dev).contiguous()
+
+    def hmc_run(self, q, n_it, with_data, collect_every=0):
+        """n_it iterations from state q (M,D, device; updated in place).  Returns (accepts (M,), samples or None)."""
+        prob = self.engine_problem()
+        M = q.shape[0]
+        acc_total = torch.zeros(M, dtype=torch.int64, device=q.device)
+        nsamp = n_it // collect_every if collect_every else 0
+        samples = torch.empty(nsamp, M, self.nweights, device=q.device) if nsamp else None
+        chunk = self._hmc_chunk()
+        if collect_every:
+            chunk = max(collect_every, chunk - chunk % collect_every)
+        done = 0
+        while done < n_it:
+            n = min(chunk, n_it - done)
+            p0, u = self._hmc_draw(n, M, q.device)
+            sl = samples[done // collect_every:(done + n) // collect_every] if collect_every else None
+            acc, _, flags = prob.hmc_iterate(q, p0, u, self.hmc_epsilon, self.hmc_l, with_data,
+                                             bool(getattr(self, "restore_on_reject", False)), samples=sl, thin=collect_every,
+                                             lanes=int(getattr(self, "lanes", 0) or 0))
+            acc_total += acc.sum(dim=0)
+            if int(flags.max()) != 0:
+                _raise_nan(self)
+            done += n
+        return acc_total, samples
+
+    def infer(self, verbose=True, with_data=True):
+        """Burn-in, then collect every hmc_ninterval-th state (inference.py:80-124).  With nchains = M > 1 every
+        collection round yields M samples (round-major order); the first infer_nsamples are kept."""
+        infer_id = len(self.all_bayes_samples) + 1
+        logging.info(f"[{self.uid}] Posterior Sample #{infer_id}: Beginning HMC inference...")
+        start_time = time.time()
+        dev = self._device()
+        M_total = max(1, int(getattr(self, "nchains", 1) or 1))
+        lo, hi = D.shard(M_total)
+        q = self._hmc_state(M_total, dev)[lo:hi].contiguous()
+        M = hi - lo
+
+        acc, _ = self.hmc_run(q, self.hmc_nburnin, with_data)
+        self.accepts = int(D.all_sum(acc.sum()))
+        self.rejects = self.hmc_nburnin * M_total - self.accepts
+        if self.hmc_nburnin:
+            logging.info(f"  All {self.hmc_nburnin} burn-in steps completed. Acceptance rate is "
+                         f"{100 * (self.accepts / (self.hmc_nburnin * M_total)):.2f}%.")
+        logging.info("  Collecting samples now...")
+        rounds = -(-self.infer_nsamples // M_total)
+        n_it = rounds * self.hmc_ninterval
+        acc, samples = self.hmc_run(q, n_it, with_data, collect_every=self.hmc_ninterval)
+        self.accepts = int(D.all_sum(acc.sum()))
+        self.rejects = n_it * M_total - self.accepts
+        end_time = time.time()
+        if self.infer_nsamples:
+            logging.info(f"  All {self.infer_nsamples} samples collected. Acceptance rate is "
+                         f"{100 * (self.accepts / max(1, n_it * M_total)):.2f}%. Time took: {(end_time - start_time):.0f} seconds.")
+        samples = D.gather_cat(samples, dim=1) if samples is not None else torch.empty(0, M_total, self.nweights, device=dev)
+        samples = samples.reshape(-1, self.nweights)[:self.infer_nsamples].cpu()
+        states = D.gather_cat(q, dim=0).cpu()
+        self.chain_states = states
+        self.weights = states[0].clone().requires_grad_(True)
+        if D.rank() == 0:
+            torch.save(samples, f"history/{self.uid}_hmc{infer_id}.pt")
+        self.all_bayes_samples.append((samples, _name(self, "hmc")))
+        logging.info(f"[{self.uid}] Posterior Sample #{infer_id}: HMC inference completed. Samples saved as `history/{self.uid}_hmc{infer_id}.pt`.")
+
+
+class SGLDMixin:
+    """Stochastic Gradient Langevin Dynamics (inference.py:295-375), M chains at once."""
+
+    def get_stepsize(self, t):
+        """epsilon_t = a (b + t)^(-gamma) in Python float64 (inference.py:300-302)."""
+        return self.sgld_epa * ((self.sgld_epb + t) ** (-1 * self.sgld_epgamma))
+
+    def _sgld_noise(self, ts, M, dev):
+        Dw = self.nweights
+        if getattr(self, "rng", "host") == "device":
+            sd = torch.tensor([self.get_stepsize(t) ** 0.5 for t in ts], device=dev, dtype=torch.float32)
+            return torch.randn(len(ts), M, Dw, device=dev) * sd[:, None, None]
+        z = torch.empty(len(ts), M, Dw)
+        for i, t in enumerate(ts):
+            eps = self.get_stepsize(t)
+            for c in range(M):
+                z[i, c] = Normal(torch.zeros(Dw), (eps ** 0.5) * torch.ones(Dw)).sample()     # inference.py:339
+        return z.to(dev)
+
+    def sgld_run(self, w, t_first, n_steps, with_data, collect_every=0):
+        prob = self.engine_problem()
+        M = w.shape[0]
+        nsamp = n_steps // collect_every if collect_every else 0
+        samples = torch.empty(nsamp, M, self.nweights, device=w.device) if nsamp else None
+        chunk = max(1, min(1024, (64 << 20) // max(1, M * self.nweights)))
+        if collect_every:
+            chunk = max(collect_every, chunk - chunk % collect_every)
+        nb = int(getattr(self, "nbatches", 0) or 0)
+        done = 0
+        while done < n_steps:
+            n = min(chunk, n_steps - done)
+            ts = list(range(t_first + done, t_first + done + n))
+            noise = self._sgld_noise(ts, M, w.device)
+            half = np.array([np.float32(self.get_stepsize(t) / 2) for t in ts], dtype=np.float32)
+            offs = np.array([t % nb if nb > 1 else 0 for t in ts], dtype=np.int32)
+            sl = samples[done // collect_every:(done + n) // collect_every] if collect_every else None
+            prob.sgld_iterate(w, noise, half, offs, nb if nb > 1 else 1, with_data, samples=sl, thin=collect_every,
+                              lanes=int(getattr(self, "lanes", 0) or 0))
+            done += n
+            if bool(torch.isnan(w).any()):
+                _raise_nan(self)
+        return samples
+
+    def infer(self, verbose=True, with_data=True):
+        infer_id = len(self.all_bayes_samples) + 1
+        logging.info(f"[{self.uid}] Posterior Sample #{infer_id}: Beginning SGLD inference...")
+        start_time = time.time()
+        dev = self._device()
+        M_total = max(1, int(getattr(self, "nchains", 1) or 1))
+        lo, hi = D.shard(M_total)
+        w = HMCMixin._hmc_state(self, M_total, dev)[lo:hi].contiguous()
+        self.sgld_run(w, 1, self.sgld_nburnin, with_data)
+        if self.sgld_nburnin:
+            logging.info(f"  All {self.sgld_nburnin} burn-in steps completed.")
+        logging.info("  Collecting samples now...")
+        rounds = -(-self.infer_nsamples // M_total)
+        samples = self.sgld_run(w, self.sgld_nburnin + 1, rounds * self.sgld_ninterval, with_data, collect_every=self.sgld_ninterval)
+        end_time = time.time()
+        if self.infer_nsamples:
+            logging.info(f"  All {self.infer_nsamples} samples collected. Time took: {(end_time - start_time):.0f} seconds.")
+        samples = D.gather_cat(samples, dim=1).reshape(-1, self.nweights)[:self.infer_nsamples].cpu()
+        states = D.gather_cat(w, dim=0).cpu()
+        self.chain_states = states
+        self.weights = states[0].clone().requires_grad_(True)
+        if D.rank() == 0:
+            torch.save(samples, f"history/{self.uid}_sgld{infer_id}.pt")
+        self.all_bayes_samples.append((samples, _name(self, "sgld")))
+        logging.info(f"[{self.uid}] Posterior Sample #{infer_id}: SGLD inference completed. Samples saved as `history/{self.uid}_sgld{infer_id}.pt`.")
+
+
+class SVGDMixin:
+    """Stein Variational Gradient Descent (inference.py:203-292); particles shard over ranks."""
+
+    def svgd_setup(self, particles):
+        """particles: (n, D) host or device tensor; this rank keeps rows [lo, hi)."""
+        dev = self._device()
+        n = particles.shape[0]
+        lo, hi = D.shard(n)
+        st = {"n": n, "lo": lo, "hi": hi,
+              "X": particles[lo:hi].to(dev, torch.float32).contiguous(),
+              "acc": torch.zeros(hi - lo, self.nweights, device=dev),
+              "h": torch.empty(1, device=dev),
+              "hist": torch.zeros(3 * 2048, dtype=torch.int32, device=dev),
+              "state": torch.zeros(4, dtype=torch.int64, device=dev)}
+        st["ws"] = E.svgd_workspace(n, self.nweights, dev)
+        return st
+
+    def svgd_epoch(self, st, epoch, with_data, use_tensor=-1):
+        """One SVGD epoch on the device: gradients (K1), all-gather, bandwidth (K3a), phi (K3b), Adagrad (K3c)."""
+        prob = self.engine_problem()
+        X = st["X"]
+        _, G = prob.logpost_grad(X, _batch_for(self, epoch), with_data, want_lp=False)
+        Xall, Gall = D.gather_cat(X, dim=0), D.gather_cat(G, dim=0)
+        n = st["n"]
+        if D.world() == 1:
+            E.svgd_bandwidth(Xall, st["ws"], st["h"])
+        else:                                   # exact global median: all-reduce the select histograms between passes
+            for p in range(3):
+                rows = len(range(D.rank(), n, D.world()))
+                E.svgd_hist_pass(Xall, D.rank(), D.world(), rows, p, st["hist"], st["state"])
+                seg = st["hist"][p * 2048:(p + 1) * 2048]
+                D.all_sum_(seg)
+                E.svgd_select_update(p, st["hist"], st["state"], n, st["h"])
+        phi = E.svgd_phi(Xall, Gall, st["h"], st["lo"], st["hi"] - st["lo"], st["ws"], use_tensor)
+        E.adagrad_step(X, st["acc"], phi, self.svgd_init_lr, -1.0)      # particles.grad = -update (inference.py:280)
+        st["phi"] = phi
+        return st
+
+    def infer(self, verbose=True, with_data=True):
+        infer_id = len(self.all_bayes_samples) + 1
+        logging.info(f"[{self.uid}] Posterior Sample #{infer_id}: Beginning SVGD inference...")
+        start_time = time.time()
+        self.particles = Normal(0, self.sigma_w).sample(torch.Size([self.infer_nsamples, self.nweights]))
+        st = self.svgd_setup(self.particles)
+        tens = int(getattr(self, "svgd_tensor", -1))
+        for epoch in range(1, self.svgd_epochs + 1):
+            self.svgd_epoch(st, epoch, with_data, tens)
+            if verbose and epoch % 10 == 0:
+                logging.info(f"  Epoch {epoch} reached.")
+        end_time = time.time()
+        logging.info(f"  {self.svgd_epochs} epochs completed. Time took: {(end_time - start_time):.0f} seconds.")
+        self.particles = D.gather_cat(st["X"], dim=0).cpu()
+        if bool(torch.isnan(self.particles).any()):
+            _raise_nan(self)
+        if D.rank() == 0:
+            torch.save(self.particles, f"history/{self.uid}_svgd{infer_id}.pt")
+        self.all_bayes_samples.append((self.particles.clone(), _name(self, "svgd")))
+        logging.info(f"[{self.uid}] Posterior Sample #{infer_id}: SVGD inference completed. Samples saved as `history/{self.uid}_svgd{infer_id}.pt`.")
+
+
+class BBBMixin:
+    """Bayes by Backprop (inference.py:127-200); Monte-Carlo samples shard over ranks."""
+
+    def sample_q(self, k, q_params=None, eps=None):
+        """k weight samples from the variational Gaussian and their log q (inference.py:132-140), on the host."""
+        qp = self.q_params if q_params is None else q_params
+        mean, std = qp[:, 0], torch.logsumexp(torch.stack((qp[:, 1], torch.zeros(self.nweights))), 0)
+        eps = torch.randn(k, self.nweights) if eps is None else eps
+        weights = mean + eps * std
+        return weights, Normal(mean, std).log_prob(weights)
+
+    def bbb_epoch(self, qp, acc, eps, epoch, with_data, k_total=None):
+        """One ELBO-gradient step on the device.  eps: this rank's (k_local, D) standard normal draws."""
+        prob = self.engine_problem()
+        k_total = eps.shape[0] * D.world() if k_total is None else k_total
+        W = E.bbb_sample(qp, eps)
+        lp, G = prob.logpost_grad(W, _batch_for(self, epoch), with_data)
+        gq, elbo = E.bbb_reduce(qp, eps, lp, G, k_total, add_entropy=(D.rank() == 0))
+        D.all_sum_(gq)
+        D.all_sum_(elbo)
+        E.adagrad_step(qp, acc, gq, self.bbb_init_lr, -1.0)             # loss = -ELBO
+        return elbo
+
+    def infer(self, verbose=True, with_data=True):
+        infer_id = len(self.all_bayes_samples) + 1
+        logging.info(f"[{self.uid}] Posterior Sample #{infer_id}: Beginning BBB inference...")
+        start_time = time.time()
+        dev = self._device()
+        init_means = self.bbb_init_mean + torch.randn(self.nweights, 1)
+        init_log_stds = self.bbb_init_std * torch.ones(self.nweights, 1)
+        qp = torch.cat([init_means, init_log_stds], dim=1).to(dev).contiguous()
+        acc = torch.zeros_like(qp)
+        k = int(self.bbb_esamples)
+        lo, hi = D.shard(k)
+        device_rng = getattr(self, "rng", "host") == "device"
+        elbos = []
+        for epoch in range(1, self.bbb_epochs + 1):
+            if device_rng:
+                eps = torch.randn(hi - lo, self.nweights, device=dev)
+            else:
+                eps = torch.randn(k, self.nweights)[lo:hi].to(dev).contiguous()    # inference.py:138
+            elbos.append(self.bbb_epoch(qp, acc, eps, epoch, with_data, k_total=k))
+            if verbose and epoch % 100 == 0:
+                logging.info(f"  Epoch {epoch}: {float(elbos[-1]):.2f}")
+        self.elbos = [float(e) for e in torch.cat(elbos).cpu()] if elbos else []
+        end_time = time.time()
+        if self.elbos:
+            logging.info(f"  {self.bbb_epochs} epochs completed. Final ELBO is {self.elbos[-1]:.2f}. Time took: {(end_time - start_time):.0f} seconds.")
+        self.q_params = qp.cpu()
+        samples, _ = self.sample_q(self.infer_nsamples)
+        if D.rank() == 0:
+            torch.save(self.q_params, f"history/{self.uid}_bbb{infer_id}_qparams.pt")
+            torch.save(samples, f"history/{self.uid}_bbb{infer_id}.pt")
+        self.all_bayes_samples.append((samples, _name(self, "bbb")))
+        logging.info(f"[{self.uid}] Posterior Sample #{infer_id}: BBB inference completed.")
+        logging.info(f"[{self.uid}] Variational parameters saved as `history/{self.uid}_bbb{infer_id}_qparams.pt`. Samples saved as `history/{self.uid}_bbb{infer_id}.pt`.")
