@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""
+bench.py — headline benchmark of the OC-BNN B200 engine.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W     (CPU arm: the oracle port on the host cores)
+
+Metric (BASELINE.json): HMC chain-leapfrog-steps/s.  Workload: W2 = repro/F1a.yaml ([1,10,1] rbf regressor on toy1,
+negative-exponential COCP with 100 constraint points, posterior) with the chain count scaled up; one "step" is one HMC
+iteration (L = 50 leapfrog steps + Metropolis-Hastings) of all chains.  Chains are independent: ranks hold disjoint
+chains, there is no data-path collective ("scaling": "weak", per-GPU chain count fixed).
+
+`value`  : chain-leapfrog-steps/s with q, momenta and uniforms resident in HBM (CUDA events, L2 flushed between steps,
+           max over ranks).
+`e2e`    : the same through host buffers: every step copies q, momenta and uniforms from pinned host memory to the device,
+           runs the kernel and copies q and the accept flags back.
+`roofline`: the HMC kernel against the fp32 instruction roofline measured in the same run (packed FFMA2 probe); the toy
+           nets keep all state in registers, so HBM traffic is ~7 B per chain-step and neither the HBM nor the tensor
+           roofline binds (fractions of those are reported for context).
+`cpu_baseline`: the numpy oracle port on the host cores (bounded sample).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "ocbnn-public_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "hmc_chain_leapfrog_steps_per_s"
+UNIT = "chain-leapfrog-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="W2")
+    ap.add_argument("--chains", type=int, default=262144, help="chains per GPU")
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--leapfrog", type=int, default=50)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--extras", action="store_true", help="also time SVGD/SGLD/BBB and the chain-count sweep (extra JSON keys)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (numpy restatement, oracle/ocbnn_oracle.py) on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _oracle_spec_arrays(m):
+    from ocbnn_b200 import workloads
+    iv = np.array([[(float(a), float(b)) for a, b in row] for row in workloads.ifunc_f1a(m._cr_neg_xsamples)])
+    return dict(sizes=list(m.layer_sizes), act=m.activation, X=m.X_train.numpy(), Y=m.Y_train.numpy(), sigma_w=float(m.sigma_w),
+                sigma_noise=float(m.sigma_noise), xs=m._cr_neg_xsamples.numpy(), iv=iv, S=int(m.ocp_nsamples),
+                gamma=float(m.cocp_expo_gamma), tau=[float(t) for t in m.cocp_expo_tau], eps=float(m.hmc_epsilon))
+
+
+def _cpu_worker(args):
+    arr, M, L, seed = args
+    import ocbnn_oracle as orc
+    spec = orc.Spec(arr["sizes"], arr["act"], "regression", arr["X"], arr["Y"], sigma_w=arr["sigma_w"], sigma_noise=arr["sigma_noise"],
+                    use_ocbnn=True, neg=dict(xs=arr["xs"], intervals=[arr["iv"]], S=arr["S"], gamma=arr["gamma"], tau=arr["tau"]))
+    rng = np.random.default_rng(seed)
+    q = (0.5 * rng.standard_normal((M, spec.nweights))).astype(np.float32)
+    p0 = rng.standard_normal((1, M, spec.nweights)).astype(np.float32)
+    u = rng.random((1, M))
+    t0 = time.perf_counter()
+    orc.hmc_iterate(spec, q, p0, u, arr["eps"], L)
+    return time.perf_counter() - t0
+
+
+def cpu_hmc_rate(arr, L, seconds, steps=1, warmup=0):
+    """chain-leapfrog-steps/s of the oracle port with one worker process per host core; each step is one HMC iteration of a
+    bounded number of chains sized for ~`seconds` of wall time in total."""
+    import concurrent.futures as cf
+    cores = os.cpu_count() or 1
+    with cf.ProcessPoolExecutor(max_workers=cores) as ex:
+        t_small = max(list(ex.map(_cpu_worker, [(arr, 16, L, s) for s in range(cores)])))
+        per_chain = t_small / 16.0
+        n = max(1, steps + warmup)
+        M = int(max(16, min(4096, seconds / n / max(per_chain, 1e-9))))
+        times = []
+        for s in range(n):
+            t0 = time.perf_counter()
+            list(ex.map(_cpu_worker, [(arr, M, L, 100 * s + c) for c in range(cores)]))
+            if s >= warmup:
+                times.append(time.perf_counter() - t0)
+    tot = sum(times)
+    rate = cores * M * L * len(times) / tot
+    return rate, cores, M, tot / len(times)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        from ocbnn_b200 import workloads
+        m = workloads.build(args.workload, seed=0)
+        arr = _oracle_spec_arrays(m)
+        os.chdir(cwd)
+    rate, cores, M, t_step = cpu_hmc_rate(arr, args.leapfrog, seconds=max(20.0, 8.0 * (args.steps + args.warmup)), steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "W2 repro/F1a.yaml HMC + negative-exponential COCP, toy1, [1,10,1] rbf", "chains": cores * M,
+                       "leapfrog_l": args.leapfrog},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{cores} processes x {M} chains x 1 HMC iteration (L={args.leapfrog}) per step, numpy oracle port"},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from ocbnn_b200 import engine, workloads
+
+    cwd = os.getcwd()
+    scratch = tempfile.mkdtemp(prefix=f"ocbnn_bench_r{rank}_")
+    os.chdir(scratch)
+    m = workloads.build(args.workload, seed=0)
+    prob = m.engine_problem()
+    os.chdir(cwd)
+    D, L, M = m.nweights, args.leapfrog, args.chains
+    K, W = args.steps, max(args.warmup, 3)
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    q = 0.5 * torch.randn(M, D, device=dev, generator=gen)
+    # short burn-in so that the timed steps run on equilibrated chains (untimed)
+    for _ in range(2):
+        prob.hmc_iterate(q, torch.randn(1, M, D, device=dev, generator=gen), torch.rand(1, M, device=dev, dtype=torch.float64, generator=gen),
+                         m.hmc_epsilon, L, True, lanes=args.lanes)
+    p0 = torch.randn(W + K, M, D, device=dev, generator=gen)
+    u = torch.rand(W + K, M, device=dev, dtype=torch.float64, generator=gen)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        return prob.hmc_iterate(q, p0[i:i + 1], u[i:i + 1], m.hmc_epsilon, L, True, want_flags=False, lanes=args.lanes)
+
+    for i in range(W):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = engine.launch_count()
+    evs = []
+    t_wall0 = time.perf_counter()
+    acc_total = 0
+    for i in range(K):
+        flush.fill_(i & 0xFF)                                           # L2 flush between timed steps (not timed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        acc, _, _ = step(W + i)
+        e1.record()
+        evs.append((e0, e1))
+        acc_total = acc_total + acc.sum()
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    launches = engine.launch_count() - launches0
+    clocks = sampler.stop()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * M * L * K / (ms_total * 1e-3)
+    accept_rate = float(acc_total) / (K * M)
+
+    # ---- end to end through host buffers -------------------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        qh = q.cpu().pin_memory()
+        p0h = p0[W:W + K].cpu().pin_memory()
+        uh = u[W:W + K].cpu().pin_memory()
+        acch = torch.empty(M, dtype=torch.uint8).pin_memory()
+        qd, pd, ud = torch.empty_like(q), torch.empty(1, M, D, device=dev), torch.empty(1, M, device=dev, dtype=torch.float64)
+        barrier()
+        ee = []
+        for i in range(K):
+            flush.fill_(i & 0xFF)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            qd.copy_(qh, non_blocking=True)
+            pd[0].copy_(p0h[i], non_blocking=True)
+            ud[0].copy_(uh[i], non_blocking=True)
+            a, _, _ = prob.hmc_iterate(qd, pd, ud, m.hmc_epsilon, L, True, want_flags=False, lanes=args.lanes)
+            qh.copy_(qd, non_blocking=True)
+            acch.copy_(a[0], non_blocking=True)
+            e1.record()
+            ee.append((e0, e1))
+        barrier()
+        ms2 = torch.tensor([sum(a.elapsed_time(b) for a, b in ee)], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
+        e2e = {"value": world * M * L * K / (float(ms2.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(M * D * 4 * 2 + M * 8), "d2h_bytes_per_step": int(M * D * 4 + M)}
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_hmc_small) -------------------------------------------------------------------
+    flop_step, mufu_step, bytes_step = workloads.hmc_step_work(m, True)
+    hbm_gbs, bf16_tf, src = load_peaks()
+    peak_ffma2 = engine.probe_peak(1)
+    peak_ffma = engine.probe_peak(0)
+    peak_mufu = engine.probe_peak(2)
+    ker_s = ms_total * 1e-3 / K                      # one launch per step: the event brackets exactly that kernel
+    ach_flops = M * L * flop_step / ker_s
+    roofline = {"bound": "fp32-simt", "kernel": "k_hmc_small", "achieved": ach_flops / 1e12, "peak": peak_ffma2 / 1e12, "unit": "TFLOP/s",
+                "frac": ach_flops / peak_ffma2, "traffic": None,
+                "peak_source": "packed FFMA2 probe kernel measured in this run (MEASURED_PEAKS.json has HBM and bf16 tensor peaks only)",
+                "flop_per_chain_step": flop_step, "mufu_per_chain_step": mufu_step, "hbm_bytes_per_chain_step": bytes_step,
+                "scalar_ffma_peak_tflops": peak_ffma / 1e12, "mufu_peak_tops": peak_mufu / 1e12,
+                "mufu_frac": (M * L * mufu_step / ker_s) / peak_mufu,
+                "hbm_frac_for_context": (M * L * bytes_step / ker_s) / (hbm_gbs * 1e9), "hbm_peak_gbs": hbm_gbs, "hbm_peak_source": src}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        os.chdir(scratch)
+        arr = _oracle_spec_arrays(m)
+        os.chdir(cwd)
+        rate, cores, Mc, _ = cpu_hmc_rate(arr, L, seconds=args.cpu_seconds)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{cores} processes x {Mc} chains x 1 HMC iteration (L={L}), numpy oracle port of the same workload"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "W2 repro/F1a.yaml HMC + negative-exponential COCP (100 constraint points), toy1 (6 points), [1,10,1] rbf, posterior",
+                       "chains_per_gpu": M, "chains_total": world * M, "leapfrog_l": L, "hmc_epsilon": m.hmc_epsilon, "lanes_per_chain": args.lanes or "auto",
+                       "l2": "flushed between timed steps (256 MiB write)", "accept_rate": accept_rate},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "wall_s_timed_region": wall}
+    if args.extras:
+        line["extras"] = extras(m, prob, dev, args)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def _time_cuda(fn, reps=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / reps
+
+
+def extras(m, prob, dev, args):
+    """Secondary measurements (single GPU): HMC chain-count sweep, SVGD particle-iters/s (W4), SGLD chain-steps/s."""
+    from ocbnn_b200 import engine as E, workloads
+    out = {}
+    D, L = m.nweights, args.leapfrog
+    sweep = {}
+    for M in (4096, 32768, 262144, 1048576):
+        for lanes in ((0,) if M > 4096 else (0, 8, 16, 32)):
+            q = 0.5 * torch.randn(M, D, device=dev)
+            p0 = torch.randn(1, M, D, device=dev)
+            u = torch.rand(1, M, device=dev, dtype=torch.float64)
+            t = _time_cuda(lambda: prob.hmc_iterate(q, p0, u, m.hmc_epsilon, L, True, want_flags=False, lanes=lanes), reps=2)
+            sweep[f"M{M}_lanes{lanes or 'auto'}"] = M * L / t
+    out["hmc_sweep_chain_leapfrog_steps_per_s"] = sweep
+    cwd = os.getcwd()
+    d = tempfile.mkdtemp(prefix="ocbnn_extras_")
+    os.chdir(d)
+    try:
+        for n in (4096, 16384):
+            ms = workloads.build("W4", seed=0, infer_nsamples=n)
+            st = ms.svgd_setup(torch.randn(n, ms.nweights))
+            t = _time_cuda(lambda: ms.svgd_epoch(st, 1, True, use_tensor=0), reps=3)
+            out[f"svgd_W4_n{n}_particle_iters_per_s"] = n / t
+        mg = workloads.build("W1", sampler="SGLD", seed=0)
+        pg = mg.engine_problem()
+        M, T = 262144, 20
+        w = 0.5 * torch.randn(M, D, device=dev)
+        noise = 0.01 * torch.randn(T, M, D, device=dev)
+        he = np.full(T, 0.003, dtype=np.float32)
+        t = _time_cuda(lambda: pg.sgld_iterate(w, noise, he, None, 1, True), reps=2)
+        out["sgld_W1_chain_steps_per_s"] = M * T / t
+    finally:
+        os.chdir(cwd)
+    return out
+
+
+if __name__ == "__main__":
+    main()

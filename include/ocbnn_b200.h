@@ -177,6 +177,10 @@ OCBNN_API int ocbnn_bbb_sample(const float *q_params, const float *eps, int64_t 
 OCBNN_API int ocbnn_bbb_reduce(const float *q_params, const float *eps, const float *lp, const float *grad, int64_t k, int64_t d,
                      int64_t k_total, int32_t add_entropy, float *out_grad_q, float *out_elbo, float *colstat, void *stream);
 
+/* Diagnostics for the roofline report: measured instruction peaks of this GPU.  mode 0: scalar fp32 FMA, 1: packed
+ * f32x2 FMA (both in FLOP/s, fma = 2), 2: MUFU.EX2 (op/s).  Synchronous. */
+OCBNN_API int ocbnn_probe_peak(int32_t mode, double *out_rate);
+
 /* Host-buffer convenience used for end-to-end timing: H2D of q/p0/u, K2, D2H of q/accept inside the call (synchronous). */
 OCBNN_API int ocbnn_hmc_iterate_host(ocbnn_problem *p, float *q_host, const float *p0_host, const double *u_host, int64_t m,
                            int32_t n_it, double eps, int32_t leapfrog_l, int32_t with_data, int32_t restore_on_reject,

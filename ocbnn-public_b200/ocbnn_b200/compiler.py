@@ -198,7 +198,7 @@ def batch_spec(batch_indices, N):
     if bi.numel() == 0:
         raise ValueError("empty batch")
     off = int(bi[0])
-    stride = int(bi[1] - bi[0]) if bi.numel() > 1 else max(N - off, 2)
+    stride = int(bi[1] - bi[0]) if bi.numel() > 1 else max(N - off, off + 1, 2)
     if stride < 1 or not torch.equal(bi, torch.arange(off, N, stride)):
         raise NotImplementedError("the engine evaluates strided batches arange(offset, N, stride) only (inference.py:180,276,334)")
     if stride == 1:

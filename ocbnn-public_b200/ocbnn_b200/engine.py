@@ -87,6 +87,7 @@ _SIGS = {
     "ocbnn_bbb_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "ocbnn_bbb_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ocbnn_probe_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
     "ocbnn_hmc_iterate_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double,
                                          C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
 }
@@ -120,6 +121,14 @@ def check(rc):
 
 def launch_count():
     return int(lib().ocbnn_launch_count())
+
+
+def probe_peak(mode):
+    """Measured instruction peak of this GPU: 0 scalar FFMA, 1 packed FFMA2 (FLOP/s), 2 MUFU.EX2 (op/s)."""
+    require_cuda()
+    r = C.c_double()
+    check(lib().ocbnn_probe_peak(int(mode), C.byref(r)))
+    return r.value
 
 
 def require_cuda():

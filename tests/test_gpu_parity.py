@@ -1,0 +1,315 @@
+"""Parity tests proper (run with -m gpu on a B200): the CUDA engine, called through the C-ABI (ctypes), against
+(a) the golden vectors produced by the unmodified reference and (b) the numpy oracle in fp32 and float64.
+
+Tolerance, as BASELINE.json states it: log-posterior and gradients within 1e-5 relative (norm-wise per weight vector).
+Rows that are ill-conditioned in fp32 — where the fp32 and float64 oracles themselves disagree by more than that,
+e.g. saturated tanh penalties — get max(1e-5, 4 x that disagreement) against the reference, and are always held to the
+float64 oracle at 1e-5 + the same slack (the engine accumulates values in float64)."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import ocbnn_oracle as orc
+from helpers import golden_config, load_golden, make_model, rel_err, spec_from_golden
+from ocbnn_b200 import engine as E
+
+pytestmark = pytest.mark.gpu
+
+ALL = list(cases.CASES)
+SMALL_NETS = ["w1_reg_vanilla", "w2_reg_neg", "f3b_reg_neg2", "reg_multi_neg", "f6_reg_pos", "reg_pos_neg", "cls_vanilla", "w3_cls_dir",
+              "bin_vanilla", "f4_bin_aocp", "f3a_reg_aocp"]
+TOL = 1e-5
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def t2d(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(dev(), dtype).contiguous()
+
+
+def check(x, ref, x32, x64, what, floor=TOL):
+    cond = rel_err(x32, x64)
+    tol = np.maximum(floor, 4 * cond)
+    e_ref, e_64 = rel_err(x, ref), rel_err(x, x64)
+    assert (e_64 <= floor + 2 * cond).all(), (what, "engine vs float64 oracle", e_64, cond)
+    assert (e_ref <= tol).all(), (what, "engine vs reference", e_ref, tol)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_k1_logpost_and_grad(name):
+    g = load_golden(name)
+    m = make_model(name, g)
+    spec = spec_from_golden(name, g)
+    W = g["W"]
+    prob = m.engine_problem()
+    lanes_list = (0, 1, 2, 4, 8, 16, 32) if name in SMALL_NETS else (0,)
+    for with_data, key in ((True, "post"), (False, "prior")):
+        f = (lambda dt: orc.log_posterior(spec, W, None, True, dtype=dt)) if with_data else (lambda dt: orc.log_prior(spec, W, dtype=dt))
+        (lp32, g32), (lp64, g64) = f(np.float32), f(np.float64)
+        for lanes in lanes_list:
+            lp, gr = prob.logpost_grad(t2d(W), (0, 1), with_data, lanes=lanes)
+            check(lp.cpu().numpy(), g["lp_" + key], lp32, lp64, (name, key, lanes))
+            check(gr.cpu().numpy(), g["g_" + key], g32, g64, (name, key, "grad", lanes))
+    nb = golden_config(g).get("nbatches")
+    if nb:
+        for off in (1, nb - 1):
+            bi = orc.batch_indices(spec.N_train, off, nb)
+            (lp32, g32), (lp64, g64) = orc.log_posterior(spec, W, bi, True), orc.log_posterior(spec, W, bi, True, dtype=np.float64)
+            lp, gr = prob.logpost_grad(t2d(W), (off, nb), True)
+            check(lp.cpu().numpy(), g[f"lp_post_b{off}"], lp32, lp64, (name, "batch", off))
+            check(gr.cpu().numpy(), g[f"g_post_b{off}"], g32, g64, (name, "batch grad", off))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_host_api_values(name):
+    """The reference-facing methods (log_prior/log_posterior/log_likelihood/forward/predict) return the reference's values."""
+    g = load_golden(name)
+    m = make_model(name, g)
+    m.weights = torch.tensor(g["W"][0]).requires_grad_(True)
+    assert abs(float(m.log_prior()) - g["lp_prior"][0]) <= 2e-5 * abs(g["lp_prior"][0])
+    assert abs(float(m.log_posterior()) - g["lp_post"][0]) <= 2e-5 * abs(g["lp_post"][0])
+    assert abs(float(m.log_likelihood()) - g["lp_lik"][0]) <= 2e-5 * max(abs(g["lp_lik"][0]), abs(g["lp_post"][0]))
+    dom = torch.tensor(g["predict_domain"])
+    F = torch.stack([m.forward(dom, weights=torch.tensor(w)) for w in g["W"][:2]])
+    scale = max(1.0, np.abs(g["forward_out"]).max())
+    assert np.abs(F.numpy() - g["forward_out"][:2]).max() < 2e-5 * scale
+    Fb = m.forward(dom, weights=torch.tensor(g["W"]))                 # batched over weight vectors
+    assert np.abs(Fb.numpy() - g["forward_out"]).max() < 2e-5 * scale
+    if "predict_probs" in g:
+        P = m.predict(torch.tensor(g["W"]), dom, return_probs=True)
+        assert np.abs(P.numpy() - g["predict_probs"]).max() < 1e-5
+        cls = m.predict(torch.tensor(g["W"]), dom)
+        assert cls.shape == tuple(g["predict_probs"].shape[:2])
+    else:
+        P = m.predict(torch.tensor(g["W"]), dom)
+        assert np.abs(P.numpy() - g["forward_out"]).max() < 2e-5 * scale
+
+
+def _hmc_tags(g):
+    return [t for t in ("hmc", "hmc_prior") if t + "_q" in g]
+
+
+@pytest.mark.parametrize("name", cases.SAMPLER_CASES)
+def test_k2_hmc_trajectory(name):
+    """Injected momenta and uniforms: same accept decisions, same (U0,K0,U1,K1), same end state as the reference."""
+    g = load_golden(name)
+    m = make_model(name, g)
+    spec = spec_from_golden(name, g)
+    cfg = golden_config(g)
+    prob = m.engine_problem()
+    for tag in _hmc_tags(g):
+        L = int(g[tag + "_L"])
+        wd = tag == "hmc"
+        for it in range(g[tag + "_p0"].shape[0]):
+            q_start = (g[tag + "_q0"] if it == 0 else g[tag + "_q"][it - 1])[None]
+            args = (g[tag + "_p0"][it][None, None], g[tag + "_u"][it][None, None], cfg["hmc_epsilon"], L)
+            q32, a32, H32 = orc.hmc_iterate(spec, q_start, *args, with_data=wd)
+            q64, a64, H64 = orc.hmc_iterate(spec, q_start, *args, with_data=wd, dtype=np.float64)
+            for lanes in ((1, 4, 32) if name in SMALL_NETS else (0,)):
+                q = t2d(q_start)
+                acc, H, flags = prob.hmc_iterate(q, t2d(args[0]), t2d(args[1], torch.float64), cfg["hmc_epsilon"], L, wd, want_h=True, lanes=lanes)
+                assert int(flags[0]) == 0
+                ref_H = g[tag + "_H"][it]
+                Hn = H.cpu().numpy()[0, 0]
+                alpha_ref = np.exp(np.float32(ref_H[0] - ref_H[2] + ref_H[1] - ref_H[3]))
+                u = float(g[tag + "_u"][it])
+                if abs(u - alpha_ref) > 1e-3 * max(alpha_ref, 1e-30):          # outside the fp32 noise band of the decision
+                    assert bool(acc[0, 0]) == bool(g[tag + "_acc"][it]), (name, tag, it, lanes)
+                assert np.abs(Hn - ref_H).max() <= 5e-5 * max(1.0, np.abs(ref_H).max()), (name, tag, it, Hn, ref_H)
+                tol = max(1e-4, 4 * rel_err(q32, q64).max())
+                assert rel_err(q.cpu().numpy(), g[tag + "_q"][it][None]).max() < tol, (name, tag, it, lanes)
+                assert rel_err(q.cpu().numpy(), q64).max() < tol
+
+
+def test_k2_chains_are_independent_and_restore_works():
+    """Replicated chains give bit-identical results whatever their position in the launch; restore_on_reject=1 restores q0."""
+    name = "w2_reg_neg"
+    g = load_golden(name)
+    m = make_model(name, g)
+    cfg = golden_config(g)
+    prob = m.engine_problem()
+    M, n_it, L = 333, 3, 7
+    q0 = np.repeat(g["hmc_q0"][None], M, 0)
+    p0 = np.repeat(g["hmc_p0"][:n_it, None, :], M, 1)
+    u = np.repeat(g["hmc_u"][:n_it, None], M, 1)
+    u[u == np.inf] = 0.5
+    for lanes in (1, 8, 32):
+        q = t2d(q0)
+        acc, H, _ = prob.hmc_iterate(q, t2d(p0), t2d(u, torch.float64), cfg["hmc_epsilon"], L, True, want_h=True, lanes=lanes)
+        qc = q.cpu().numpy()
+        assert (qc == qc[0]).all() and (acc.cpu().numpy() == acc.cpu().numpy()[:, :1]).all()
+        single = t2d(q0[:1])
+        prob.hmc_iterate(single, t2d(p0[:, :1]), t2d(u[:, :1], torch.float64), cfg["hmc_epsilon"], L, True, lanes=lanes)
+        assert (single.cpu().numpy() == qc[:1]).all()
+    # forced rejects: the reference-faithful mode keeps the proposal, restore mode returns to q0 exactly
+    u_rej = np.full_like(u, np.inf)
+    q_keep, q_rest = t2d(q0[:5]), t2d(q0[:5])
+    a1, _, _ = prob.hmc_iterate(q_keep, t2d(p0[:, :5]), t2d(u_rej[:, :5], torch.float64), cfg["hmc_epsilon"], L, True, restore_on_reject=False)
+    a2, _, _ = prob.hmc_iterate(q_rest, t2d(p0[:, :5]), t2d(u_rej[:, :5], torch.float64), cfg["hmc_epsilon"], L, True, restore_on_reject=True)
+    assert int(a1.sum()) == 0 and int(a2.sum()) == 0
+    assert (q_rest.cpu().numpy() == q0[:5]).all()
+    assert np.abs(q_keep.cpu().numpy() - q0[:5]).max() > 0
+
+
+def test_hmc_infer_driver_semantics():
+    """infer(): burn-in, thinning, sample packing, naming and history file as in inference.py:80-124."""
+    import os
+    name = "w1_reg_vanilla"
+    g = load_golden(name)
+    m = make_model(name, g, hmc_nburnin=2, infer_nsamples=3, hmc_ninterval=2, hmc_l=5)
+    m.weights = torch.tensor(g["hmcdrv_q0"]).requires_grad_(True)
+    p_all, u_all, pos = g["hmcdrv_p0"], g["hmcdrv_u"], [0]
+
+    def draw(n_it, M, device):
+        p = torch.tensor(p_all[pos[0]:pos[0] + n_it])[:, None, :].to(device)
+        u = torch.tensor(u_all[pos[0]:pos[0] + n_it])[:, None].to(device)
+        pos[0] += n_it
+        return p.contiguous(), u.contiguous()
+    m._hmc_draw = draw
+    m.infer(verbose=False)
+    samples, nm = m.all_bayes_samples[-1]
+    assert nm == str(g["hmcdrv_name"]) and samples.shape == g["hmcdrv_samples"].shape and samples.dtype == torch.float32
+    assert rel_err(samples.numpy(), g["hmcdrv_samples"]).max() < 1e-4
+    assert os.path.exists(f"history/{m.uid}_hmc1.pt")
+    assert torch.equal(torch.load(f"history/{m.uid}_hmc1.pt"), samples)
+    assert pos[0] == 2 + 3 * 2
+
+
+def test_hmc_multichain_infer():
+    g = load_golden("w1_reg_vanilla")
+    m = make_model("w1_reg_vanilla", g, hmc_nburnin=3, infer_nsamples=10, hmc_ninterval=2, hmc_l=5, nchains=4, rng="device")
+    m.infer(verbose=False)
+    s, _ = m.all_bayes_samples[-1]
+    assert s.shape == (10, m.nweights) and torch.isfinite(s).all()
+    assert m.chain_states.shape == (4, m.nweights)
+    assert 0 <= m.accepts <= 3 * 2 * 4
+
+
+@pytest.mark.parametrize("name", cases.SAMPLER_CASES + cases.BATCHED_SAMPLER_CASES)
+def test_k4_sgld(name):
+    g = load_golden(name)
+    epa = float(g["sgld_epa"])
+    m = make_model(name, g, sampler="SGLD", sgld_nburnin=3, infer_nsamples=2, sgld_ninterval=2, sgld_epa=epa)
+    m.weights = torch.tensor(g["sgld_w0"]).requires_grad_(True)
+    z, pos = g["sgld_z"], [0]
+
+    def noise(ts, M, device):
+        sd = np.array([np.float32(m.get_stepsize(t) ** 0.5) for t in ts], dtype=np.float32)
+        out = torch.tensor(z[pos[0]:pos[0] + len(ts)] * sd[:, None])[:, None, :].to(device)
+        pos[0] += len(ts)
+        return out.contiguous()
+    m._sgld_noise = noise
+    m.infer(verbose=False)
+    samples, nm = m.all_bayes_samples[-1]
+    assert nm.startswith("sgld_") and samples.shape == g["sgld_samples"].shape
+    assert rel_err(samples.numpy(), g["sgld_samples"]).max() < 1e-4
+    assert rel_err(m.weights.detach().numpy()[None], g["sgld_final"][None]).max() < 1e-4
+
+
+@pytest.mark.parametrize("name", cases.SAMPLER_CASES + cases.BATCHED_SAMPLER_CASES)
+def test_k3_svgd(name):
+    g = load_golden(name)
+    n = g["svgd_x0"].shape[0]
+    m = make_model(name, g, sampler="SVGD", svgd_epochs=3, infer_nsamples=n)
+    spec = spec_from_golden(name, g)
+    cfg = golden_config(g)
+    st = m.svgd_setup(torch.tensor(g["svgd_x0"]))
+    # bandwidth: exact lower median -> h equal to the reference's to fp32 rounding
+    h = E.svgd_bandwidth(st["X"], st["ws"])
+    assert abs(float(h) - g["svgd_h"][0]) <= 2e-6 * g["svgd_h"][0]
+    assert abs(float(h) - orc.svgd_rbf_h(g["svgd_x0"])) <= 2e-6 * g["svgd_h"][0]
+    for ep in range(1, 4):
+        m.svgd_epoch(st, ep, True, use_tensor=0)
+        if ep == 1:
+            assert rel_err(st["phi"].cpu().numpy(), g["svgd_phi"][0]).max() < 2e-5
+        assert abs(float(st["h"]) - g["svgd_h"][ep - 1]) <= 1e-4 * g["svgd_h"][ep - 1]
+    assert np.abs(st["X"].cpu().numpy() - g["svgd_final"]).max() < 5e-3 * max(1.0, np.abs(g["svgd_final"]).max())
+
+
+def test_k3_median_select_and_phi_at_scale():
+    """n = 1500, D = 31 / 63 / 200: radix-select median equals the sorted lower median; phi equals the oracle's closed form."""
+    gen = torch.Generator().manual_seed(5)
+    for D in (31, 63, 200):
+        n = 1500 if D < 100 else 300
+        X = torch.randn(n, D, generator=gen) * 0.8
+        G = torch.randn(n, D, generator=gen)
+        Xd, Gd = X.to(dev()), G.to(dev())
+        ws = E.svgd_workspace(n, D, dev())
+        h = E.svgd_bandwidth(Xd, ws)
+        h_ref = orc.svgd_rbf_h(X.numpy())
+        assert abs(float(h) - float(h_ref)) <= 2e-6 * float(h_ref), (D, float(h), float(h_ref))
+        phi = E.svgd_phi(Xd, Gd, h, 0, n, ws, use_tensor=0)
+        ref = orc.svgd_phi(X.numpy().astype(np.float64), G.numpy().astype(np.float64), float(h), dtype=np.float64)
+        assert rel_err(phi.cpu().numpy(), ref).max() < 1e-5
+        part = E.svgd_phi(Xd, Gd, h, 100, 57, ws, use_tensor=0)          # a rank's row share
+        assert torch.equal(part, phi[100:157])
+
+
+@pytest.mark.parametrize("name", cases.SAMPLER_CASES + cases.BATCHED_SAMPLER_CASES)
+def test_k5_bbb(name):
+    g = load_golden(name)
+    cfg = golden_config(g)
+    m = make_model(name, g, sampler="BBB", bbb_epochs=3, bbb_esamples=5, infer_nsamples=4)
+    spec = spec_from_golden(name, g)
+    D = m.nweights
+    qp0 = np.concatenate([cfg["bbb_init_mean"] + g["bbb_init_noise"], cfg["bbb_init_std"] * np.ones((D, 1), np.float32)], 1).astype(np.float32)
+    qp, acc = t2d(qp0), torch.zeros(D, 2, device=dev())
+    nb = cfg.get("nbatches") or 0
+    batch1 = orc.batch_indices(spec.N_train, 1 % nb, nb) if nb else None
+    elbo_o, grad_o = orc.bbb_elbo_grad(spec, qp0, g["bbb_eps"][0], batch1, dtype=np.float64)
+    W = E.bbb_sample(qp, t2d(g["bbb_eps"][0]))
+    lp, G = m.engine_problem().logpost_grad(W, (1 % nb, nb) if nb else (0, 1), True)
+    gq, elbo = E.bbb_reduce(qp, t2d(g["bbb_eps"][0]), lp, G, 5)
+    assert abs(float(elbo) - g["bbb_elbos"][0]) <= 2e-5 * abs(g["bbb_elbos"][0])
+    assert abs(float(elbo) - elbo_o) <= 1e-5 * abs(elbo_o)
+    assert rel_err(gq.cpu().numpy().T, grad_o.T).max() < 2e-5
+    elbos = [float(m.bbb_epoch(qp, acc, t2d(g["bbb_eps"][ep - 1]), ep, True, k_total=5)) for ep in range(1, 4)]
+    assert abs(elbos[0] - g["bbb_elbos"][0]) <= 2e-5 * abs(g["bbb_elbos"][0])
+    assert np.abs(qp.cpu().numpy() - g["bbb_qparams"]).max() < 5e-3 * max(1.0, np.abs(g["bbb_qparams"]).max())
+
+
+def test_bbb_infer_matches_reference_stream():
+    """With rng='host' a seeded infer() consumes the same torch.randn stream as the reference: same q_params and samples."""
+    name = "cls_vanilla"
+    g = load_golden(name)
+    m = make_model(name, g, sampler="BBB", bbb_epochs=3, bbb_esamples=5, infer_nsamples=4)
+    torch.manual_seed(21)
+    m.infer(verbose=False)
+    assert np.abs(m.q_params.numpy() - g["bbb_qparams"]).max() < 5e-3 * max(1.0, np.abs(g["bbb_qparams"]).max())
+    s, nm = m.all_bayes_samples[-1]
+    assert nm.startswith("bbb_") and s.shape == g["bbb_samples"].shape
+    assert np.abs(s.numpy() - g["bbb_samples"]).max() < 2e-2 * max(1.0, np.abs(g["bbb_samples"]).max())
+    assert abs(m.elbos[0] - g["bbb_elbos"][0]) <= 2e-5 * abs(g["bbb_elbos"][0])
+
+
+def test_full_size_properties():
+    """At the bench scale (M = 65536 chains, W2 shapes) through size-independent properties: replicated chains agree
+    bit-for-bit across the launch, lanes variants agree to fp32 reassociation, energy error of a short trajectory is small."""
+    name = "w2_reg_neg"
+    g = load_golden(name)
+    m = make_model(name, g)
+    cfg = golden_config(g)
+    prob = m.engine_problem()
+    M = 65536
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    base = t2d(g["hmc_q0"])
+    q0 = base[None].repeat(M, 1) + 0.01 * torch.randn(M, base.numel(), device=dev(), generator=gen)
+    q0[M // 2:] = q0[:M // 2]                       # second half replicates the first half
+    p0 = torch.randn(2, M, base.numel(), device=dev(), generator=gen)
+    p0[:, M // 2:] = p0[:, :M // 2]
+    u = torch.rand(2, M, device=dev(), dtype=torch.float64, generator=gen)
+    u[:, M // 2:] = u[:, :M // 2]
+    outs = {}
+    for lanes in (1, 2):
+        q = q0.clone()
+        acc, H, flags = prob.hmc_iterate(q, p0, u, cfg["hmc_epsilon"], 10, True, want_h=True, lanes=lanes)
+        assert int(flags.max()) == 0 and torch.isfinite(q).all()
+        assert torch.equal(q[M // 2:], q[:M // 2]) and torch.equal(acc[:, M // 2:], acc[:, :M // 2])
+        outs[lanes] = (q, H)
+    rel = (outs[1][0] - outs[2][0]).norm(dim=1) / outs[1][0].norm(dim=1)
+    assert float(rel.median()) < 1e-5
+    lp, _ = prob.logpost_grad(q0, (0, 1), True, want_grad=False)
+    assert torch.allclose(-lp, outs[1][1][0, :, 0], rtol=1e-6, atol=1e-3)      # U0 of iteration 0 = -log posterior(q0)
