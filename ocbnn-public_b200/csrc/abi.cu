@@ -190,13 +190,30 @@ extern "C" OCBNN_API int ocbnn_problem_create(const ocbnn_desc* desc, ocbnn_prob
         r[s0 + 1] = 1.f;
         for (int k = 0; k < desc->y_width; ++k) r[s0 + 2 + k] = desc->y_train[n * desc->y_width + k];
     }
-    for (long long c = 0; c < desc->n_cpoints; ++c) {
-        float* r = &pts[(size_t)(desc->n_train + c) * rs];
-        for (int k = 0; k < s0; ++k) r[k] = desc->cx[c * s0 + k];
-        int kind = desc->ckind[c];
-        memcpy(&r[s0], &kind, sizeof(int));
-        r[s0 + 1] = desc->cweight[c];
-        for (int k = 0; k < desc->cparam_stride; ++k) r[s0 + 2 + k] = desc->cparam[c * desc->cparam_stride + k];
+    // constraint rows grouped by head kind (positive | negative | Dirichlet) so that the kernels run one compile-time
+    // head per segment; the order inside a group is the caller's
+    int seg_n[3] = {0, 0, 0};
+    {
+        const int order[3] = {OCBNN_HEAD_POS_GAUSS, OCBNN_HEAD_NEG_EXP, OCBNN_HEAD_DIRICHLET};
+        long long out_row = desc->n_train;
+        for (int sgi = 0; sgi < 3; ++sgi) {
+            for (long long c = 0; c < desc->n_cpoints; ++c) {
+                if (desc->ckind[c] != order[sgi]) continue;
+                float* r = &pts[(size_t)out_row * rs];
+                for (int k = 0; k < s0; ++k) r[k] = desc->cx[c * s0 + k];
+                int kind = desc->ckind[c];
+                memcpy(&r[s0], &kind, sizeof(int));
+                r[s0 + 1] = desc->cweight[c];
+                for (int k = 0; k < desc->cparam_stride; ++k) r[s0 + 2 + k] = desc->cparam[c * desc->cparam_stride + k];
+                ++out_row;
+                ++seg_n[sgi];
+            }
+        }
+        if (out_row != rows) {
+            delete p;
+            set_error("ckind must be OCBNN_HEAD_POS_GAUSS, OCBNN_HEAD_NEG_EXP or OCBNN_HEAD_DIRICHLET for every constraint point");
+            return OCBNN_EINVAL;
+        }
     }
     std::vector<float2> pri((size_t)d);
     for (int i = 0; i < d; ++i) {
@@ -224,6 +241,10 @@ extern "C" OCBNN_API int ocbnn_problem_create(const ocbnn_desc* desc, ocbnn_prob
     a.pri = p->pri;
     a.n_train = desc->n_train;
     a.n_cpoints = desc->n_cpoints;
+    a.n_pos = seg_n[0];
+    a.n_neg = seg_n[1];
+    a.n_dir = seg_n[2];
+    a.lik_head = desc->lik_head;
     a.rs = rs;
     a.s0 = s0;
     a.batch_offset = 0;

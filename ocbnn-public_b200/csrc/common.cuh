@@ -48,6 +48,8 @@ struct EvalArgs {
     const float2* pri;     // D x (mean, 1/var)
     long long n_train;
     int n_cpoints;
+    int n_pos, n_neg, n_dir;   // constraint rows are grouped: positive-Gaussian | negative-exponential | Dirichlet
+    int lik_head;          // OCBNN_HEAD_LIK_* of the training rows
     int rs;                // record stride
     int s0;
     int batch_offset;      // B = {offset, offset+stride, ...}

@@ -1,15 +1,15 @@
 // small_kernels.cuh — K1 (log-posterior + gradient), K2 (fused HMC trajectory + Metropolis-Hastings) and
 // K4 (fused SGLD steps) for the register-resident one-hidden-layer nets.  Included by one .cu per net shape.
 #pragma once
+#include <cstdlib>
 #include "small_net.cuh"
 
 namespace ocbnn {
 
 constexpr int kSmallThreads = 128;
+constexpr int kDefaultHmcMb = 3;
 
-__device__ __forceinline__ void load_pri(float2* pri_s, const EvalArgs& a, int d) {
-    for (int i = threadIdx.x; i < d; i += blockDim.x) pri_s[i] = a.pri[i];
-}
+__host__ __device__ constexpr int kSmemFixedFloats(int ns) { return 4 * ns; }   // float4 prior table per slot
 
 // ---- K1 ------------------------------------------------------------------------------------------------
 template <class N, int G>
@@ -17,26 +17,40 @@ __global__ void __launch_bounds__(kSmallThreads)
 k_logpost_small(EvalArgs a, const float* __restrict__ w, long long m, float* __restrict__ out_lp, float* __restrict__ out_grad,
                 int tile_cap) {
     extern __shared__ __align__(16) float smem[];
-    float2* pri_s = reinterpret_cast<float2*>(smem);
-    float* tab = smem + 2 * ((N::D + 1) & ~1);
+    float4* pri_s = reinterpret_cast<float4*>(smem);
+    float* tab = smem + kSmemFixedFloats(N::NS);
     EvalCtx c = make_ctx(a, tab, pri_s, tile_cap);
-    load_pri(pri_s, a, N::D);
+    load_pri_slots<N>(pri_s, a);
     const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int lane = threadIdx.x % G;
     const bool active = gid < m;
     const long long chain = active ? gid : m - 1;
-    float wv[N::D], g[N::D];
-#pragma unroll
-    for (int i = 0; i < N::D; ++i) wv[i] = __ldg(w + chain * N::D + i);
+    float2 wv[N::NS], g[N::NS];
+    load_state<N>(wv, w + chain * N::D);
     float lp;
     evaluate<N, G>(a, c, /*restage=*/true, wv, g, lp, lane);
     if (active && lane == 0) {
         if (out_lp) out_lp[chain] = lp;
-        if (out_grad) {
-#pragma unroll
-            for (int i = 0; i < N::D; ++i) out_grad[chain * N::D + i] = g[i];
-        }
+        if (out_grad) store_state<N>(g, out_grad + chain * N::D);
     }
+}
+
+template <class N>
+__device__ __forceinline__ float kinetic(const float2 (&p)[N::NS]) {
+    double ks = 0.0;
+#pragma unroll
+    for (int s = 0; s < N::NS; ++s) {
+        const float2 e = __fmul2_rn(p[s], p[s]);
+        ks += (double)e.x + (double)e.y;
+    }
+    return 0.5f * (float)ks;
+}
+// y += fl(c * x), elementwise, two roundings like the reference's `y += c * x` on fp32 tensors
+template <class N>
+__device__ __forceinline__ void axpy_rn(float2 (&y)[N::NS], float c, const float2 (&x)[N::NS]) {
+    const float2 cc = f2(c);
+#pragma unroll
+    for (int s = 0; s < N::NS; ++s) y[s] = __fadd2_rn(y[s], __fmul2_rn(cc, x[s]));
 }
 
 // ---- K2 ------------------------------------------------------------------------------------------------
@@ -44,25 +58,24 @@ k_logpost_small(EvalArgs a, const float* __restrict__ w, long long m, float* __r
 // p -= eps/2 dU;  U1,K1;  accept iff u < exp(U0 - U1 + K0 - K1)  (fp32 exp, float64 compare, strict <).
 // dU = -grad log posterior, so "p -= c*dU" is "p += c*g" with identical rounding (fl(c*g) then one add).
 // The value+gradient at q_L is reused as U0/grad of the next iteration (the reference recomputes both).
-template <class N, int G>
-__global__ void __launch_bounds__(kSmallThreads)
+template <class N, int G, int MB>
+__global__ void __launch_bounds__(kSmallThreads, MB)
 k_hmc_small(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, const double* __restrict__ u, long long m, int n_it,
             float eps, float eps_half, int L, int restore, uint8_t* __restrict__ out_acc, float* __restrict__ out_h,
             int* __restrict__ out_flags, float* __restrict__ out_samples, int thin, int tile_cap) {
     extern __shared__ __align__(16) float smem[];
-    float2* pri_s = reinterpret_cast<float2*>(smem);
-    float* tab = smem + 2 * ((N::D + 1) & ~1);
+    float4* pri_s = reinterpret_cast<float4*>(smem);
+    float* tab = smem + kSmemFixedFloats(N::NS);
     EvalCtx c = make_ctx(a, tab, pri_s, tile_cap);
-    load_pri(pri_s, a, N::D);
+    load_pri_slots<N>(pri_s, a);
     const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int lane = threadIdx.x % G;
     const bool active = gid < m;
     const long long chain = active ? gid : m - 1;
     const bool writer = active && lane == 0;
 
-    float q[N::D], p[N::D], g[N::D];
-#pragma unroll
-    for (int i = 0; i < N::D; ++i) q[i] = q_io[chain * N::D + i];
+    float2 q[N::NS], p[N::NS], g[N::NS];
+    load_state<N>(q, q_io + chain * N::D);
     float lp;
     evaluate<N, G>(a, c, /*restage=*/true, q, g, lp, lane);   // stages the (fixed) point set once
     int nan_flag = 0;
@@ -71,39 +84,25 @@ k_hmc_small(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, 
     for (int it = 0; it < n_it; ++it) {
         if (__any_sync(0xffffffffu, need_eval)) evaluate<N, G>(a, c, false, q, g, lp, lane);
         need_eval = false;
-        const float* pin = p0 + ((long long)it * m + chain) * N::D;
-        double ksum = 0.0;
-#pragma unroll
-        for (int i = 0; i < N::D; ++i) {
-            p[i] = __ldg(pin + i);
-            ksum += (double)(p[i] * p[i]);
-        }
+        load_state<N>(p, p0 + ((long long)it * m + chain) * N::D);
         const float U0 = -lp;
-        const float K0 = 0.5f * (float)ksum;
-        if (restore && writer) {   // keep q0 for a possible restore (scratch: this iteration's slot of out_samples is not used yet)
-#pragma unroll
-            for (int i = 0; i < N::D; ++i) q_io[chain * N::D + i] = q[i];
+        const float K0 = kinetic<N>(p);
+        if (restore) {   // keep q0 for a possible restore
+            if (writer) store_state<N>(q, q_io + chain * N::D);
+            __syncwarp();
         }
-#pragma unroll
-        for (int i = 0; i < N::D; ++i) p[i] = __fadd_rn(p[i], __fmul_rn(eps_half, g[i]));
+        axpy_rn<N>(p, eps_half, g);
         for (int l = 1; l <= L; ++l) {
-#pragma unroll
-            for (int i = 0; i < N::D; ++i) q[i] = __fadd_rn(q[i], __fmul_rn(eps, p[i]));
+            axpy_rn<N>(q, eps, p);
             evaluate<N, G>(a, c, false, q, g, lp, lane);
-            const float e = (l < L) ? eps : eps_half;
-#pragma unroll
-            for (int i = 0; i < N::D; ++i) p[i] = __fadd_rn(p[i], __fmul_rn(e, g[i]));
+            axpy_rn<N>(p, (l < L) ? eps : eps_half, g);
         }
         bool isn = false;
-        ksum = 0.0;
 #pragma unroll
-        for (int i = 0; i < N::D; ++i) {
-            isn |= isnan(q[i]);
-            ksum += (double)(p[i] * p[i]);
-        }
+        for (int s = 0; s < N::NS; ++s) isn |= isnan(q[s].x) | isnan(q[s].y);
         nan_flag |= isn ? 1 : 0;
         const float U1 = -lp;
-        const float K1 = 0.5f * (float)ksum;
+        const float K1 = kinetic<N>(p);
         const float dH = __fsub_rn(__fadd_rn(__fsub_rn(U0, U1), K0), K1);
         const double alpha = (double)expf(dH);
         const double ui = __ldg(u + (long long)it * m + chain);
@@ -113,20 +112,14 @@ k_hmc_small(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, 
             if (out_h) reinterpret_cast<float4*>(out_h)[(long long)it * m + chain] = make_float4(U0, K0, U1, K1);
         }
         if (restore && !acc) {
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < N::D; ++i) q[i] = q_io[chain * N::D + i];
+            load_state<N>(q, q_io + chain * N::D);
             need_eval = true;
         }
-        if (out_samples && thin > 0 && ((it + 1) % thin == 0) && writer) {
-            float* dst = out_samples + ((long long)((it + 1) / thin - 1) * m + chain) * N::D;
-#pragma unroll
-            for (int i = 0; i < N::D; ++i) dst[i] = q[i];
-        }
+        if (out_samples && thin > 0 && ((it + 1) % thin == 0) && writer)
+            store_state<N>(q, out_samples + ((long long)((it + 1) / thin - 1) * m + chain) * N::D);
     }
     if (writer) {
-#pragma unroll
-        for (int i = 0; i < N::D; ++i) q_io[chain * N::D + i] = q[i];
+        store_state<N>(q, q_io + chain * N::D);
         if (out_flags) out_flags[chain] = nan_flag;
     }
 }
@@ -138,17 +131,16 @@ __global__ void __launch_bounds__(kSmallThreads)
 k_sgld_small(EvalArgs a, float* __restrict__ w_io, const float* __restrict__ noise, const float* __restrict__ half_eps,
              const int* __restrict__ offsets, long long m, int t_steps, float* __restrict__ out_samples, int thin, int tile_cap) {
     extern __shared__ __align__(16) float smem[];
-    float2* pri_s = reinterpret_cast<float2*>(smem);
-    float* tab = smem + 2 * ((N::D + 1) & ~1);
-    load_pri(pri_s, a, N::D);
+    float4* pri_s = reinterpret_cast<float4*>(smem);
+    float* tab = smem + kSmemFixedFloats(N::NS);
+    load_pri_slots<N>(pri_s, a);
     const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int lane = threadIdx.x % G;
     const bool active = gid < m;
     const long long chain = active ? gid : m - 1;
     const bool writer = active && lane == 0;
-    float w[N::D], g[N::D];
-#pragma unroll
-    for (int i = 0; i < N::D; ++i) w[i] = w_io[chain * N::D + i];
+    float2 w[N::NS], g[N::NS], nz[N::NS];
+    load_state<N>(w, w_io + chain * N::D);
     const bool batched = a.batch_stride > 1;
     EvalCtx c = make_ctx(a, tab, pri_s, tile_cap);
     for (int t = 0; t < t_steps; ++t) {
@@ -158,23 +150,14 @@ k_sgld_small(EvalArgs a, float* __restrict__ w_io, const float* __restrict__ noi
         }
         float lp;
         evaluate<N, G>(a, c, /*restage=*/batched || t == 0, w, g, lp, lane);
-        const float he = half_eps[t];
-        const float* nz = noise + ((long long)t * m + chain) * N::D;
+        const float2 he = f2(half_eps[t]);
+        load_state<N>(nz, noise + ((long long)t * m + chain) * N::D);
 #pragma unroll
-        for (int i = 0; i < N::D; ++i) {
-            float upd = __fadd_rn(__fmul_rn(g[i], he), __ldg(nz + i));
-            w[i] = __fadd_rn(w[i], upd);
-        }
-        if (out_samples && thin > 0 && ((t + 1) % thin == 0) && writer) {
-            float* dst = out_samples + ((long long)((t + 1) / thin - 1) * m + chain) * N::D;
-#pragma unroll
-            for (int i = 0; i < N::D; ++i) dst[i] = w[i];
-        }
+        for (int s = 0; s < N::NS; ++s) w[s] = __fadd2_rn(w[s], __fadd2_rn(__fmul2_rn(g[s], he), nz[s]));
+        if (out_samples && thin > 0 && ((t + 1) % thin == 0) && writer)
+            store_state<N>(w, out_samples + ((long long)((t + 1) / thin - 1) * m + chain) * N::D);
     }
-    if (writer) {
-#pragma unroll
-        for (int i = 0; i < N::D; ++i) w_io[chain * N::D + i] = w[i];
-    }
+    if (writer) store_state<N>(w, w_io + chain * N::D);
 }
 
 // ---- forward (predict) -----------------------------------------------------------------------------------
@@ -183,9 +166,8 @@ __global__ void __launch_bounds__(kSmallThreads)
 k_forward_small(const float* __restrict__ w, long long m, const float* __restrict__ x, long long npts, float* __restrict__ out) {
     const long long chain = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (chain >= m) return;
-    float wv[N::D];
-#pragma unroll
-    for (int i = 0; i < N::D; ++i) wv[i] = __ldg(w + chain * N::D + i);
+    float2 wv[N::NS];
+    load_state<N>(wv, w + chain * N::D);
     for (long long j = 0; j < npts; ++j) {
         float xv[N::S0], f[N::SK];
 #pragma unroll
@@ -200,7 +182,7 @@ k_forward_small(const float* __restrict__ w, long long m, const float* __restric
 template <class N>
 struct SmallLaunch {
     static size_t smem_bytes(const Problem& p, int npts, int& tile_cap) {
-        size_t fixed = sizeof(float) * 2 * ((N::D + 1) & ~1);
+        size_t fixed = sizeof(float) * kSmemFixedFloats(N::NS);
         int cap = (int)((kMaxSmemTable - fixed) / (sizeof(float) * p.rs));
         tile_cap = npts < cap ? (npts > 0 ? npts : 1) : cap;
         return fixed + sizeof(float) * (size_t)tile_cap * p.rs;
@@ -220,18 +202,27 @@ struct SmallLaunch {
         OCBNN_LAUNCH_CHECK();
         return OCBNN_OK;
     }
-    template <int G>
-    static int hmc(const Problem& p, const EvalArgs& a, float* q, const float* p0, const double* u, long long m, int n_it, float eps,
-                   float eps_half, int L, int restore, uint8_t* acc, float* h, int* flags, float* samples, int thin, cudaStream_t st) {
+    template <int G, int MB>
+    static int hmc_mb(const Problem& p, const EvalArgs& a, float* q, const float* p0, const double* u, long long m, int n_it, float eps,
+                      float eps_half, int L, int restore, uint8_t* acc, float* h, int* flags, float* samples, int thin, cudaStream_t st) {
         int tile_cap;
         size_t sm = smem_bytes(p, npts(a), tile_cap);
-        auto k = k_hmc_small<N, G>;
+        auto k = k_hmc_small<N, G, MB>;
         OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         long long blocks = (m * G + kSmallThreads - 1) / kSmallThreads;
         k<<<(unsigned)blocks, kSmallThreads, sm, st>>>(a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin,
                                                        tile_cap);
         OCBNN_LAUNCH_CHECK();
         return OCBNN_OK;
+    }
+    // MB = resident CTAs per SM the kernel is compiled for (register cap 65536/(128*MB)); tuning knob OCBNN_HMC_MB
+    template <int G>
+    static int hmc(const Problem& p, const EvalArgs& a, float* q, const float* p0, const double* u, long long m, int n_it, float eps,
+                   float eps_half, int L, int restore, uint8_t* acc, float* h, int* flags, float* samples, int thin, cudaStream_t st) {
+        static const int mb = [] { const char* e = getenv("OCBNN_HMC_MB"); return e ? atoi(e) : kDefaultHmcMb; }();
+        if (mb == 2) return hmc_mb<G, 2>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
+        if (mb == 4) return hmc_mb<G, 4>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
+        return hmc_mb<G, 3>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
     }
     template <int G>
     static int sgld(const Problem& p, const EvalArgs& a, float* w, const float* noise, const float* he, const int* offs, long long m,

@@ -2,8 +2,16 @@
 // [2,10,3], [2,10,1]): every chain keeps its packed weight vector, momentum and gradient in registers;
 // training points and constraint points are staged once in shared memory and streamed through.
 //
-// G lanes cooperate on one chain: lane r evaluates points r, r+G, ... and the partial gradients are combined
-// with a warp-shuffle butterfly, so that 4096 chains (G=16..32) and 10^6 chains (G=1) both fill the GPU.
+// B200 specifics:
+//   * all per-weight state lives in float2 register pairs (two adjacent hidden units per pair) and the MLP
+//     forward/backward, the leapfrog update and the kinetic energy use the packed fp32x2 instructions of
+//     sm_100 (FFMA2/FMUL2/FADD2): half the issue slots of scalar code on the fma pipe;
+//   * exp(-z^2) is one FMUL2 + two MUFU.EX2 (ex2.approx, 2^-22 relative error), reciprocals are MUFU.RCP;
+//   * points are grouped by head kind (likelihood | positive | negative | Dirichlet rows), so every inner
+//     loop has a compile-time head and no per-point dispatch;
+//   * G lanes cooperate on one chain: lane r evaluates points r, r+G, ... and the partial gradients are
+//     combined with a warp-shuffle butterfly, so that 4096 chains (G=8..32) and 10^6 chains (G=1) both fill
+//     the 148 SMs.
 //
 // Replaces forward/_unpack_layers/_nonlinearity (bnn/base.py:72-104), the heads (heads.cuh) and the autograd
 // backward pass that follows every log_posterior() in bnn/inference.py.
@@ -12,93 +20,233 @@
 
 namespace ocbnn {
 
+// Slot layout (float2 slots): W1 pairs over h for every input d | b1 pairs | W2 pairs over h for every output k | b2 pairs.
 template <int S0_, int H_, int SK_, int ACT_>
 struct Net1 {
     static constexpr int S0 = S0_, H = H_, SK = SK_, ACT = ACT_;
-    static constexpr int OW1 = 0, OB1 = S0 * H, OW2 = OB1 + H, OB2 = OW2 + H * SK, D = OB2 + SK;
+    static constexpr int HP = (H + 1) / 2, SKP = (SK + 1) / 2;
+    static constexpr int SW1 = 0, SB1 = S0 * HP, SW2 = SB1 + HP, SB2 = SW2 + SK * HP, NS = SB2 + SKP;
+    static constexpr int D = S0 * H + H + H * SK + SK;
+    // index into the packed (reference) layout of element e (0/1) of slot s; -1 for padding
+    __host__ __device__ static constexpr int cidx(int s, int e) {
+        if (s < SB1) {
+            int d = s / HP, h = 2 * (s % HP) + e;
+            return h < H ? d * H + h : -1;
+        }
+        if (s < SW2) {
+            int h = 2 * (s - SB1) + e;
+            return h < H ? S0 * H + h : -1;
+        }
+        if (s < SB2) {
+            int k = (s - SW2) / HP, h = 2 * ((s - SW2) % HP) + e;
+            return h < H ? S0 * H + H + h * SK + k : -1;
+        }
+        int k = 2 * (s - SB2) + e;
+        return k < SK ? S0 * H + H + H * SK + k : -1;
+    }
 };
 
-template <int ACT>
-__device__ __forceinline__ float act_fwd(float z) {
-    if (ACT == OCBNN_ACT_RBF) return expf(-z * z);      // base.py:84
-    if (ACT == OCBNN_ACT_RELU) return fmaxf(z, 0.f);    // base.py:86
-    return z;
+template <class N>
+__device__ __forceinline__ void load_state(float2 (&v)[N::NS], const float* __restrict__ src) {
+#pragma unroll
+    for (int s = 0; s < N::NS; ++s) {
+        v[s].x = N::cidx(s, 0) >= 0 ? __ldg(src + N::cidx(s, 0)) : 0.f;
+        v[s].y = N::cidx(s, 1) >= 0 ? __ldg(src + N::cidx(s, 1)) : 0.f;
+    }
 }
-template <int ACT>
-__device__ __forceinline__ float act_bwd(float z, float a) {
-    if (ACT == OCBNN_ACT_RBF) return a * (-2.f * z);
-    if (ACT == OCBNN_ACT_RELU) return z > 0.f ? 1.f : 0.f;
-    return 1.f;
+template <class N>
+__device__ __forceinline__ void store_state(const float2 (&v)[N::NS], float* __restrict__ dst) {
+#pragma unroll
+    for (int s = 0; s < N::NS; ++s) {
+        if (N::cidx(s, 0) >= 0) dst[N::cidx(s, 0)] = v[s].x;
+        if (N::cidx(s, 1) >= 0) dst[N::cidx(s, 1)] = v[s].y;
+    }
 }
 
-// value + gradient contribution of ONE point record
-template <class N>
-__device__ __forceinline__ void point_eval(const float (&w)[N::D], float (&g)[N::D], double& lp, const float* __restrict__ rec,
-                                           const HeadConsts& hc) {
-    float x[N::S0];
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+
+// activation on a pair; returns a and m = da/dz
+template <int ACT>
+__device__ __forceinline__ void act_pair(float2 z, float2& a, float2& m) {
+    if (ACT == OCBNN_ACT_RBF) {                       // exp(-z^2), base.py:84 ; d/dz = -2 z a
+        float2 t = __fmul2_rn(z, z);
+        float2 u = __fmul2_rn(t, f2(-1.4426950408889634f));
+        a = make_float2(ex2_approx(u.x), ex2_approx(u.y));
+        m = __fmul2_rn(__fmul2_rn(z, f2(-2.f)), a);
+    } else if (ACT == OCBNN_ACT_RELU) {               // max(z,0), base.py:86
+        a = make_float2(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f));
+        m = make_float2(z.x > 0.f ? 1.f : 0.f, z.y > 0.f ? 1.f : 0.f);
+    } else {
+        a = z;
+        m = f2(1.f);
+    }
+}
+
+// ---- fast heads for the register kernels (same formulas as heads.cuh, MUFU approximations) ----------------------
+struct FastConsts {
+    float2 tau_l2e;      // 2*tau_i*log2(e)
+    float2 tau2;         // 2*tau_i
+    float lik_scale, pos_inv_var;
+};
+
+// Phi(z) = 1/((1+e^{2 tau0 z})(1+e^{2 tau1 z})) and dPhi/dz (see heads.cuh); exponent clamped at 2^57.7 ~ e^40
+__device__ __forceinline__ void phi_fast(float z, const FastConsts& c, float& P, float& dP) {
+    float2 u = __fmul2_rn(f2(z), c.tau_l2e);
+    float2 e = make_float2(ex2_approx(fminf(u.x, 57.7f)), ex2_approx(fminf(u.y, 57.7f)));
+    float2 ab = __fadd2_rn(e, f2(1.f));
+    float r = rcp_approx(ab.x * ab.y);
+    float2 t = __fmul2_rn(e, c.tau2);
+    float s = fmaf(t.x, ab.y, t.y * ab.x);
+    P = r;
+    dP = -(r * r) * s;
+}
+
+template <int KIND, int SK>
+struct FastHead;
+
+template <int SK>
+struct FastHead<OCBNN_HEAD_LIK_GAUSS, SK> {
+    static __device__ __forceinline__ void run(const float (&f)[SK], const float* __restrict__ prm, const FastConsts& c, float& val, float (&df)[SK]) {
+        val = 0.f;
 #pragma unroll
-    for (int d = 0; d < N::S0; ++d) x[d] = rec[d];
-    const int kind = __float_as_int(rec[N::S0]);
+        for (int k = 0; k < SK; ++k) {
+            float r = f[k] - prm[k];
+            val = fmaf(-r * r, c.lik_scale, val);
+            df[k] = -2.f * c.lik_scale * r;
+        }
+    }
+};
+template <int SK>
+struct FastHead<OCBNN_HEAD_NEG_EXP, SK> {
+    static __device__ __forceinline__ void run(const float (&f)[SK], const float* __restrict__ prm, const FastConsts& c, float& val, float (&df)[SK]) {
+        const int ngaps = (int)prm[0];
+        val = 0.f;
+        float d = 0.f;
+        for (int k = 0; k < ngaps; ++k) {
+            const float a = prm[1 + 2 * k], b = prm[2 + 2 * k];
+            float P1 = 1.f, D1 = 0.f, P2 = 1.f, D2 = 0.f;
+            if (a > -INFINITY) phi_fast(a - f[0], c, P1, D1);
+            if (b < INFINITY) phi_fast(f[0] - b, c, P2, D2);
+            val = fmaf(P1, P2, val);
+            d += P1 * D2 - D1 * P2;
+        }
+#pragma unroll
+        for (int k = 0; k < SK; ++k) df[k] = 0.f;
+        df[0] = d;
+    }
+};
+template <int SK>
+struct FastHead<OCBNN_HEAD_POS_GAUSS, SK> {
+    static __device__ __forceinline__ void run(const float (&f)[SK], const float* __restrict__ prm, const FastConsts& c, float& val, float (&df)[SK]) {
+        HeadConsts hc;
+        hc.pos_inv_var = c.pos_inv_var;
+#pragma unroll
+        for (int k = 0; k < SK; ++k) df[k] = 0.f;
+        head_pos_gauss(f[0], prm, hc, val, df[0]);
+    }
+};
+template <int SK>
+struct FastHead<OCBNN_HEAD_DIRICHLET, SK> {
+    static __device__ __forceinline__ void run(const float (&f)[SK], const float* __restrict__ prm, const FastConsts&, float& val, float (&df)[SK]) {
+        head_dirichlet<SK>(f, prm, val, df);
+    }
+};
+template <int SK>
+struct FastHead<OCBNN_HEAD_LIK_SOFTMAX, SK> {
+    static __device__ __forceinline__ void run(const float (&f)[SK], const float* __restrict__ prm, const FastConsts&, float& val, float (&df)[SK]) {
+        head_lik_softmax<SK>(f, prm, val, df);
+    }
+};
+template <int SK>
+struct FastHead<OCBNN_HEAD_LIK_BERNOULLI, SK> {
+    static __device__ __forceinline__ void run(const float (&f)[SK], const float* __restrict__ prm, const FastConsts&, float& val, float (&df)[SK]) {
+#pragma unroll
+        for (int k = 0; k < SK; ++k) df[k] = 0.f;
+        head_lik_bernoulli(f[0], prm, val, df[0]);
+    }
+};
+
+// value + gradient contribution of ONE point record with a compile-time head
+template <class N, int KIND>
+__device__ __forceinline__ void point_eval(const float2 (&w)[N::NS], float2 (&g)[N::NS], double& lp, const float* __restrict__ rec,
+                                           const FastConsts& fc) {
+    float2 xx[N::S0];
+#pragma unroll
+    for (int d = 0; d < N::S0; ++d) xx[d] = f2(rec[d]);
     const float wgt = rec[N::S0 + 1];
 
-    float z[N::H], a[N::H];
+    float2 a[N::HP], m[N::HP], facc[N::SK];
 #pragma unroll
-    for (int h = 0; h < N::H; ++h) {
-        float s = w[N::OB1 + h];
+    for (int k = 0; k < N::SK; ++k) facc[k] = f2(0.f);
 #pragma unroll
-        for (int d = 0; d < N::S0; ++d) s = fmaf(w[N::OW1 + d * N::H + h], x[d], s);
-        z[h] = s;
-        a[h] = act_fwd<N::ACT>(s);
+    for (int hp = 0; hp < N::HP; ++hp) {
+        float2 z = w[N::SB1 + hp];
+#pragma unroll
+        for (int d = 0; d < N::S0; ++d) z = __ffma2_rn(w[N::SW1 + d * N::HP + hp], xx[d], z);
+        act_pair<N::ACT>(z, a[hp], m[hp]);
+#pragma unroll
+        for (int k = 0; k < N::SK; ++k) facc[k] = __ffma2_rn(w[N::SW2 + k * N::HP + hp], a[hp], facc[k]);
     }
     float f[N::SK];
 #pragma unroll
     for (int k = 0; k < N::SK; ++k) {
-        float s = w[N::OB2 + k];
-#pragma unroll
-        for (int h = 0; h < N::H; ++h) s = fmaf(w[N::OW2 + h * N::SK + k], a[h], s);
-        f[k] = s;
+        const float b2 = (k & 1) ? w[N::SB2 + k / 2].y : w[N::SB2 + k / 2].x;
+        f[k] = (facc[k].x + facc[k].y) + b2;
     }
     float val, df[N::SK];
-    eval_head<N::SK>(kind, f, rec + N::S0 + 2, hc, val, df);
+    FastHead<KIND, N::SK>::run(f, rec + N::S0 + 2, fc, val, df);
     lp += (double)(wgt * val);
 #pragma unroll
     for (int k = 0; k < N::SK; ++k) {
         df[k] *= wgt;
-        g[N::OB2 + k] += df[k];
+        if (k & 1) g[N::SB2 + k / 2].y += df[k]; else g[N::SB2 + k / 2].x += df[k];
     }
 #pragma unroll
-    for (int h = 0; h < N::H; ++h) {
-        float da = 0.f;
+    for (int hp = 0; hp < N::HP; ++hp) {
+        float2 da = f2(0.f);
 #pragma unroll
         for (int k = 0; k < N::SK; ++k) {
-            da = fmaf(df[k], w[N::OW2 + h * N::SK + k], da);
-            g[N::OW2 + h * N::SK + k] = fmaf(df[k], a[h], g[N::OW2 + h * N::SK + k]);
+            const float2 dk = f2(df[k]);
+            da = __ffma2_rn(dk, w[N::SW2 + k * N::HP + hp], da);
+            g[N::SW2 + k * N::HP + hp] = __ffma2_rn(dk, a[hp], g[N::SW2 + k * N::HP + hp]);
         }
-        float dz = da * act_bwd<N::ACT>(z[h], a[h]);
-        g[N::OB1 + h] += dz;
+        const float2 dz = __fmul2_rn(da, m[hp]);
+        g[N::SB1 + hp] = __fadd2_rn(g[N::SB1 + hp], dz);
 #pragma unroll
-        for (int d = 0; d < N::S0; ++d) g[N::OW1 + d * N::H + h] = fmaf(dz, x[d], g[N::OW1 + d * N::H + h]);
+        for (int d = 0; d < N::S0; ++d) g[N::SW1 + d * N::HP + hp] = __ffma2_rn(dz, xx[d], g[N::SW1 + d * N::HP + hp]);
     }
 }
 
-// forward only (predict path)
+// forward only (predict path), scalar
 template <class N>
-__device__ __forceinline__ void point_forward(const float (&w)[N::D], const float* __restrict__ x, float (&f)[N::SK]) {
-    float a[N::H];
+__device__ __forceinline__ void point_forward(const float2 (&w)[N::NS], const float* __restrict__ x, float (&f)[N::SK]) {
+    float2 facc[N::SK];
 #pragma unroll
-    for (int h = 0; h < N::H; ++h) {
-        float s = w[N::OB1 + h];
+    for (int k = 0; k < N::SK; ++k) facc[k] = f2(0.f);
 #pragma unroll
-        for (int d = 0; d < N::S0; ++d) s = fmaf(w[N::OW1 + d * N::H + h], x[d], s);
-        a[h] = act_fwd<N::ACT>(s);
+    for (int hp = 0; hp < N::HP; ++hp) {
+        float2 z = w[N::SB1 + hp];
+#pragma unroll
+        for (int d = 0; d < N::S0; ++d) z = __ffma2_rn(w[N::SW1 + d * N::HP + hp], f2(x[d]), z);
+        float2 a;
+        if (N::ACT == OCBNN_ACT_RBF) a = make_float2(expf(-z.x * z.x), expf(-z.y * z.y));      // accurate exp on the predict path
+        else if (N::ACT == OCBNN_ACT_RELU) a = make_float2(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f));
+        else a = z;
+#pragma unroll
+        for (int k = 0; k < N::SK; ++k) facc[k] = __ffma2_rn(w[N::SW2 + k * N::HP + hp], a, facc[k]);
     }
 #pragma unroll
-    for (int k = 0; k < N::SK; ++k) {
-        float s = w[N::OB2 + k];
-#pragma unroll
-        for (int h = 0; h < N::H; ++h) s = fmaf(w[N::OW2 + h * N::SK + k], a[h], s);
-        f[k] = s;
-    }
+    for (int k = 0; k < N::SK; ++k) f[k] = (facc[k].x + facc[k].y) + ((k & 1) ? w[N::SB2 + k / 2].y : w[N::SB2 + k / 2].x);
 }
 
 // ---- staging of point records into shared memory -----------------------------------------------------
@@ -120,21 +268,27 @@ __device__ __forceinline__ void stage_points(float* __restrict__ tab, const Eval
 
 struct EvalCtx {
     float* tab;            // shared: staged records (tile_cap x rs)
-    const float2* pri;     // shared: D x (mean, 1/var)
+    const float4* pri;     // shared: per slot (mean.x, mean.y, 1/var.x, 1/var.y)   [register kernels]
     int nb;                // training points in this evaluation
     int npts;              // nb + constraint points
+    int seg_end[4];        // end (exclusive) of the likelihood | positive | negative | Dirichlet rows in evaluation order
     int tile_cap;          // records that fit in `tab`
     float mult;            // N/|B|
     double lp_const;
     HeadConsts hc;
+    FastConsts fc;
 };
 
-__device__ __forceinline__ EvalCtx make_ctx(const EvalArgs& a, float* tab, const float2* pri, int tile_cap) {
+__device__ __forceinline__ EvalCtx make_ctx(const EvalArgs& a, float* tab, const float4* pri, int tile_cap) {
     EvalCtx c;
     c.tab = tab;
     c.pri = pri;
     c.nb = a.with_data ? batch_count(a.n_train, a.batch_offset, a.batch_stride) : 0;
     c.npts = c.nb + a.n_cpoints;
+    c.seg_end[0] = c.nb;
+    c.seg_end[1] = c.seg_end[0] + a.n_pos;
+    c.seg_end[2] = c.seg_end[1] + a.n_neg;
+    c.seg_end[3] = c.seg_end[2] + a.n_dir;
     c.tile_cap = tile_cap;
     c.mult = (a.with_data && a.batch_stride > 1) ? (float)((double)a.n_train / (double)c.nb) : 1.f;
     c.lp_const = a.const_prior + (a.with_data ? a.const_lik : 0.0);
@@ -142,44 +296,89 @@ __device__ __forceinline__ EvalCtx make_ctx(const EvalArgs& a, float* tab, const
     c.hc.tau0x2 = 2.f * a.tau0;
     c.hc.tau1x2 = 2.f * a.tau1;
     c.hc.pos_inv_var = a.pos_inv_var;
+    c.fc.tau2 = make_float2(2.f * a.tau0, 2.f * a.tau1);
+    c.fc.tau_l2e = make_float2(2.f * a.tau0 * 1.4426950408889634f, 2.f * a.tau1 * 1.4426950408889634f);
+    c.fc.lik_scale = a.lik_scale;
+    c.fc.pos_inv_var = a.pos_inv_var;
     return c;
+}
+
+// prior table in slot order
+template <class N>
+__device__ __forceinline__ void load_pri_slots(float4* pri_s, const EvalArgs& a) {
+    for (int s = threadIdx.x; s < N::NS; s += blockDim.x) {
+        int i0 = N::cidx(s, 0), i1 = N::cidx(s, 1);
+        float2 m0 = i0 >= 0 ? a.pri[i0] : make_float2(0.f, 0.f);
+        float2 m1 = i1 >= 0 ? a.pri[i1] : make_float2(0.f, 0.f);
+        pri_s[s] = make_float4(m0.x, m1.x, m0.y, m1.y);
+    }
+}
+
+template <class N, int G, int KIND>
+__device__ __forceinline__ void eval_segment(const EvalCtx& c, int rs, int lo, int hi, const float2 (&w)[N::NS], float2 (&g)[N::NS],
+                                             double& lp, int lane) {
+    for (int j = lo + lane; j < hi; j += G) point_eval<N, KIND>(w, g, lp, c.tab + j * rs, c.fc);
 }
 
 // log posterior value and gradient at w.  Block-uniform control flow (contains __syncthreads when the point set
 // does not fit one tile or `restage` is set).  On return every lane of the group holds the full g and lp.
 template <class N, int G>
-__device__ __forceinline__ void evaluate(const EvalArgs& a, const EvalCtx& c, bool restage, const float (&w)[N::D], float (&g)[N::D],
+__device__ __forceinline__ void evaluate(const EvalArgs& a, const EvalCtx& c, bool restage, const float2 (&w)[N::NS], float2 (&g)[N::NS],
                                          float& lp_out, int lane) {
 #pragma unroll
-    for (int i = 0; i < N::D; ++i) g[i] = 0.f;
+    for (int s = 0; s < N::NS; ++s) g[s] = f2(0.f);
     double lp = 0.0;
     const bool multi = c.npts > c.tile_cap;
     for (int begin = 0; begin < c.npts; begin += c.tile_cap) {
-        int count = min(c.tile_cap, c.npts - begin);
+        const int count = min(c.tile_cap, c.npts - begin);
         if (multi || restage) {
             __syncthreads();
             stage_points(c.tab, a, c.nb, c.mult, begin, count);
             __syncthreads();
         }
-        for (int j = lane; j < count; j += G) point_eval<N>(w, g, lp, c.tab + j * a.rs, c.hc);
+        int seg_lo = 0;
+#pragma unroll
+        for (int sg = 0; sg < 4; ++sg) {
+            const int lo = max(seg_lo, begin) - begin, hi = min(c.seg_end[sg], begin + count) - begin;
+            seg_lo = c.seg_end[sg];
+            if (lo >= hi) continue;
+            if (sg == 0) {
+                if (a.lik_head == OCBNN_HEAD_LIK_GAUSS) eval_segment<N, G, OCBNN_HEAD_LIK_GAUSS>(c, a.rs, lo, hi, w, g, lp, lane);
+                else if (a.lik_head == OCBNN_HEAD_LIK_SOFTMAX) eval_segment<N, G, OCBNN_HEAD_LIK_SOFTMAX>(c, a.rs, lo, hi, w, g, lp, lane);
+                else eval_segment<N, G, OCBNN_HEAD_LIK_BERNOULLI>(c, a.rs, lo, hi, w, g, lp, lane);
+            } else if (sg == 1) {
+                eval_segment<N, G, OCBNN_HEAD_POS_GAUSS>(c, a.rs, lo, hi, w, g, lp, lane);
+            } else if (sg == 2) {
+                eval_segment<N, G, OCBNN_HEAD_NEG_EXP>(c, a.rs, lo, hi, w, g, lp, lane);
+            } else {
+                eval_segment<N, G, OCBNN_HEAD_DIRICHLET>(c, a.rs, lo, hi, w, g, lp, lane);
+            }
+        }
     }
     if (G > 1) {
 #pragma unroll
         for (int off = G / 2; off > 0; off >>= 1) {
 #pragma unroll
-            for (int i = 0; i < N::D; ++i) g[i] += __shfl_xor_sync(0xffffffffu, g[i], off);
+            for (int s = 0; s < N::NS; ++s) {
+                g[s].x += __shfl_xor_sync(0xffffffffu, g[s].x, off);
+                g[s].y += __shfl_xor_sync(0xffffffffu, g[s].y, off);
+            }
             lp += __shfl_xor_sync(0xffffffffu, lp, off);
         }
     }
-    // Gaussian prior over the weights (isotropic, or the AOCP diagonal Gaussian): base.py:106-133
+    // Gaussian prior over the weights (isotropic, or the AOCP diagonal Gaussian): base.py:106-133.
+    // Padding slots have 1/var = 0 and are masked so that they never move.
     double pr = 0.0;
 #pragma unroll
-    for (int i = 0; i < N::D; ++i) {
-        float2 mv = c.pri[i];
-        float diff = w[i] - mv.x;
-        float t = diff * mv.y;
-        g[i] -= t;
-        pr += (double)(diff * t);
+    for (int s = 0; s < N::NS; ++s) {
+        const float4 mv = c.pri[s];
+        const float2 diff = __fadd2_rn(w[s], make_float2(-mv.x, -mv.y));
+        const float2 t = __fmul2_rn(diff, make_float2(mv.z, mv.w));
+        g[s] = __fadd2_rn(g[s], make_float2(-t.x, -t.y));
+        const float2 e = __fmul2_rn(diff, t);
+        pr += (double)e.x + (double)e.y;
+        if (N::cidx(s, 0) < 0) g[s].x = 0.f;
+        if (N::cidx(s, 1) < 0) g[s].y = 0.f;
     }
     lp += c.lp_const - 0.5 * pr;
     lp_out = (float)lp;
