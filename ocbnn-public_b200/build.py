@@ -19,6 +19,8 @@ LIB = os.path.join(HERE, "ocbnn_b200", "libocbnn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+if os.environ.get("OCBNN_POINT_UNROLL"):      # tuning knob: points evaluated per loop trip in the register kernels
+    FLAGS += [f"-DOCBNN_POINT_UNROLL={int(os.environ['OCBNN_POINT_UNROLL'])}"]
 
 
 def _newer(src, dst, deps):

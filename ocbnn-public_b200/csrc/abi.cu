@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <vector>
 #include "common.cuh"
@@ -173,8 +174,8 @@ extern "C" OCBNN_API int ocbnn_problem_create(const ocbnn_desc* desc, ocbnn_prob
     int d = 0;
     for (int l = 1; l <= desc->n_layers; ++l) d += (desc->layer_sizes[l - 1] + 1) * desc->layer_sizes[l];
     p->d = d;
-    int np = desc->y_width > desc->cparam_stride ? desc->y_width : desc->cparam_stride;
-    if (np < 1) np = 1;
+    int np = desc->y_width > desc->cparam_stride + 1 ? desc->y_width : desc->cparam_stride + 1;   // +1: internal NEG_EXP layout
+    if (np < 2) np = 2;
     int rs = s0 + 2 + np;
     if ((rs & 1) == 0) ++rs;
     p->rs = rs;
@@ -204,7 +205,33 @@ extern "C" OCBNN_API int ocbnn_problem_create(const ocbnn_desc* desc, ocbnn_prob
                 int kind = desc->ckind[c];
                 memcpy(&r[s0], &kind, sizeof(int));
                 r[s0 + 1] = desc->cweight[c];
-                for (int k = 0; k < desc->cparam_stride; ++k) r[s0 + 2 + k] = desc->cparam[c * desc->cparam_stride + k];
+                const float* src = desc->cparam_stride ? desc->cparam + c * desc->cparam_stride : nullptr;
+                if (kind == OCBNN_HEAD_NEG_EXP) {
+                    // ABI: ngaps, (a,b)...  ->  internal: n1, n2, one-sided (c, s) terms, two-sided (a, b) terms
+                    const int ngaps = src ? (int)src[0] : 0;
+                    if (ngaps < 0 || 1 + 2 * ngaps > desc->cparam_stride) {
+                        delete p;
+                        set_error("constraint point %lld: gap count %d does not fit cparam_stride %d", c, ngaps, desc->cparam_stride);
+                        return OCBNN_EINVAL;
+                    }
+                    float* dst = &r[s0 + 2];
+                    int n1 = 0, n2 = 0;
+                    float* w1 = dst + 2;
+                    for (int k = 0; k < ngaps; ++k) {
+                        const float a = src[1 + 2 * k], b = src[2 + 2 * k];
+                        if (std::isinf(a) && a < 0) { w1[2 * n1] = b; w1[2 * n1 + 1] = 1.f; ++n1; }        // Phi(f - b)
+                        else if (std::isinf(b) && b > 0) { w1[2 * n1] = a; w1[2 * n1 + 1] = -1.f; ++n1; }  // Phi(a - f)
+                    }
+                    float* w2 = dst + 2 + 2 * n1;
+                    for (int k = 0; k < ngaps; ++k) {
+                        const float a = src[1 + 2 * k], b = src[2 + 2 * k];
+                        if (!(std::isinf(a) && a < 0) && !(std::isinf(b) && b > 0)) { w2[2 * n2] = a; w2[2 * n2 + 1] = b; ++n2; }
+                    }
+                    memcpy(&dst[0], &n1, sizeof(int));
+                    memcpy(&dst[1], &n2, sizeof(int));
+                } else {
+                    for (int k = 0; k < desc->cparam_stride; ++k) r[s0 + 2 + k] = src[k];
+                }
                 ++out_row;
                 ++seg_n[sgi];
             }

@@ -24,16 +24,24 @@ __device__ __forceinline__ void phi_classifier(float z, const HeadConsts& c, flo
     dP = -(r * r) * (c.tau0x2 * e0 * B + c.tau1x2 * e1 * A);
 }
 
-// negative_exponential_cocp (base.py:364-388): sum over forbidden gaps (a,b) of Phi(a-f) Phi(f-b).
+// negative_exponential_cocp (base.py:364-388): sum over the forbidden gaps (a,b) of Phi(a-f) Phi(f-b).
+// Internal row layout (built by ocbnn_problem_create from the ABI's gap list): n1, n2 (int bits), n1 x (c, s) one-sided terms
+// Phi(s (f - c)) [gaps with one infinite end], n2 x (a, b) two-sided terms.
 __device__ __forceinline__ void head_neg_exp(float f, const float* __restrict__ prm, const HeadConsts& c, float& val, float& df) {
-    int ngaps = (int)prm[0];
+    const int n1 = __float_as_int(prm[0]), n2 = __float_as_int(prm[1]);
     val = 0.f;
     df = 0.f;
-    for (int k = 0; k < ngaps; ++k) {
-        float a = prm[1 + 2 * k], b = prm[2 + 2 * k];
-        float P1 = 1.f, D1 = 0.f, P2 = 1.f, D2 = 0.f;
-        if (a > -INFINITY) phi_classifier(a - f, c, P1, D1);
-        if (b < INFINITY) phi_classifier(f - b, c, P2, D2);
+    const float* q = prm + 2;
+    for (int k = 0; k < n1; ++k, q += 2) {
+        float P, D;
+        phi_classifier(q[1] * (f - q[0]), c, P, D);
+        val += P;
+        df = fmaf(q[1], D, df);
+    }
+    for (int k = 0; k < n2; ++k, q += 2) {
+        float P1, D1, P2, D2;
+        phi_classifier(q[0] - f, c, P1, D1);
+        phi_classifier(f - q[1], c, P2, D2);
         val = fmaf(P1, P2, val);
         df += P1 * D2 - D1 * P2;
     }

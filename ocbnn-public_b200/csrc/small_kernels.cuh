@@ -7,7 +7,7 @@
 namespace ocbnn {
 
 constexpr int kSmallThreads = 128;
-constexpr int kDefaultHmcMb = 3;
+constexpr int kDefaultHmcMb = 2;   // measured on B200: 2 resident CTAs (no spills, 2 points in flight per thread) beats 3 and 4
 
 __host__ __device__ constexpr int kSmemFixedFloats(int ns) { return 4 * ns; }   // float4 prior table per slot
 

@@ -75,14 +75,14 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 
-// activation on a pair; returns a and m = da/dz
+// activation on a pair; returns a and m with da/dz = kActScale<ACT> * m (the constant is folded into the upstream gradient)
 template <int ACT>
 __device__ __forceinline__ void act_pair(float2 z, float2& a, float2& m) {
     if (ACT == OCBNN_ACT_RBF) {                       // exp(-z^2), base.py:84 ; d/dz = -2 z a
         float2 t = __fmul2_rn(z, z);
         float2 u = __fmul2_rn(t, f2(-1.4426950408889634f));
         a = make_float2(ex2_approx(u.x), ex2_approx(u.y));
-        m = __fmul2_rn(__fmul2_rn(z, f2(-2.f)), a);
+        m = __fmul2_rn(z, a);
     } else if (ACT == OCBNN_ACT_RELU) {               // max(z,0), base.py:86
         a = make_float2(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f));
         m = make_float2(z.x > 0.f ? 1.f : 0.f, z.y > 0.f ? 1.f : 0.f);
@@ -91,6 +91,8 @@ __device__ __forceinline__ void act_pair(float2 z, float2& a, float2& m) {
         m = f2(1.f);
     }
 }
+template <int ACT>
+__device__ __forceinline__ constexpr float act_scale() { return ACT == OCBNN_ACT_RBF ? -2.f : 1.f; }
 
 // ---- fast heads for the register kernels (same formulas as heads.cuh, MUFU approximations) ----------------------
 struct FastConsts {
@@ -111,8 +113,29 @@ __device__ __forceinline__ void phi_fast(float z, const FastConsts& c, float& P,
     dP = -(r * r) * s;
 }
 
+// two Phi evaluations packed in f32x2 lanes: 4 EX2 + 2 RCP, every other op a packed instruction
+__device__ __forceinline__ void phi_fast2(float2 z, const FastConsts& c, float2& P, float2& dP) {
+    const float2 u0 = __fmul2_rn(z, f2(c.tau_l2e.x)), u1 = __fmul2_rn(z, f2(c.tau_l2e.y));
+    const float2 e0 = make_float2(ex2_approx(fminf(u0.x, 57.7f)), ex2_approx(fminf(u0.y, 57.7f)));
+    const float2 e1 = make_float2(ex2_approx(fminf(u1.x, 57.7f)), ex2_approx(fminf(u1.y, 57.7f)));
+    const float2 a = __fadd2_rn(e0, f2(1.f)), b = __fadd2_rn(e1, f2(1.f));
+    const float2 ab = __fmul2_rn(a, b);
+    const float2 r = make_float2(rcp_approx(ab.x), rcp_approx(ab.y));
+    const float2 s = __ffma2_rn(__fmul2_rn(e0, f2(c.tau2.x)), b, __fmul2_rn(__fmul2_rn(e1, f2(c.tau2.y)), a));
+    P = r;
+    dP = __fmul2_rn(__fmul2_rn(r, make_float2(-r.x, -r.y)), s);
+}
+
+// Heads are evaluated for U points at once (run_many) so that their long serial MUFU chains interleave.
 template <int KIND, int SK>
 struct FastHead;
+
+template <int KIND, int SK, int U>
+__device__ __forceinline__ void head_many_generic(const float (&f)[U][SK], const float* const (&prm)[U], const FastConsts& c, float (&val)[U],
+                                                  float (&df)[U][SK]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) FastHead<KIND, SK>::run(f[u], prm[u], c, val[u], df[u]);
+}
 
 template <int SK>
 struct FastHead<OCBNN_HEAD_LIK_GAUSS, SK> {
@@ -126,17 +149,25 @@ struct FastHead<OCBNN_HEAD_LIK_GAUSS, SK> {
         }
     }
 };
+// internal parameter layout of a negative-COCP row (built by ocbnn_problem_create from the ABI's gap list):
+//   n1, n2 (int bits), n1 x (c, s) one-sided terms Phi(s (f - c)), n2 x (a, b) two-sided terms Phi(a - f) Phi(f - b)
 template <int SK>
 struct FastHead<OCBNN_HEAD_NEG_EXP, SK> {
     static __device__ __forceinline__ void run(const float (&f)[SK], const float* __restrict__ prm, const FastConsts& c, float& val, float (&df)[SK]) {
-        const int ngaps = (int)prm[0];
+        const int n1 = __float_as_int(prm[0]), n2 = __float_as_int(prm[1]);
         val = 0.f;
         float d = 0.f;
-        for (int k = 0; k < ngaps; ++k) {
-            const float a = prm[1 + 2 * k], b = prm[2 + 2 * k];
-            float P1 = 1.f, D1 = 0.f, P2 = 1.f, D2 = 0.f;
-            if (a > -INFINITY) phi_fast(a - f[0], c, P1, D1);
-            if (b < INFINITY) phi_fast(f[0] - b, c, P2, D2);
+        const float* q = prm + 2;
+        for (int k = 0; k < n1; ++k, q += 2) {
+            float P, D;
+            phi_fast(q[1] * (f[0] - q[0]), c, P, D);
+            val += P;
+            d = fmaf(q[1], D, d);
+        }
+        for (int k = 0; k < n2; ++k, q += 2) {
+            float P1, D1, P2, D2;
+            phi_fast(q[0] - f[0], c, P1, D1);
+            phi_fast(f[0] - q[1], c, P2, D2);
             val = fmaf(P1, P2, val);
             d += P1 * D2 - D1 * P2;
         }
@@ -144,7 +175,56 @@ struct FastHead<OCBNN_HEAD_NEG_EXP, SK> {
         for (int k = 0; k < SK; ++k) df[k] = 0.f;
         df[0] = d;
     }
+    // two points in lockstep: term k of both points is one packed Phi evaluation; a point with fewer terms is masked
+    static __device__ __forceinline__ void run_pair(float fa, float fb, const float* __restrict__ pa, const float* __restrict__ pb,
+                                                    const FastConsts& c, float2& val, float2& d) {
+        const int n1a = __float_as_int(pa[0]), n2a = __float_as_int(pa[1]);
+        const int n1b = __float_as_int(pb[0]), n2b = __float_as_int(pb[1]);
+        const int n1 = max(n1a, n1b), n2 = max(n2a, n2b);
+        const float2 ff = make_float2(fa, fb);
+        val = f2(0.f);
+        d = f2(0.f);
+        for (int k = 0; k < n1; ++k) {
+            const bool va = k < n1a, vb = k < n1b;
+            const float2 cc = make_float2(va ? pa[2 + 2 * k] : 0.f, vb ? pb[2 + 2 * k] : 0.f);
+            const float2 ss = make_float2(va ? pa[3 + 2 * k] : 0.f, vb ? pb[3 + 2 * k] : 0.f);
+            float2 P, D;
+            phi_fast2(__fmul2_rn(ss, __fadd2_rn(ff, make_float2(-cc.x, -cc.y))), c, P, D);
+            val = __ffma2_rn(P, make_float2(va ? 1.f : 0.f, vb ? 1.f : 0.f), val);
+            d = __ffma2_rn(ss, D, d);
+        }
+        const float* qa = pa + 2 + 2 * n1a;
+        const float* qb = pb + 2 + 2 * n1b;
+        for (int k = 0; k < n2; ++k) {
+            const bool va = k < n2a, vb = k < n2b;
+            const float2 lo = make_float2(va ? qa[2 * k] : 0.f, vb ? qb[2 * k] : 0.f);
+            const float2 hi = make_float2(va ? qa[2 * k + 1] : 0.f, vb ? qb[2 * k + 1] : 0.f);
+            const float2 msk = make_float2(va ? 1.f : 0.f, vb ? 1.f : 0.f);
+            float2 P1, D1, P2, D2;
+            phi_fast2(__fadd2_rn(lo, make_float2(-ff.x, -ff.y)), c, P1, D1);
+            phi_fast2(__fadd2_rn(ff, make_float2(-hi.x, -hi.y)), c, P2, D2);
+            val = __ffma2_rn(__fmul2_rn(P1, P2), msk, val);
+            const float2 dd = __ffma2_rn(P1, D2, make_float2(-D1.x * P2.x, -D1.y * P2.y));
+            d = __ffma2_rn(dd, msk, d);
+        }
+    }
 };
+template <int SK, int U>
+__device__ __forceinline__ void head_many_neg(const float (&f)[U][SK], const float* const (&prm)[U], const FastConsts& c, float (&val)[U],
+                                              float (&df)[U][SK]) {
+#pragma unroll
+    for (int u = 0; u + 1 < U; u += 2) {
+        float2 v, d;
+        FastHead<OCBNN_HEAD_NEG_EXP, SK>::run_pair(f[u][0], f[u + 1][0], prm[u], prm[u + 1], c, v, d);
+        val[u] = v.x;
+        val[u + 1] = v.y;
+#pragma unroll
+        for (int k = 0; k < SK; ++k) df[u][k] = df[u + 1][k] = 0.f;
+        df[u][0] = d.x;
+        df[u + 1][0] = d.y;
+    }
+    if (U & 1) FastHead<OCBNN_HEAD_NEG_EXP, SK>::run(f[U - 1], prm[U - 1], c, val[U - 1], df[U - 1]);
+}
 template <int SK>
 struct FastHead<OCBNN_HEAD_POS_GAUSS, SK> {
     static __device__ __forceinline__ void run(const float (&f)[SK], const float* __restrict__ prm, const FastConsts& c, float& val, float (&df)[SK]) {
@@ -176,54 +256,76 @@ struct FastHead<OCBNN_HEAD_LIK_BERNOULLI, SK> {
     }
 };
 
-// value + gradient contribution of ONE point record with a compile-time head
-template <class N, int KIND>
-__device__ __forceinline__ void point_eval(const float2 (&w)[N::NS], float2 (&g)[N::NS], double& lp, const float* __restrict__ rec,
-                                           const FastConsts& fc) {
-    float2 xx[N::S0];
-#pragma unroll
-    for (int d = 0; d < N::S0; ++d) xx[d] = f2(rec[d]);
-    const float wgt = rec[N::S0 + 1];
+#ifndef OCBNN_POINT_UNROLL
+#define OCBNN_POINT_UNROLL 2
+#endif
 
-    float2 a[N::HP], m[N::HP], facc[N::SK];
+// value + gradient contribution of U point records with a compile-time head.  The U points are independent until the
+// gradient accumulation, which gives the scheduler U forward/head dependency chains to interleave (the head is a long
+// serial chain of MUFU ops).  Records beyond the segment are passed with live[u] = 0 and contribute nothing.
+template <class N, int KIND, int U>
+__device__ __forceinline__ void point_eval(const float2 (&w)[N::NS], float2 (&g)[N::NS], double& lp, const float* const (&rec)[U],
+                                           const float (&live)[U], const FastConsts& fc) {
+    float2 xx[U][N::S0], a[U][N::HP], m[U][N::HP];
+    float f[U][N::SK], df[U][N::SK], val[U];
+    const float* prm[U];
 #pragma unroll
-    for (int k = 0; k < N::SK; ++k) facc[k] = f2(0.f);
+    for (int u = 0; u < U; ++u) {
 #pragma unroll
-    for (int hp = 0; hp < N::HP; ++hp) {
-        float2 z = w[N::SB1 + hp];
+        for (int d = 0; d < N::S0; ++d) xx[u][d] = f2(rec[u][d]);
+        prm[u] = rec[u] + N::S0 + 2;
+        float2 facc[N::SK];
 #pragma unroll
-        for (int d = 0; d < N::S0; ++d) z = __ffma2_rn(w[N::SW1 + d * N::HP + hp], xx[d], z);
-        act_pair<N::ACT>(z, a[hp], m[hp]);
+        for (int k = 0; k < N::SK; ++k) facc[k] = f2(0.f);
 #pragma unroll
-        for (int k = 0; k < N::SK; ++k) facc[k] = __ffma2_rn(w[N::SW2 + k * N::HP + hp], a[hp], facc[k]);
-    }
-    float f[N::SK];
+        for (int hp = 0; hp < N::HP; ++hp) {
+            float2 z = w[N::SB1 + hp];
 #pragma unroll
-    for (int k = 0; k < N::SK; ++k) {
-        const float b2 = (k & 1) ? w[N::SB2 + k / 2].y : w[N::SB2 + k / 2].x;
-        f[k] = (facc[k].x + facc[k].y) + b2;
-    }
-    float val, df[N::SK];
-    FastHead<KIND, N::SK>::run(f, rec + N::S0 + 2, fc, val, df);
-    lp += (double)(wgt * val);
+            for (int d = 0; d < N::S0; ++d) z = __ffma2_rn(w[N::SW1 + d * N::HP + hp], xx[u][d], z);
+            act_pair<N::ACT>(z, a[u][hp], m[u][hp]);
 #pragma unroll
-    for (int k = 0; k < N::SK; ++k) {
-        df[k] *= wgt;
-        if (k & 1) g[N::SB2 + k / 2].y += df[k]; else g[N::SB2 + k / 2].x += df[k];
-    }
-#pragma unroll
-    for (int hp = 0; hp < N::HP; ++hp) {
-        float2 da = f2(0.f);
+            for (int k = 0; k < N::SK; ++k) facc[k] = __ffma2_rn(w[N::SW2 + k * N::HP + hp], a[u][hp], facc[k]);
+        }
 #pragma unroll
         for (int k = 0; k < N::SK; ++k) {
-            const float2 dk = f2(df[k]);
-            da = __ffma2_rn(dk, w[N::SW2 + k * N::HP + hp], da);
-            g[N::SW2 + k * N::HP + hp] = __ffma2_rn(dk, a[hp], g[N::SW2 + k * N::HP + hp]);
+            const float b2 = (k & 1) ? w[N::SB2 + k / 2].y : w[N::SB2 + k / 2].x;
+            f[u][k] = (facc[k].x + facc[k].y) + b2;
         }
-        const float2 dz = __fmul2_rn(da, m[hp]);
-        g[N::SB1 + hp] = __fadd2_rn(g[N::SB1 + hp], dz);
+    }
+    if (KIND == OCBNN_HEAD_NEG_EXP) head_many_neg<N::SK, U>(f, prm, fc, val, df);
+    else head_many_generic<KIND, N::SK, U>(f, prm, fc, val, df);
+    float vsum = 0.f;                      // the U values are added in fp32, then once into the float64 accumulator
 #pragma unroll
-        for (int d = 0; d < N::S0; ++d) g[N::SW1 + d * N::HP + hp] = __ffma2_rn(dz, xx[d], g[N::SW1 + d * N::HP + hp]);
+    for (int u = 0; u < U; ++u) {
+        const float wgt = rec[u][N::S0 + 1] * live[u];
+        vsum = fmaf(wgt, val[u], vsum);
+#pragma unroll
+        for (int k = 0; k < N::SK; ++k) df[u][k] *= wgt;
+    }
+    lp += (double)vsum;
+#pragma unroll
+    for (int k = 0; k < N::SK; ++k) {
+        float s = 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) s += df[u][k];
+        if (k & 1) g[N::SB2 + k / 2].y += s; else g[N::SB2 + k / 2].x += s;
+    }
+#pragma unroll
+    for (int hp = 0; hp < N::HP; ++hp) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float2 da = f2(0.f);
+#pragma unroll
+            for (int k = 0; k < N::SK; ++k) {
+                const float2 dk = f2(df[u][k]);
+                da = __ffma2_rn(dk, w[N::SW2 + k * N::HP + hp], da);
+                g[N::SW2 + k * N::HP + hp] = __ffma2_rn(dk, a[u][hp], g[N::SW2 + k * N::HP + hp]);
+            }
+            const float2 dz = __fmul2_rn(__fmul2_rn(da, f2(act_scale<N::ACT>())), m[u][hp]);
+            g[N::SB1 + hp] = __fadd2_rn(g[N::SB1 + hp], dz);
+#pragma unroll
+            for (int d = 0; d < N::S0; ++d) g[N::SW1 + d * N::HP + hp] = __ffma2_rn(dz, xx[u][d], g[N::SW1 + d * N::HP + hp]);
+        }
     }
 }
 
@@ -317,7 +419,18 @@ __device__ __forceinline__ void load_pri_slots(float4* pri_s, const EvalArgs& a)
 template <class N, int G, int KIND>
 __device__ __forceinline__ void eval_segment(const EvalCtx& c, int rs, int lo, int hi, const float2 (&w)[N::NS], float2 (&g)[N::NS],
                                              double& lp, int lane) {
-    for (int j = lo + lane; j < hi; j += G) point_eval<N, KIND>(w, g, lp, c.tab + j * rs, c.fc);
+    constexpr int U = OCBNN_POINT_UNROLL;
+    for (int j = lo + lane; j < hi; j += U * G) {
+        const float* rec[U];
+        float live[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool ok = j + u * G < hi;
+            rec[u] = c.tab + (ok ? j + u * G : j) * rs;
+            live[u] = ok ? 1.f : 0.f;
+        }
+        point_eval<N, KIND, U>(w, g, lp, rec, live, c.fc);
+    }
 }
 
 // log posterior value and gradient at w.  Block-uniform control flow (contains __syncthreads when the point set
