@@ -1,0 +1,92 @@
+"""Multi-GPU agreement check (run under torchrun, one rank per GPU): the sharded HMC / SVGD / BBB paths against the same
+work done by one rank.  HMC chains must agree bit-for-bit; SVGD and BBB within 1e-5.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/multigpu_check.py
+"""
+import os
+import sys
+import tempfile
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "ocbnn-public_b200"))
+
+from ocbnn_b200 import dist as D, engine as E, workloads  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    os.chdir(tempfile.mkdtemp(prefix=f"mg_r{rank}_"))
+    ok = True
+
+    # ---- HMC: independent chains, no data-path collective ---------------------------------------------------------
+    m = workloads.build("W2", seed=0)
+    prob = m.engine_problem()
+    M, n_it, L = 1000, 3, 10
+    g = torch.Generator().manual_seed(5)
+    q0 = 0.3 * torch.randn(M, m.nweights, generator=g)
+    p0 = torch.randn(n_it, M, m.nweights, generator=g)
+    u = torch.rand(n_it, M, generator=g, dtype=torch.float64)
+    lo, hi = D.shard(M)
+    q = q0[lo:hi].to(dev).contiguous()
+    acc, _, _ = prob.hmc_iterate(q, p0[:, lo:hi].to(dev).contiguous(), u[:, lo:hi].to(dev).contiguous(), m.hmc_epsilon, L, True, lanes=4)
+    q_all, acc_all = D.gather_cat(q, 0), D.gather_cat(acc, 1)
+    q1 = q0.to(dev).contiguous()
+    acc1, _, _ = prob.hmc_iterate(q1, p0.to(dev), u.to(dev), m.hmc_epsilon, L, True, lanes=4)
+    same = torch.equal(q_all, q1) and torch.equal(acc_all, acc1)
+    ok &= same
+    if rank == 0:
+        print(f"HMC {world} ranks vs 1 rank: bit-identical = {same} (M={M}, {n_it} iterations, L={L})")
+
+    # ---- SVGD: all-gather of particles and gradients + all-reduced select histograms ------------------------------------
+    ms = workloads.build("W4", seed=0, infer_nsamples=257)
+    X0 = torch.randn(257, ms.nweights, generator=g)
+    st = ms.svgd_setup(X0)
+    for ep in range(1, 4):
+        ms.svgd_epoch(st, ep, True, use_tensor=0)
+    Xs, hs = D.gather_cat(st["X"], 0), st["h"].clone()
+    # single-rank arm: same model code with the process group hidden
+    saved = D.active
+    D.active = lambda: False
+    st1 = ms.svgd_setup(X0)
+    for ep in range(1, 4):
+        ms.svgd_epoch(st1, ep, True, use_tensor=0)
+    D.active = saved
+    rel = float((Xs - st1["X"]).norm() / st1["X"].norm())
+    hrel = float((hs - st1["h"]).abs() / st1["h"])
+    ok &= rel < 1e-5 and hrel < 1e-6
+    if rank == 0:
+        print(f"SVGD {world} ranks vs 1 rank: particles rel diff {rel:.2e}, bandwidth rel diff {hrel:.2e} (n=257, 3 epochs)")
+
+    # ---- BBB: all-reduce of the (D,2) gradient ----------------------------------------------------------------------------
+    mb = workloads.build("W1", sampler="BBB", seed=0)
+    k = 64
+    eps = torch.randn(k, mb.nweights, generator=g)
+    qp0 = torch.cat([torch.randn(mb.nweights, 1, generator=g), -0.5 * torch.ones(mb.nweights, 1)], 1)
+    lo, hi = D.shard(k)
+    qp, ac = qp0.to(dev).contiguous(), torch.zeros(mb.nweights, 2, device=dev)
+    e_sh = mb.bbb_epoch(qp, ac, eps[lo:hi].to(dev).contiguous(), 1, True, k_total=k)
+    D.active = lambda: False
+    qp1, ac1 = qp0.to(dev).contiguous(), torch.zeros(mb.nweights, 2, device=dev)
+    e_1 = mb.bbb_epoch(qp1, ac1, eps.to(dev).contiguous(), 1, True, k_total=k)
+    D.active = saved
+    rel = float((qp - qp1).norm() / qp1.norm())
+    erel = float((e_sh - e_1).abs() / e_1.abs())
+    ok &= rel < 1e-5 and erel < 1e-5
+    if rank == 0:
+        print(f"BBB {world} ranks vs 1 rank: q_params rel diff {rel:.2e}, ELBO rel diff {erel:.2e} (k={k})")
+        print("MULTIGPU_CHECK", "PASS" if ok else "FAIL")
+    t = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if float(t) == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
