@@ -177,6 +177,18 @@ OCBNN_API int ocbnn_bbb_sample(const float *q_params, const float *eps, int64_t 
 OCBNN_API int ocbnn_bbb_reduce(const float *q_params, const float *eps, const float *lp, const float *grad, int64_t k, int64_t d,
                      int64_t k_total, int32_t add_entropy, float *out_grad_q, float *out_elbo, float *colstat, void *stream);
 
+/* K6 — Gaussian AOCP objective and its gradient w.r.t. params (D x 2 = mean, rho; std = softplus(rho)).
+ * Replaces gaussian_aocp_objective + autograd (base.py:390-419 regression, :624-672 binary) for C constraint points cx (C x s_0):
+ * mode 0: binary deterministic, targets (C) = desired class, loss |class - p| ; mode 1: binary probabilistic, targets (C) =
+ * desired p(Y=1), symmetric Bernoulli KL with both sides clamped to [0.001, 0.999] ; mode 2: regression, targets
+ * (C x 2*max_iv) = permitted (lb, ub) pairs, NaN padded, loss = 1 - permitted mass of N(f(x;mean), sigma_noise + sigma^2).
+ * Writes (or, with accumulate != 0, adds) sum_c loss_c * inv_denom to out_loss (device scalar) and the gradient * inv_denom to
+ * out_grad (D x 2).  workspace >= ocbnn_aocp_workspace_bytes(C, D) device bytes.  Uses only the net shape of `p`. */
+OCBNN_API int64_t ocbnn_aocp_workspace_bytes(int64_t c, int64_t d);
+OCBNN_API int ocbnn_aocp_objective(ocbnn_problem *p, const float *params, const float *cx, const float *targets, int64_t c,
+                                   int32_t mode, int32_t max_iv, float sigma_noise, float inv_denom, int32_t accumulate,
+                                   float *out_loss, float *out_grad, void *workspace, int64_t workspace_bytes, void *stream);
+
 /* Diagnostics for the roofline report: measured instruction peaks of this GPU.  mode 0: scalar fp32 FMA, 1: packed
  * f32x2 FMA (both in FLOP/s, fma = 2), 2: MUFU.EX2 (op/s).  Synchronous. */
 OCBNN_API int ocbnn_probe_peak(int32_t mode, double *out_rate);

@@ -184,6 +184,11 @@ class BayesianNeuralNetwork:
         from .aocp import learn_gaussian_aocp
         learn_gaussian_aocp(self, verbose)
 
+    def gaussian_aocp_objective(self):
+        """AOCP objective at self._aocp_params (base.py:390-419, 624-672); value only."""
+        from .aocp import gaussian_aocp_objective
+        return gaussian_aocp_objective(self)[0].cpu()[0]
+
     def update_config(self, **kwargs):
         self.__dict__.update(**kwargs)
         logging.info(f"[{self.uid}] Configs updated.")

@@ -87,6 +87,9 @@ _SIGS = {
     "ocbnn_bbb_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "ocbnn_bbb_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ocbnn_aocp_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
+    "ocbnn_aocp_objective": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float,
+                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ocbnn_probe_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
     "ocbnn_hmc_iterate_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double,
                                          C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
@@ -241,6 +244,17 @@ class DeviceProblem:
         check(lib().ocbnn_sgld_iterate(self._h, _ptr(w), _ptr(noise), he.ctypes.data_as(_fp), bo.ctypes.data_as(_ip),
                                        int(batch_stride), w.shape[0], T, int(bool(with_data)), _ptr(samples), int(thin), int(lanes),
                                        _stream()))
+
+
+    # ---- K6 -------------------------------------------------------------------------------------------
+    def aocp_objective(self, params, cx, targets, mode, max_iv, sigma_noise, inv_denom, out_loss, out_grad, accumulate=False):
+        params, cx, targets = _f32(params, "params"), _f32(cx, "cx"), _f32(targets, "targets")
+        Cn = cx.shape[0]
+        nbytes = int(lib().ocbnn_aocp_workspace_bytes(Cn, self.D))
+        ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=params.device)
+        check(lib().ocbnn_aocp_objective(self._h, _ptr(params), _ptr(cx), _ptr(targets), Cn, int(mode), int(max_iv), float(sigma_noise),
+                                         float(inv_denom), int(bool(accumulate)), _ptr(out_loss), _ptr(out_grad), _ptr(ws), ws.numel() * 4,
+                                         _stream()))
 
 
 # ---- K3 (problem independent) ------------------------------------------------------------------------------

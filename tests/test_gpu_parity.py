@@ -313,3 +313,38 @@ def test_full_size_properties():
     assert float(rel.median()) < 1e-5
     lp, _ = prob.logpost_grad(q0, (0, 1), True, want_grad=False)
     assert torch.allclose(-lp, outs[1][1][0, :, 0], rtol=1e-6, atol=1e-3)      # U0 of iteration 0 = -log posterior(q0)
+
+
+@pytest.mark.parametrize("name", ["f4_bin_aocp", "f3a_reg_aocp"])
+def test_k6_aocp_objective_and_learning(name):
+    """AOCP objective, its gradient (vs the reference's autograd) and three epochs of learn_gaussian_aocp."""
+    from ocbnn_b200.aocp import gaussian_aocp_objective
+    g = load_golden(name)
+    m = make_model(name, g)
+    m._aocp_params = torch.tensor(g["aocp_params"])
+    loss, grad = gaussian_aocp_objective(m)
+    assert abs(float(loss) - float(g["aocp_loss"])) <= 5e-5 * max(abs(float(g["aocp_loss"])), 1e-3)
+    assert rel_err(grad.cpu().numpy().T, g["aocp_grad"].T).max() < 5e-4
+    assert abs(float(m.gaussian_aocp_objective()) - float(g["aocp_loss"])) <= 5e-5 * max(abs(float(g["aocp_loss"])), 1e-3)
+    m.update_config(aocp_nepochs=3)
+    torch.manual_seed(11)
+    m.learn_gaussian_aocp(verbose=False)
+    assert np.abs(m._aocp_params.numpy() - g["aocp_learn_params"]).max() < 5e-3 * max(1.0, np.abs(g["aocp_learn_params"]).max())
+    assert np.abs(m.aocp_mean.numpy() - g["aocp_learn_mean"]).max() < 5e-3 * max(1.0, np.abs(g["aocp_learn_mean"]).max())
+    import os
+    assert os.path.exists(f"history/{m.uid}_aocp.pt")
+
+
+def test_k6_aocp_at_recid_scale():
+    """D = 11201, 6 constraint points (the reference needs a 500 MB dense matrix per point here): float64 oracle parity."""
+    from ocbnn_b200.aocp import gaussian_aocp_objective
+    name = "recid_small"
+    g = load_golden(name)
+    m = make_model(name, g)
+    spec = spec_from_golden(name, g)
+    m._aocp_params = torch.tensor(g["aocp_params"])
+    loss, grad = gaussian_aocp_objective(m)
+    xs = g["cr_cr_prob_xsamples"]
+    lo, go = orc.aocp_objective_binary(spec, g["aocp_params"], prob=dict(xs=xs, p=xs[:, 1]), dtype=np.float64)
+    assert abs(float(loss) - lo) <= 2e-5 * abs(lo)
+    assert rel_err(grad.cpu().numpy().T, go.T).max() < 1e-4
