@@ -164,6 +164,13 @@ OCBNN_API int ocbnn_svgd_phi(const float *x, const float *g, int64_t n, int64_t 
                    const float *h, float *out_phi, int32_t use_tensor, void *workspace, int64_t workspace_bytes, void *stream);
 OCBNN_API int64_t ocbnn_svgd_workspace_bytes(int64_t n, int64_t d);
 
+/* tcgen05/TMA building block of the K3b tensor path, exported for testing: C (m x n) = A (m x k) * B (n x k)^T with every
+ * fp32 operand split into tf32 hi + lo parts and three tensor-core MMAs per K step (fp32-class accuracy, ~2^-21 relative).
+ * Row-major device arrays; workspace >= ocbnn_gemm_tf32x3_workspace_bytes(m, n, k) device bytes. */
+OCBNN_API int64_t ocbnn_gemm_tf32x3_workspace_bytes(int64_t m, int64_t n, int64_t k);
+OCBNN_API int ocbnn_gemm_tf32x3(const float *a, const float *b, float *c, int64_t m, int64_t n, int64_t k, void *workspace,
+                                int64_t workspace_bytes, void *stream);
+
 /* K3c — Adagrad (torch.optim.Adagrad defaults, inference.py:173,272): acc += g^2 ; x -= lr * g / (sqrt(acc)+1e-10),
  * with g = grad_sign * dir (SVGD passes dir = phi, grad_sign = -1). */
 OCBNN_API int ocbnn_adagrad_step(float *x, float *acc, const float *dir, int64_t n_elem, float lr, float grad_sign, void *stream);

@@ -83,6 +83,8 @@ _SIGS = {
     "ocbnn_svgd_phi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                  C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "ocbnn_svgd_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
+    "ocbnn_gemm_tf32x3_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64]),
+    "ocbnn_gemm_tf32x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "ocbnn_adagrad_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p]),
     "ocbnn_bbb_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "ocbnn_bbb_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
@@ -286,6 +288,18 @@ def svgd_phi(X, G, h, row_begin, n_rows, workspace, use_tensor=-1, out=None):
     check(lib().ocbnn_svgd_phi(_ptr(X), _ptr(G), X.shape[0], X.shape[1], int(row_begin), int(n_rows), _ptr(h), _ptr(phi), int(use_tensor),
                                _ptr(workspace), workspace.numel() * 8 if workspace is not None else 0, _stream()))
     return phi
+
+
+def gemm_tf32x3(A, B):
+    """C = A @ B.T on tcgen05 in 3xTF32 precision (building block of the SVGD tensor path)."""
+    A, B = _f32(A, "A"), _f32(B, "B")
+    m, k = A.shape
+    n = B.shape[0]
+    Cm = torch.empty(m, n, device=A.device)
+    nbytes = int(lib().ocbnn_gemm_tf32x3_workspace_bytes(m, n, k))
+    ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=A.device)
+    check(lib().ocbnn_gemm_tf32x3(_ptr(A), _ptr(B), _ptr(Cm), m, n, k, _ptr(ws), ws.numel() * 4, _stream()))
+    return Cm
 
 
 def adagrad_step(x, acc, direction, lr, grad_sign):
