@@ -145,24 +145,37 @@ OCBNN_API int ocbnn_sgld_iterate(ocbnn_problem *p, float *w, const float *noise,
                        int32_t batch_stride, int64_t m, int32_t t_steps, int32_t with_data, float *out_samples,
                        int32_t thin, int32_t lanes, void *stream);
 
-/* K3a — SVGD median-heuristic bandwidth h = med^2 / ln n (inference.py:208-217): exact LOWER median of
- * ||x_i - x_j + 1e-6|| over i<j, zeros dropped, by a 3-pass radix select (11+11+10 bits of the fp32 pattern).
- * out_h: device scalar.  A pass histograms rows i = row_start + t*row_step, t < n_rows, of x (n x D) against all j > i
- * (cyclic row assignment balances the triangle across ranks).  hist (device, 3 x 2048 u32; zeroed by pass 0) and
- * select_state (device, 4 x u64) are exposed so that a multi-GPU caller can all-reduce hist between hist_pass and
- * select_update. */
+/* K3 — SVGD (inference.py:208-292).  Two implementations behind one interface, selected by use_tensor:
+ *   0  exact fp32 SIMT kernels (distances recomputed from x on every pass);
+ *   1  tcgen05 path: x is centred and split into tf32 hi/lo parts, squared distances of this rank's rows are formed once
+ *      (exact differences for D <= 64, 3xTF32 Gram GEMM on the tensor cores above that) and kept in the workspace, the
+ *      kernel matrix K = exp(-d2/h) and O = K [G | Xc] run as a TMA-fed tcgen05 GEMM in 3xTF32 precision;
+ *  -1  choose (tensor path from 1024 particles up).
+ * workspace >= ocbnn_svgd_workspace_bytes(n, d, n_rows, use_tensor) device bytes, 256-byte aligned; it starts with the
+ * select histogram (3 x 2048 u32) and the select state (4 x u64), which a multi-GPU caller all-reduces between passes.
+ *
+ * K3a — bandwidth h = med^2 / ln n: exact LOWER median of ||x_i - x_j + 1e-6|| over i<j, zeros dropped, by a 3-pass radix
+ * select (11+11+10 bits of the fp32 pattern).  out_h: device scalar.  A SIMT pass histograms rows i = row_start + t*row_step,
+ * t < n_rows, against all j > i; a "prepared" pass reads the distances ocbnn_svgd_prepare left in the workspace for rows
+ * [row_begin, row_begin + n_rows). */
+OCBNN_API int64_t ocbnn_svgd_workspace_bytes(int64_t n, int64_t d, int64_t n_rows, int32_t use_tensor);
+OCBNN_API int ocbnn_svgd_prepare(const float *x, int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t use_tensor,
+                                 void *workspace, int64_t workspace_bytes, void *stream);
 OCBNN_API int ocbnn_svgd_hist_pass(const float *x, int64_t n, int64_t d, int64_t row_start, int64_t row_step, int64_t n_rows,
-                         int32_t pass, uint32_t *hist, uint64_t *select_state, void *stream);
+                                   int32_t pass, uint32_t *hist, uint64_t *select_state, void *stream);
+OCBNN_API int ocbnn_svgd_hist_pass_prepared(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t pass, uint32_t *hist,
+                                            uint64_t *select_state, void *workspace, void *stream);
 OCBNN_API int ocbnn_svgd_select_update(int32_t pass, uint32_t *hist, uint64_t *select_state, int64_t n, float *out_h, void *stream);
-/* single-GPU convenience: all three passes; workspace >= ocbnn_svgd_workspace_bytes(n, d) */
-OCBNN_API int ocbnn_svgd_bandwidth(const float *x, int64_t n, int64_t d, float *out_h, void *workspace, int64_t workspace_bytes, void *stream);
+/* single-GPU convenience: prepare (tensor path) + all three passes */
+OCBNN_API int ocbnn_svgd_bandwidth(const float *x, int64_t n, int64_t d, float *out_h, int32_t use_tensor, void *workspace,
+                                   int64_t workspace_bytes, void *stream);
 
 /* K3b — SVGD update direction phi_i = (1/n) sum_j [K_ji g_j + grad_{x_j} K_ji] (inference.py:219-259) for rows
  * [row_begin, row_begin + n_rows) of the (gathered) particle matrix x (n x D) with gradients g (n x D).
- * use_tensor: 0 = exact fp32 SIMT path, 1 = tcgen05 3xTF32 path, -1 = choose by shape. */
+ * use_tensor = 2: tensor path, and the workspace was already prepared for this x and these rows (by ocbnn_svgd_prepare
+ * or ocbnn_svgd_bandwidth); 1 prepares it itself. */
 OCBNN_API int ocbnn_svgd_phi(const float *x, const float *g, int64_t n, int64_t d, int64_t row_begin, int64_t n_rows,
-                   const float *h, float *out_phi, int32_t use_tensor, void *workspace, int64_t workspace_bytes, void *stream);
-OCBNN_API int64_t ocbnn_svgd_workspace_bytes(int64_t n, int64_t d);
+                             const float *h, float *out_phi, int32_t use_tensor, void *workspace, int64_t workspace_bytes, void *stream);
 
 /* tcgen05/TMA building block of the K3b tensor path, exported for testing: C (m x n) = A (m x k) * B (n x k)^T with every
  * fp32 operand split into tf32 hi + lo parts and three tensor-core MMAs per K step (fp32-class accuracy, ~2^-21 relative).

@@ -333,20 +333,57 @@ extern "C" OCBNN_API int ocbnn_svgd_select_update(int32_t pass, uint32_t* hist, 
     return OCBNN_OK;
 }
 
-extern "C" OCBNN_API int64_t ocbnn_svgd_workspace_bytes(int64_t n, int64_t d) {
-    int64_t b = 3 * kBins * sizeof(uint32_t) + 64;                 // histogram + select state
-    if (d > 64) b += (n * n + n) * (int64_t)sizeof(float);         // kernel matrix + row sums (exact wide path)
+// tensor path (svgd_tc.cu)
+namespace ocbnn { namespace tc {
+long long tc_workspace_bytes(long long n, long long d, long long n_rows);
+int tc_svgd_prepare(const float* x, long long n, long long d, long long row_begin, long long n_rows, void* ws, long long ws_bytes, cudaStream_t st);
+int tc_svgd_hist(long long n, long long d, long long row_begin, long long n_rows, int pass, unsigned* hist, const unsigned long long* state, void* ws,
+                 cudaStream_t st);
+int tc_svgd_phi(const float* g, const float* h, long long n, long long d, long long row_begin, long long n_rows, float* phi, void* ws, cudaStream_t st);
+} }
+
+// use_tensor: 0 exact fp32 SIMT kernels ; 1 tcgen05 path ; -1 choose (tensor path from 1024 particles up)
+static bool want_tensor(int32_t use_tensor, int64_t n) { return use_tensor > 0 || (use_tensor < 0 && n >= 1024); }
+
+extern "C" OCBNN_API int64_t ocbnn_svgd_workspace_bytes(int64_t n, int64_t d, int64_t n_rows, int32_t use_tensor) {
+    int64_t b = 3 * kBins * sizeof(uint32_t) + 256;                       // histogram + select state
+    if (want_tensor(use_tensor, n)) return b + tc::tc_workspace_bytes(n, d, n_rows);
+    if (d > 64) b += (n_rows * n + n_rows) * (int64_t)sizeof(float);      // kernel matrix + row sums (exact wide path)
     return b;
 }
 
-extern "C" OCBNN_API int ocbnn_svgd_bandwidth(const float* x, int64_t n, int64_t d, float* out_h, void* workspace, int64_t workspace_bytes,
-                                    void* stream) {
-    OCBNN_REQUIRE(workspace && workspace_bytes >= (int64_t)(3 * kBins * sizeof(uint32_t) + 64), OCBNN_EINVAL,
-                  "ocbnn_svgd_bandwidth: workspace too small");
+extern "C" OCBNN_API int ocbnn_svgd_prepare(const float* x, int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t use_tensor,
+                                            void* workspace, int64_t workspace_bytes, void* stream) {
+    OCBNN_REQUIRE(x && n >= 2 && d >= 1 && row_begin >= 0 && row_begin + n_rows <= n, OCBNN_EINVAL, "ocbnn_svgd_prepare: bad argument");
+    if (!want_tensor(use_tensor, n) || n_rows == 0) return OCBNN_OK;
+    return tc::tc_svgd_prepare(x, n, d, row_begin, n_rows, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" OCBNN_API int ocbnn_svgd_hist_pass_prepared(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t pass, uint32_t* hist,
+                                                       uint64_t* select_state, void* workspace, void* stream) {
+    OCBNN_REQUIRE(hist && select_state && workspace && pass >= 0 && pass < 3, OCBNN_EINVAL, "ocbnn_svgd_hist_pass_prepared: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pass == 0) {
+        k_zero_u32<<<(3 * kBins + 255) / 256, 256, 0, st>>>(hist, 3 * kBins);
+        OCBNN_LAUNCH_CHECK();
+    }
+    if (n_rows <= 0) return OCBNN_OK;
+    return tc::tc_svgd_hist(n, d, row_begin, n_rows, pass, hist, reinterpret_cast<const unsigned long long*>(select_state), workspace, st);
+}
+
+extern "C" OCBNN_API int ocbnn_svgd_bandwidth(const float* x, int64_t n, int64_t d, float* out_h, int32_t use_tensor, void* workspace,
+                                              int64_t workspace_bytes, void* stream) {
+    OCBNN_REQUIRE(workspace && workspace_bytes >= ocbnn_svgd_workspace_bytes(n, d, n, use_tensor), OCBNN_EINVAL,
+                  "ocbnn_svgd_bandwidth: workspace too small (see ocbnn_svgd_workspace_bytes)");
     uint32_t* hist = reinterpret_cast<uint32_t*>(workspace);
     uint64_t* state = reinterpret_cast<uint64_t*>(hist + 3 * kBins);
+    void* tcws = reinterpret_cast<char*>(workspace) + 3 * kBins * sizeof(uint32_t) + 256;
+    const bool tensor = want_tensor(use_tensor, n);
+    int rc;
+    if (tensor && (rc = tc::tc_svgd_prepare(x, n, d, 0, n, tcws, workspace_bytes - (3 * kBins * sizeof(uint32_t) + 256), (cudaStream_t)stream))) return rc;
     for (int pass = 0; pass < 3; ++pass) {
-        int rc = ocbnn_svgd_hist_pass(x, n, d, 0, 1, n, pass, hist, state, stream);
+        rc = tensor ? ocbnn_svgd_hist_pass_prepared(n, d, 0, n, pass, hist, state, tcws, stream)
+                    : ocbnn_svgd_hist_pass(x, n, d, 0, 1, n, pass, hist, state, stream);
         if (rc) return rc;
         rc = ocbnn_svgd_select_update(pass, hist, state, n, pass == 2 ? out_h : nullptr, stream);
         if (rc) return rc;
@@ -354,13 +391,24 @@ extern "C" OCBNN_API int ocbnn_svgd_bandwidth(const float* x, int64_t n, int64_t
     return OCBNN_OK;
 }
 
+// use_tensor: 0 SIMT ; 1 tensor path (centres/splits X and forms the distances itself) ; 2 tensor path, the workspace was prepared
+// for this X and these rows by ocbnn_svgd_prepare / ocbnn_svgd_bandwidth ; -1 choose between 0 and 1
 extern "C" OCBNN_API int ocbnn_svgd_phi(const float* x, const float* g, int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, const float* h,
                               float* out_phi, int32_t use_tensor, void* workspace, int64_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     OCBNN_REQUIRE(x && g && h && out_phi && n >= 1 && d >= 1 && row_begin >= 0 && row_begin + n_rows <= n, OCBNN_EINVAL,
                   "ocbnn_svgd_phi: bad argument");
-    OCBNN_REQUIRE(use_tensor <= 0, OCBNN_EUNSUPPORTED, "tcgen05 SVGD path is not built in this revision");
     if (n_rows == 0) return OCBNN_OK;
+    if (want_tensor(use_tensor, n)) {
+        OCBNN_REQUIRE(workspace && workspace_bytes >= ocbnn_svgd_workspace_bytes(n, d, n_rows, 1), OCBNN_EINVAL,
+                      "ocbnn_svgd_phi: workspace too small for the tensor path (see ocbnn_svgd_workspace_bytes)");
+        void* tcws = reinterpret_cast<char*>(workspace) + 3 * kBins * sizeof(uint32_t) + 256;
+        if (use_tensor != 2) {
+            int rc = tc::tc_svgd_prepare(x, n, d, row_begin, n_rows, tcws, workspace_bytes - (3 * kBins * sizeof(uint32_t) + 256), st);
+            if (rc) return rc;
+        }
+        return tc::tc_svgd_phi(g, h, n, d, row_begin, n_rows, out_phi, tcws, st);
+    }
     if (d <= 64) {
         unsigned blocks = (unsigned)((n_rows + kRowsPerCta - 1) / kRowsPerCta);
         if (d <= 32) k_svgd_phi_small<8><<<blocks, kRowsPerCta * kLpr, 0, st>>>(x, g, n, (int)d, row_begin, n_rows, h, out_phi);
@@ -368,7 +416,7 @@ extern "C" OCBNN_API int ocbnn_svgd_phi(const float* x, const float* g, int64_t 
         OCBNN_LAUNCH_CHECK();
         return OCBNN_OK;
     }
-    const int64_t off = 3 * kBins * sizeof(uint32_t) + 64;
+    const int64_t off = 3 * kBins * sizeof(uint32_t) + 256;
     OCBNN_REQUIRE(workspace && workspace_bytes >= off + (n_rows * n + n_rows) * (int64_t)sizeof(float), OCBNN_EINVAL,
                   "ocbnn_svgd_phi: workspace too small for the wide exact path (see ocbnn_svgd_workspace_bytes)");
     float* kmat = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + off);

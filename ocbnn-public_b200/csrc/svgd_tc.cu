@@ -55,27 +55,23 @@ struct EpiStore {          // C[split][row][col] = acc
     }
 };
 
-struct EpiGram {           // D2[row][col] = max(r_row + r_col - 2 S, 0)
+// Gram epilogue: d2[row][col] = max(r_i + r_j - 2 S, 0) for the local rows of a rank (i = row_begin + row), zero in the n..n4 padding
+struct EpiGramRows {
     float* d2;
     const float* r;
-    long long n;
+    long long n, n4, row_begin, n_rows;
     __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[32], int) const {
-        if (row >= n) return;
-        const float ri = r[row];
-        float* dst = d2 + (long long)row * n + col0;
-        if (col0 + 32 <= n && (n & 3) == 0) {
+        if (row >= n_rows) return;
+        const float ri = r[row_begin + row];
+        float* dst = d2 + (long long)row * n4 + col0;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float4 rj = *reinterpret_cast<const float4*>(r + col0 + i);
-                *reinterpret_cast<float4*>(dst + i) =
-                    make_float4(fmaxf(fmaf(-2.f, acc[i], ri + rj.x), 0.f), fmaxf(fmaf(-2.f, acc[i + 1], ri + rj.y), 0.f),
-                                fmaxf(fmaf(-2.f, acc[i + 2], ri + rj.z), 0.f), fmaxf(fmaf(-2.f, acc[i + 3], ri + rj.w), 0.f));
+        for (int i = 0; i < 32; ++i)
+            if (col0 + i < n4) {
+                // the diagonal is exactly 0 (the Gram form would leave the tensor core's accumulation bias of S_ii there, and
+                // K_ii = 1 is the largest term of every row)
+                const bool off_diag = col0 + i < n && col0 + i != row_begin + row;
+                dst[i] = off_diag ? fmaxf(fmaf(-2.f, acc[i], ri + r[col0 + i]), 0.f) : 0.f;
             }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (col0 + i < n) dst[i] = fmaxf(fmaf(-2.f, acc[i], ri + r[col0 + i]), 0.f);
-        }
     }
 };
 
@@ -93,6 +89,11 @@ static int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     return OCBNN_OK;
 }
 
+static unsigned grid_for_ll(long long n) {
+    long long b = (n + 255) / 256;
+    return (unsigned)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
+}
+
 // hi = x with the 13 low mantissa bits cleared (exact tf32), lo = x - hi (exact in fp32); optional column padding with zeros
 __global__ void __launch_bounds__(256)
 k_split_tf32(const float* __restrict__ x, long long rows, long long cols, long long ld_out, float* __restrict__ hi, float* __restrict__ lo) {
@@ -107,13 +108,330 @@ k_split_tf32(const float* __restrict__ x, long long rows, long long cols, long l
     }
 }
 
+
+// =========================================================================================================================
+// SVGD tensor pipeline.  Workspace layout (floats unless noted), n4 = n rounded up to 4, dp = D rounded up to 32:
+//   hdr (256 B) | mean[dp] | r[n] | s[n] | xc_hi[n x dp] | xc_lo[n x dp] | d2[n_rows x n4] | k_hi, k_lo[n_rows x n4] |
+//   vt_hi, vt_lo[2dp x n4] | rowsum[n_rows] | o[splits x n_rows x 2dp]
+// =========================================================================================================================
+struct TcWs {
+    long long n, d, n4, dp, n_rows, row_begin;
+    int splits, bn;
+    float *mean, *r, *s, *xc_hi, *xc_lo, *d2, *k_hi, *k_lo, *vt_hi, *vt_lo, *rowsum, *o;
+    unsigned* hist;
+    unsigned long long* state;
+    long long bytes;
+};
+
+static int pick_splits(long long n_rows, long long n4, int two_dp, int bn) {
+    const long long tiles = ((n_rows + kBM - 1) / kBM) * ((two_dp + bn - 1) / bn);
+    long long s = (148 + tiles - 1) / tiles;
+    const long long kb = (n4 + kBK - 1) / kBK;
+    if (s > 16) s = 16;
+    if (s > kb) s = kb;
+    return (int)(s < 1 ? 1 : s);
+}
+
+static TcWs carve(void* workspace, long long n, long long d, long long row_begin, long long n_rows) {
+    TcWs w{};
+    w.n = n; w.d = d; w.n4 = (n + 3) / 4 * 4; w.dp = (d + 31) / 32 * 32; w.n_rows = n_rows; w.row_begin = row_begin;
+    w.bn = 2 * w.dp <= 64 ? 64 : 128;
+    w.splits = pick_splits(n_rows, w.n4, (int)(2 * w.dp), w.bn);
+    char* p = reinterpret_cast<char*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    auto take = [&](long long floats) { float* q = reinterpret_cast<float*>(p); p += (floats * 4 + 255) / 256 * 256; return q; };
+    w.hist = reinterpret_cast<unsigned*>(take(3 * 2048));
+    w.state = reinterpret_cast<unsigned long long*>(take(16));
+    w.mean = take(w.dp);
+    w.r = take(n);
+    w.s = take(n);
+    w.xc_hi = take(n * w.dp);
+    w.xc_lo = take(n * w.dp);
+    w.d2 = take(n_rows * w.n4);
+    w.k_hi = take(n_rows * w.n4);
+    w.k_lo = take(n_rows * w.n4);
+    w.vt_hi = take(2 * w.dp * w.n4);
+    w.vt_lo = take(2 * w.dp * w.n4);
+    w.rowsum = take(n_rows);
+    w.o = take((long long)w.splits * n_rows * 2 * w.dp);
+    w.bytes = p - reinterpret_cast<char*>(workspace);
+    return w;
+}
+
+// column means of x (n x d): one block per column
+__global__ void __launch_bounds__(256) k_colmean(const float* __restrict__ x, long long n, int d, int dp, float* __restrict__ mean) {
+    const int c = blockIdx.x;
+    double s = 0.0;
+    if (c < d)
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) s += (double)x[i * d + c];
+    __shared__ double red[8];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        mean[c] = c < d ? (float)(s / (double)n) : 0.f;
+    }
+}
+
+// one warp per row: xc = x - mean split into tf32 hi/lo (zero padded to dp), r = ||xc||^2, s = sum xc
+__global__ void __launch_bounds__(256)
+k_center_split(const float* __restrict__ x, const float* __restrict__ mean, long long n, int d, int dp, float* __restrict__ hi,
+               float* __restrict__ lo, float* __restrict__ r, float* __restrict__ ssum) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double rr = 0.0, ss = 0.0;
+    for (int c = lane; c < dp; c += 32) {
+        const float v = c < d ? x[row * d + c] - mean[c] : 0.f;
+        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        hi[row * dp + c] = h;
+        lo[row * dp + c] = v - h;
+        rr += (double)v * (double)v;
+        ss += (double)v;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        rr += __shfl_xor_sync(0xffffffffu, rr, off);
+        ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    }
+    if (lane == 0) { r[row] = (float)rr; ssum[row] = (float)ss; }
+}
+
+// exact squared distances for small D (dp <= 64): d2[t][j] = ||xc_i - xc_j||^2 by direct differences
+template <int DP>
+__global__ void __launch_bounds__(256)
+k_d2_direct(const float* __restrict__ hi, const float* __restrict__ lo, long long n, long long n4, long long row_begin, long long n_rows,
+            float* __restrict__ d2) {
+    __shared__ float xi[16][DP + 1];
+    __shared__ float xj[64][DP + 1];
+    const long long t0 = (long long)blockIdx.y * 16, j0 = (long long)blockIdx.x * 64;
+    for (int idx = threadIdx.x; idx < 16 * DP; idx += 256) {
+        int rr = idx / DP, c = idx % DP;
+        long long i = row_begin + t0 + rr;
+        xi[rr][c] = (t0 + rr < n_rows) ? hi[i * DP + c] + lo[i * DP + c] : 0.f;
+    }
+    for (int idx = threadIdx.x; idx < 64 * DP; idx += 256) {
+        int rr = idx / DP, c = idx % DP;
+        long long j = j0 + rr;
+        xj[rr][c] = j < n ? hi[j * DP + c] + lo[j * DP + c] : 0.f;
+    }
+    __syncthreads();
+    const int jj = threadIdx.x & 63, tq = threadIdx.x >> 6;      // 4 rows per thread
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int rr = tq * 4 + a;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < DP; ++c) {
+            const float df = xi[rr][c] - xj[jj][c];
+            acc = fmaf(df, df, acc);
+        }
+        const long long t = t0 + rr, j = j0 + jj;
+        if (t < n_rows && j < n4) d2[t * n4 + j] = j < n ? acc : 0.f;
+    }
+}
+
+// radix-select histogram pass over the eps-perturbed distances reconstructed from d2:
+//   ||x_i - x_j + eps||^2 = d2 + 2 eps (s_i - s_j) + D eps^2 ,  pairs i < j only, exact zeros dropped.
+// Equal bins inside a warp are combined with __match_any_sync before touching shared memory.
+__global__ void __launch_bounds__(256)
+k_hist_d2(const float* __restrict__ d2, const float* __restrict__ ssum, long long n, long long n4, int d, long long row_begin, long long n_rows,
+          int pass, unsigned* __restrict__ hist, const unsigned long long* __restrict__ state) {
+    __shared__ unsigned sh[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh[i] = 0u;
+    __syncthreads();
+    const unsigned prefix = pass > 0 ? (unsigned)state[0] : 0u;
+    const float eps = 1e-6f, deps2 = (float)d * 1e-12f;
+    for (long long t = blockIdx.x; t < n_rows; t += gridDim.x) {
+        const long long i = row_begin + t;
+        const float si = ssum[i];
+        for (long long j0 = (i + 1) / 256 * 256; j0 < n; j0 += 256) {
+            const long long j = j0 + threadIdx.x;
+            unsigned bin = 0xFFFFFFFFu;
+            if (j > i && j < n) {
+                const float v = sqrtf(fmaxf(d2[t * n4 + j] + 2.f * eps * (si - ssum[j]) + deps2, 0.f));
+                const unsigned b = __float_as_uint(v);
+                if (b != 0u) {
+                    if (pass == 0) bin = b >> 21;
+                    else if (pass == 1) { if ((b >> 21) == (prefix >> 21)) bin = (b >> 10) & 2047u; }
+                    else if ((b >> 10) == (prefix >> 10)) bin = b & 1023u;
+                }
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            if (bin != 0xFFFFFFFFu && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[bin], (unsigned)__popc(peers));
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < 2048; b += blockDim.x)
+        if (sh[b]) atomicAdd(&hist[pass * 2048 + b], sh[b]);
+}
+
+// K = exp(-d2/h) split into tf32 hi/lo, row sums; one block per row
+__global__ void __launch_bounds__(256)
+k_kmat_split(const float* __restrict__ d2, const float* __restrict__ hptr, long long n, long long n4, long long n_rows, float* __restrict__ k_hi,
+             float* __restrict__ k_lo, float* __restrict__ rowsum) {
+    const float nih = -1.f / *hptr;
+    for (long long t = blockIdx.x; t < n_rows; t += gridDim.x) {
+        float rs = 0.f;
+        for (long long j = threadIdx.x * 4; j < n4; j += 256 * 4) {
+            const float4 v = *reinterpret_cast<const float4*>(d2 + t * n4 + j);
+            float k[4] = {expf(v.x * nih), expf(v.y * nih), expf(v.z * nih), expf(v.w * nih)};
+            float h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (j + e >= n) k[e] = 0.f;
+                h[e] = __uint_as_float(__float_as_uint(k[e]) & 0xFFFFE000u);
+                l[e] = k[e] - h[e];
+                rs += k[e];
+            }
+            *reinterpret_cast<float4*>(k_hi + t * n4 + j) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(k_lo + t * n4 + j) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+        __shared__ float red[8];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = rs;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f;
+            for (int w = 0; w < 8; ++w) s += red[w];
+            rowsum[t] = s;
+        }
+    }
+}
+
+// Vt[c][j] : c < dp -> g[j][c] ; c >= dp -> xc[j][c - dp] ; split hi/lo, zero padded.  32x32 shared-memory transpose.
+__global__ void __launch_bounds__(256)
+k_vt_split(const float* __restrict__ g, const float* __restrict__ xc_hi, const float* __restrict__ xc_lo, long long n, long long n4, int d, int dp,
+           float* __restrict__ vt_hi, float* __restrict__ vt_lo) {
+    __shared__ float tile[32][33];
+    const long long j0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 8 rows per pass
+    for (int rr = ty; rr < 32; rr += 8) {
+        const long long j = j0 + rr;
+        const int c = c0 + tx;
+        float v = 0.f;
+        if (j < n) {
+            if (c < dp) v = c < d ? g[j * d + c] : 0.f;
+            else v = xc_hi[j * dp + (c - dp)] + xc_lo[j * dp + (c - dp)];
+        }
+        tile[rr][tx] = v;
+    }
+    __syncthreads();
+    for (int rr = ty; rr < 32; rr += 8) {
+        const int c = c0 + rr;
+        const long long j = j0 + tx;
+        if (j < n4) {
+            const float v = tile[tx][rr];
+            const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            vt_hi[(long long)c * n4 + j] = h;
+            vt_lo[(long long)c * n4 + j] = v - h;
+        }
+    }
+}
+
+// phi[t][c] = (O_G - (2/h)(O_X - xc_i[c] rowsum_t)) / n, summing the K splits
+__global__ void __launch_bounds__(256)
+k_phi_finalize(const float* __restrict__ o, int splits, const float* __restrict__ rowsum, const float* __restrict__ xc_hi,
+               const float* __restrict__ xc_lo, const float* __restrict__ hptr, long long n, int d, int dp, long long row_begin, long long n_rows,
+               float* __restrict__ phi) {
+    const float c2 = 2.f / *hptr, invn = 1.f / (float)n;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long tot = n_rows * d, stride = (long long)gridDim.x * blockDim.x;
+    for (; idx < tot; idx += stride) {
+        const long long t = idx / d;
+        const int c = (int)(idx - t * d);
+        float og = 0.f, ox = 0.f;
+        for (int sp = 0; sp < splits; ++sp) {
+            const float* base = o + ((long long)sp * n_rows + t) * 2 * dp;
+            og += base[c];
+            ox += base[dp + c];
+        }
+        const long long i = row_begin + t;
+        const float xi = xc_hi[i * dp + c] + xc_lo[i * dp + c];
+        phi[idx] = (og - c2 * (ox - xi * rowsum[t])) * invn;
+    }
+}
+
+// centre + split X, squared distances of rows [row_begin, row_begin + n_rows) into the workspace
+static int tc_prepare(const TcWs& w, const float* x, cudaStream_t st) {
+    k_colmean<<<(unsigned)w.dp, 256, 0, st>>>(x, w.n, (int)w.d, (int)w.dp, w.mean);
+    OCBNN_LAUNCH_CHECK();
+    k_center_split<<<(unsigned)((w.n * 32 + 255) / 256), 256, 0, st>>>(x, w.mean, w.n, (int)w.d, (int)w.dp, w.xc_hi, w.xc_lo, w.r, w.s);
+    OCBNN_LAUNCH_CHECK();
+    if (w.dp <= 64) {
+        dim3 grid((unsigned)((w.n4 + 63) / 64), (unsigned)((w.n_rows + 15) / 16));
+        if (w.dp == 32) k_d2_direct<32><<<grid, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.n, w.n4, w.row_begin, w.n_rows, w.d2);
+        else k_d2_direct<64><<<grid, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.n, w.n4, w.row_begin, w.n_rows, w.d2);
+        OCBNN_LAUNCH_CHECK();
+        return OCBNN_OK;
+    }
+    // Gram on tensor cores: A = rows of this rank, B = all rows
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    int rc;
+    if ((rc = make_tmap(&ta_hi, w.xc_hi + w.row_begin * w.dp, w.n_rows, w.dp, kBM))) return rc;
+    if ((rc = make_tmap(&ta_lo, w.xc_lo + w.row_begin * w.dp, w.n_rows, w.dp, kBM))) return rc;
+    if ((rc = make_tmap(&tb_hi, w.xc_hi, w.n, w.dp, 128))) return rc;
+    if ((rc = make_tmap(&tb_lo, w.xc_lo, w.n, w.dp, 128))) return rc;
+    EpiGramRows epi{w.d2, w.r, w.n, w.n4, w.row_begin, w.n_rows};
+    return launch_gemm<128>(ta_hi, ta_lo, tb_hi, tb_lo, epi, w.n_rows, w.n, w.dp, 1, st);
+}
+
+static int tc_phi(const TcWs& w, const float* g, const float* h, float* phi, cudaStream_t st) {
+    k_kmat_split<<<(unsigned)(w.n_rows < 148 * 8 ? w.n_rows : 148 * 8), 256, 0, st>>>(w.d2, h, w.n, w.n4, w.n_rows, w.k_hi, w.k_lo, w.rowsum);
+    OCBNN_LAUNCH_CHECK();
+    dim3 gv((unsigned)((w.n4 + 31) / 32), (unsigned)(2 * w.dp / 32));
+    k_vt_split<<<gv, 256, 0, st>>>(g, w.xc_hi, w.xc_lo, w.n, w.n4, (int)w.d, (int)w.dp, w.vt_hi, w.vt_lo);
+    OCBNN_LAUNCH_CHECK();
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    int rc;
+    if ((rc = make_tmap(&ta_hi, w.k_hi, w.n_rows, w.n4, kBM))) return rc;
+    if ((rc = make_tmap(&ta_lo, w.k_lo, w.n_rows, w.n4, kBM))) return rc;
+    if ((rc = make_tmap(&tb_hi, w.vt_hi, 2 * w.dp, w.n4, w.bn))) return rc;
+    if ((rc = make_tmap(&tb_lo, w.vt_lo, 2 * w.dp, w.n4, w.bn))) return rc;
+    EpiStore epi{w.o, 2 * w.dp, w.n_rows * 2 * w.dp, (int)w.n_rows, (int)(2 * w.dp)};
+    rc = w.bn == 64 ? launch_gemm<64>(ta_hi, ta_lo, tb_hi, tb_lo, epi, w.n_rows, 2 * w.dp, w.n4, w.splits, st)
+                    : launch_gemm<128>(ta_hi, ta_lo, tb_hi, tb_lo, epi, w.n_rows, 2 * w.dp, w.n4, w.splits, st);
+    if (rc) return rc;
+    k_phi_finalize<<<grid_for_ll(w.n_rows * w.d), 256, 0, st>>>(w.o, w.splits, w.rowsum, w.xc_hi, w.xc_lo, h, w.n, (int)w.d, (int)w.dp, w.row_begin,
+                                                              w.n_rows, phi);
+    OCBNN_LAUNCH_CHECK();
+    return OCBNN_OK;
+}
+
+long long tc_workspace_bytes(long long n, long long d, long long n_rows) { return carve(nullptr, n, d, 0, n_rows).bytes + 512; }
+
+int tc_svgd_prepare(const float* x, long long n, long long d, long long row_begin, long long n_rows, void* ws, long long ws_bytes, cudaStream_t st) {
+    OCBNN_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(n, d, n_rows), OCBNN_EINVAL, "SVGD tensor path: workspace too small");
+    return tc_prepare(carve(ws, n, d, row_begin, n_rows), x, st);
+}
+int tc_svgd_hist(long long n, long long d, long long row_begin, long long n_rows, int pass, unsigned* hist, const unsigned long long* state, void* ws,
+                 cudaStream_t st) {
+    TcWs w = carve(ws, n, d, row_begin, n_rows);
+    k_hist_d2<<<(unsigned)(n_rows < 148 * 8 ? n_rows : 148 * 8), 256, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, row_begin, n_rows, pass, hist, state);
+    OCBNN_LAUNCH_CHECK();
+    return OCBNN_OK;
+}
+int tc_svgd_phi(const float* g, const float* h, long long n, long long d, long long row_begin, long long n_rows, float* phi, void* ws, cudaStream_t st) {
+    return tc_phi(carve(ws, n, d, row_begin, n_rows), g, h, phi, st);
+}
+void tc_ws_hist(void* ws, long long n, long long d, long long n_rows, unsigned** hist, unsigned long long** state) {
+    TcWs w = carve(ws, n, d, 0, n_rows);
+    *hist = w.hist;
+    *state = w.state;
+}
+
 }  // namespace tc
 }  // namespace ocbnn
 
 using namespace ocbnn;
 using namespace ocbnn::tc;
 
-static unsigned grid_for(long long n) {
+static unsigned grid_for(long long n) {   // (used by the exported GEMM)
     long long b = (n + 255) / 256;
     return (unsigned)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
 }

@@ -79,10 +79,13 @@ _SIGS = {
     "ocbnn_svgd_hist_pass": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "ocbnn_svgd_select_update": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
-    "ocbnn_svgd_bandwidth": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ocbnn_svgd_bandwidth": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ocbnn_svgd_prepare": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ocbnn_svgd_hist_pass_prepared": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p]),
     "ocbnn_svgd_phi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                  C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
-    "ocbnn_svgd_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
+    "ocbnn_svgd_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64, C.c_int32]),
     "ocbnn_gemm_tf32x3_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64]),
     "ocbnn_gemm_tf32x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "ocbnn_adagrad_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p]),
@@ -261,16 +264,38 @@ class DeviceProblem:
 
 # ---- K3 (problem independent) ------------------------------------------------------------------------------
 
-def svgd_workspace(n, d, device):
-    nbytes = int(lib().ocbnn_svgd_workspace_bytes(n, d))
+SVGD_HDR_BYTES = 3 * 2048 * 4 + 256      # select histogram (3 x 2048 u32) + select state at the start of every SVGD workspace
+
+
+def svgd_use_tensor(use_tensor, n):
+    """Resolve the use_tensor knob (0 SIMT, 1 tcgen05, -1 choose) to a bool, the same way the library does."""
+    return use_tensor > 0 or (use_tensor < 0 and n >= 1024)
+
+
+def svgd_workspace(n, d, device, n_rows=None, use_tensor=-1):
+    nbytes = int(lib().ocbnn_svgd_workspace_bytes(n, d, n if n_rows is None else n_rows, int(use_tensor)))
     return torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=device)
 
 
-def svgd_bandwidth(X, workspace, out_h=None):
+def svgd_ws_views(workspace):
+    """(hist int32[3*2048], state int64[4]) views of the workspace header (what a multi-GPU caller all-reduces)."""
+    hist = workspace[:3 * 2048 * 4 // 8].view(torch.int32)
+    state = workspace[3 * 2048 * 4 // 8:3 * 2048 * 4 // 8 + 4]
+    return hist, state
+
+
+def svgd_bandwidth(X, workspace, out_h=None, use_tensor=0):
     X = _f32(X, "X")
     h = out_h if out_h is not None else torch.empty(1, device=X.device)
-    check(lib().ocbnn_svgd_bandwidth(_ptr(X), X.shape[0], X.shape[1], _ptr(h), _ptr(workspace), workspace.numel() * 8, _stream()))
+    check(lib().ocbnn_svgd_bandwidth(_ptr(X), X.shape[0], X.shape[1], _ptr(h), int(use_tensor), _ptr(workspace), workspace.numel() * 8, _stream()))
     return h
+
+
+def svgd_prepare(X, row_begin, n_rows, workspace, use_tensor=1):
+    X = _f32(X, "X")
+    ws = workspace[SVGD_HDR_BYTES // 8:]
+    check(lib().ocbnn_svgd_prepare(_ptr(X), X.shape[0], X.shape[1], int(row_begin), int(n_rows), int(use_tensor), _ptr(ws), ws.numel() * 8,
+                                   _stream()))
 
 
 def svgd_hist_pass(X, row_start, row_step, n_rows, pass_, hist, state):
@@ -278,11 +303,16 @@ def svgd_hist_pass(X, row_start, row_step, n_rows, pass_, hist, state):
                                      _ptr(state), _stream()))
 
 
+def svgd_hist_pass_prepared(n, d, row_begin, n_rows, pass_, hist, state, workspace):
+    ws = workspace[SVGD_HDR_BYTES // 8:]
+    check(lib().ocbnn_svgd_hist_pass_prepared(int(n), int(d), int(row_begin), int(n_rows), int(pass_), _ptr(hist), _ptr(state), _ptr(ws), _stream()))
+
+
 def svgd_select_update(pass_, hist, state, n, out_h):
     check(lib().ocbnn_svgd_select_update(int(pass_), _ptr(hist), _ptr(state), int(n), _ptr(out_h), _stream()))
 
 
-def svgd_phi(X, G, h, row_begin, n_rows, workspace, use_tensor=-1, out=None):
+def svgd_phi(X, G, h, row_begin, n_rows, workspace, use_tensor=0, out=None):
     X, G = _f32(X, "X"), _f32(G, "G")
     phi = out if out is not None else torch.empty(n_rows, X.shape[1], device=X.device)
     check(lib().ocbnn_svgd_phi(_ptr(X), _ptr(G), X.shape[0], X.shape[1], int(row_begin), int(n_rows), _ptr(h), _ptr(phi), int(use_tensor),

@@ -214,37 +214,40 @@ class SGLDMixin:
 class SVGDMixin:
     """Stein Variational Gradient Descent (inference.py:203-292); particles shard over ranks."""
 
-    def svgd_setup(self, particles):
-        """particles: (n, D) host or device tensor; this rank keeps rows [lo, hi)."""
+    def svgd_setup(self, particles, use_tensor=-1):
+        """particles: (n, D) host or device tensor; this rank keeps rows [lo, hi).  use_tensor: 0 exact SIMT kernels,
+        1 tcgen05 path, -1 choose (tensor path from 1024 particles up)."""
         dev = self._device()
         n = particles.shape[0]
         lo, hi = D.shard(n)
-        st = {"n": n, "lo": lo, "hi": hi,
-              "X": particles[lo:hi].to(dev, torch.float32).contiguous(),
-              "acc": torch.zeros(hi - lo, self.nweights, device=dev),
-              "h": torch.empty(1, device=dev),
-              "hist": torch.zeros(3 * 2048, dtype=torch.int32, device=dev),
-              "state": torch.zeros(4, dtype=torch.int64, device=dev)}
-        st["ws"] = E.svgd_workspace(n, self.nweights, dev)
-        return st
+        tensor = E.svgd_use_tensor(int(use_tensor), n)
+        ws = E.svgd_workspace(n, self.nweights, dev, n_rows=(n if D.world() == 1 else hi - lo), use_tensor=1 if tensor else 0)
+        hist, state = E.svgd_ws_views(ws)
+        return {"n": n, "lo": lo, "hi": hi, "tensor": tensor, "ws": ws, "hist": hist, "state": state,
+                "X": particles[lo:hi].to(dev, torch.float32).contiguous(),
+                "acc": torch.zeros(hi - lo, self.nweights, device=dev), "h": torch.empty(1, device=dev)}
 
-    def svgd_epoch(self, st, epoch, with_data, use_tensor=-1):
+    def svgd_epoch(self, st, epoch, with_data, use_tensor=None):
         """One SVGD epoch on the device: gradients (K1), all-gather, bandwidth (K3a), phi (K3b), Adagrad (K3c)."""
         prob = self.engine_problem()
         X = st["X"]
+        tensor = st["tensor"] if use_tensor is None else E.svgd_use_tensor(int(use_tensor), st["n"]) and st["tensor"]
         _, G = prob.logpost_grad(X, _batch_for(self, epoch), with_data, want_lp=False)
         Xall, Gall = D.gather_cat(X, dim=0), D.gather_cat(G, dim=0)
-        n = st["n"]
+        n, lo, rows = st["n"], st["lo"], st["hi"] - st["lo"]
         if D.world() == 1:
-            E.svgd_bandwidth(Xall, st["ws"], st["h"])
+            E.svgd_bandwidth(Xall, st["ws"], st["h"], use_tensor=1 if tensor else 0)
         else:                                   # exact global median: all-reduce the select histograms between passes
+            if tensor:
+                E.svgd_prepare(Xall, lo, rows, st["ws"])
             for p in range(3):
-                rows = len(range(D.rank(), n, D.world()))
-                E.svgd_hist_pass(Xall, D.rank(), D.world(), rows, p, st["hist"], st["state"])
-                seg = st["hist"][p * 2048:(p + 1) * 2048]
-                D.all_sum_(seg)
+                if tensor:
+                    E.svgd_hist_pass_prepared(n, self.nweights, lo, rows, p, st["hist"], st["state"], st["ws"])
+                else:
+                    E.svgd_hist_pass(Xall, D.rank(), D.world(), len(range(D.rank(), n, D.world())), p, st["hist"], st["state"])
+                D.all_sum_(st["hist"][p * 2048:(p + 1) * 2048])
                 E.svgd_select_update(p, st["hist"], st["state"], n, st["h"])
-        phi = E.svgd_phi(Xall, Gall, st["h"], st["lo"], st["hi"] - st["lo"], st["ws"], use_tensor)
+        phi = E.svgd_phi(Xall, Gall, st["h"], lo, rows, st["ws"], 2 if tensor else 0)
         E.adagrad_step(X, st["acc"], phi, self.svgd_init_lr, -1.0)      # particles.grad = -update (inference.py:280)
         st["phi"] = phi
         return st
@@ -254,10 +257,9 @@ class SVGDMixin:
         logging.info(f"[{self.uid}] Posterior Sample #{infer_id}: Beginning SVGD inference...")
         start_time = time.time()
         self.particles = Normal(0, self.sigma_w).sample(torch.Size([self.infer_nsamples, self.nweights]))
-        st = self.svgd_setup(self.particles)
-        tens = int(getattr(self, "svgd_tensor", -1))
+        st = self.svgd_setup(self.particles, int(getattr(self, "svgd_tensor", -1)))
         for epoch in range(1, self.svgd_epochs + 1):
-            self.svgd_epoch(st, epoch, with_data, tens)
+            self.svgd_epoch(st, epoch, with_data)
             if verbose and epoch % 10 == 0:
                 logging.info(f"  Epoch {epoch} reached.")
         end_time = time.time()

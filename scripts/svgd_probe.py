@@ -23,15 +23,24 @@ for n in [int(a) for a in sys.argv[2:]] or [4096, 16384]:
         X = (m.aocp_mean[None] + 3 * m.aocp_std[None] * torch.randn(n, m.nweights)).to(dev).contiguous()
     else:
         X = torch.randn(n, m.nweights, device=dev)
-    ws = E.svgd_workspace(n, m.nweights, dev)
+    use_t = int(os.environ.get("SVGD_TENSOR", "0"))
+    ws = E.svgd_workspace(n, m.nweights, dev, use_tensor=use_t)
     h = torch.empty(1, device=dev); acc = torch.zeros_like(X)
     G = torch.empty_like(X); phi = torch.empty_like(X)
-    use_t = int(os.environ.get("SVGD_TENSOR", "0"))
     r = {}
     r["K1 grad"] = t(lambda: prob.logpost_grad(X, (1, m.nbatches) if m.nbatches else (0, 1), True, want_lp=False, out_grad=G))
-    r["K3a bandwidth"] = t(lambda: E.svgd_bandwidth(X, ws, h))
-    r["K3b phi"] = t(lambda: E.svgd_phi(X, G, h, 0, n, ws, use_t, out=phi))
+    r["K3a bandwidth"] = t(lambda: E.svgd_bandwidth(X, ws, h, use_tensor=use_t))
+    r["K3b phi"] = t(lambda: E.svgd_phi(X, G, h, 0, n, ws, 2 if use_t else 0, out=phi))
     r["K3c adagrad"] = t(lambda: E.adagrad_step(X.clone(), acc, phi, 0.5, -1.0))
-    st = m.svgd_setup(X.cpu())
-    r["epoch (host API)"] = t(lambda: m.svgd_epoch(st, 1, True, use_tensor=use_t))
+    def raw_epoch():
+        prob.logpost_grad(X, (1, m.nbatches) if m.nbatches else (0, 1), True, want_lp=False, out_grad=G)
+        E.svgd_bandwidth(X, ws, h, use_tensor=use_t)
+        E.svgd_phi(X, G, h, 0, n, ws, 2 if use_t else 0, out=phi)
+        E.adagrad_step(X, acc, phi, 1e-6, -1.0)
+    r["epoch (raw engine calls)"] = t(raw_epoch)
+    import time
+    torch.cuda.synchronize(); t0 = time.perf_counter(); raw_epoch(); t1 = time.perf_counter(); torch.cuda.synchronize()
+    r["host time of raw epoch"] = (t1 - t0) * 1e3
+    st = m.svgd_setup(X.cpu(), use_tensor=use_t)
+    r["epoch (host API)"] = t(lambda: m.svgd_epoch(st, 1, True))
     print(wl, "n", n, "D", m.nweights, {k: f"{v:.3f} ms" for k, v in r.items()}, "particle-iters/s %.3e" % (n / (r["epoch (host API)"] * 1e-3)))

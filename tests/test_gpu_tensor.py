@@ -21,3 +21,44 @@ def test_gemm_tf32x3(m, n, k):
     assert err < 2e-6, err
     plain_tf32 = 5e-4
     assert err < plain_tf32 / 50
+
+
+@pytest.mark.parametrize("n,D", [(1500, 31), (1111, 63), (1100, 200), (2050, 41)])
+def test_svgd_tensor_path_matches_float64_oracle(n, D):
+    """K3a/K3b on tcgen05 (3xTF32, TMA): bandwidth and phi against the float64 closed form and the exact SIMT arm."""
+    gen = torch.Generator().manual_seed(n + D)
+    X = torch.randn(n, D, generator=gen) * 0.8 + 0.3          # non-zero mean: the path centres X
+    G = torch.randn(n, D, generator=gen) * 5
+    Xd, Gd = X.cuda(), G.cuda()
+    ws = E.svgd_workspace(n, D, Xd.device, use_tensor=1)
+    h_t = E.svgd_bandwidth(Xd, ws, use_tensor=1)
+    h_s = E.svgd_bandwidth(Xd, E.svgd_workspace(n, D, Xd.device, use_tensor=0), use_tensor=0)
+    h_ref = float(orc.svgd_rbf_h(X.numpy()))
+    assert abs(float(h_s) - h_ref) <= 2e-6 * h_ref
+    assert abs(float(h_t) - h_ref) <= (3e-6 if D <= 64 else 1e-5) * h_ref, (float(h_t), h_ref)
+    phi_t = E.svgd_phi(Xd, Gd, h_t, 0, n, ws, use_tensor=2)                     # workspace prepared by svgd_bandwidth
+    ref = orc.svgd_phi(X.numpy().astype(np.float64), G.numpy().astype(np.float64), float(h_t), dtype=np.float64)
+    err = np.linalg.norm(phi_t.cpu().numpy() - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert err.max() < 1e-5, err.max()
+    phi_1 = E.svgd_phi(Xd, Gd, h_t, 0, n, ws, use_tensor=1)                     # prepares the workspace itself
+    assert torch.equal(phi_1, phi_t)
+    ws_part = E.svgd_workspace(n, D, Xd.device, n_rows=157, use_tensor=1)
+    part = E.svgd_phi(Xd, Gd, h_t, 300, 157, ws_part, use_tensor=1)             # a rank's row share
+    assert (part - phi_t[300:457]).norm() / phi_t[300:457].norm() < 2e-6
+
+
+def test_svgd_epoch_tensor_vs_simt():
+    import os, tempfile
+    from ocbnn_b200 import workloads
+    os.chdir(tempfile.mkdtemp())
+    n = 2048
+    m = workloads.build("W4", seed=0, infer_nsamples=n)
+    X0 = torch.randn(n, m.nweights, generator=torch.Generator().manual_seed(3))
+    st_t, st_s = m.svgd_setup(X0, use_tensor=1), m.svgd_setup(X0, use_tensor=0)
+    assert st_t["tensor"] and not st_s["tensor"]
+    for ep in range(1, 3):
+        m.svgd_epoch(st_t, ep, True)
+        m.svgd_epoch(st_s, ep, True)
+        assert abs(float(st_t["h"]) - float(st_s["h"])) <= 1e-5 * float(st_s["h"])
+        rel = (st_t["phi"] - st_s["phi"]).norm(dim=1) / st_s["phi"].norm(dim=1)
+        assert float(rel.max()) < 2e-5, float(rel.max())
