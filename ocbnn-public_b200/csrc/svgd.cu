@@ -111,35 +111,58 @@ __global__ void k_zero_u32(uint32_t* p, int n) {
     if (i < n) p[i] = 0u;
 }
 
-// after pass p: locate the bin holding the wanted rank; after pass 2 emit h
-__global__ void k_select_update(int pass, const uint32_t* __restrict__ hist, unsigned long long* __restrict__ state, long long n,
-                                float* __restrict__ out_h) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// after pass p: locate the bin holding the wanted rank; after pass 2 emit h.  One block of 256 threads: 8 bins per thread,
+// block-wide exclusive scan, the thread whose range contains the rank writes the new state.
+__global__ void __launch_bounds__(256)
+k_select_update(int pass, const uint32_t* __restrict__ hist, unsigned long long* __restrict__ state, long long n,
+                float* __restrict__ out_h) {
+    __shared__ unsigned long long wsum[8];
+    __shared__ unsigned long long s_tot;
     const uint32_t* h = hist + pass * kBins;
-    unsigned long long rank;
-    if (pass == 0) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    unsigned long long loc[8], mine = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { loc[k] = h[t * 8 + k]; mine += loc[k]; }
+    unsigned long long incl = mine;                         // inclusive scan over threads
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        unsigned long long v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    unsigned long long base = 0;
+    for (int w = 0; w < warp; ++w) base += wsum[w];
+    if (t == 0) {
         unsigned long long tot = 0;
-        for (int b = 0; b < kBins; ++b) tot += h[b];
-        state[2] = tot;
-        rank = tot ? (tot - 1) / 2 : 0;                 // LOWER median (torch.median)
-    } else {
-        rank = state[1];
+        for (int w = 0; w < 8; ++w) tot += wsum[w];
+        s_tot = tot;
     }
-    unsigned long long cum = 0;
-    int b = 0;
-    for (; b < kBins; ++b) {
-        if (cum + h[b] > rank) break;
-        cum += h[b];
-    }
-    if (b == kBins) b = kBins - 1;
-    uint32_t prefix = pass == 0 ? 0u : (uint32_t)state[0];
-    prefix |= pass == 0 ? ((uint32_t)b << 21) : pass == 1 ? ((uint32_t)b << 10) : (uint32_t)b;
-    state[0] = prefix;
-    state[1] = rank - cum;
-    if (pass == 2 && out_h) {
-        float med = __uint_as_float(prefix);
-        if (state[2] == 0) med = nanf("");             // torch: median of an empty tensor
-        *out_h = __fdiv_rn(__fmul_rn(med, med), (float)log((double)n));
+    __syncthreads();
+    const unsigned long long tot = s_tot;
+    const unsigned long long rank = pass == 0 ? (tot ? (tot - 1) / 2 : 0) : state[1];     // LOWER median (torch.median)
+    const unsigned long long excl = base + incl - mine;
+    const bool owner = tot == 0 ? t == 0 : (rank >= excl && rank < excl + mine);
+    __syncthreads();                                        // every thread has read state[1] before the owner overwrites it
+    if (owner) {
+        unsigned long long cum = excl;
+        int b = t * 8;
+        for (int k = 0; k < 8; ++k, ++b) {
+            if (cum + loc[k] > rank) break;
+            cum += loc[k];
+        }
+        if (b >= kBins) b = kBins - 1;
+        uint32_t prefix = pass == 0 ? 0u : (uint32_t)state[0];
+        prefix |= pass == 0 ? ((uint32_t)b << 21) : pass == 1 ? ((uint32_t)b << 10) : (uint32_t)b;
+        if (pass == 0) state[2] = tot;
+        const unsigned long long cands = pass == 0 ? tot : state[2];
+        state[0] = prefix;
+        state[1] = rank - cum;
+        if (pass == 2 && out_h) {
+            float med = __uint_as_float(prefix);
+            if (cands == 0) med = nanf("");                // torch: median of an empty tensor
+            *out_h = __fdiv_rn(__fmul_rn(med, med), (float)log((double)n));
+        }
     }
 }
 
@@ -328,7 +351,7 @@ extern "C" OCBNN_API int ocbnn_svgd_hist_pass(const float* x, int64_t n, int64_t
 
 extern "C" OCBNN_API int ocbnn_svgd_select_update(int32_t pass, uint32_t* hist, uint64_t* select_state, int64_t n, float* out_h, void* stream) {
     OCBNN_REQUIRE(hist && select_state && pass >= 0 && pass < 3, OCBNN_EINVAL, "ocbnn_svgd_select_update: bad argument");
-    k_select_update<<<1, 32, 0, (cudaStream_t)stream>>>(pass, hist, reinterpret_cast<unsigned long long*>(select_state), n, out_h);
+    k_select_update<<<1, 256, 0, (cudaStream_t)stream>>>(pass, hist, reinterpret_cast<unsigned long long*>(select_state), n, out_h);
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }
@@ -336,7 +359,8 @@ extern "C" OCBNN_API int ocbnn_svgd_select_update(int32_t pass, uint32_t* hist, 
 // tensor path (svgd_tc.cu)
 namespace ocbnn { namespace tc {
 long long tc_workspace_bytes(long long n, long long d, long long n_rows);
-int tc_svgd_prepare(const float* x, long long n, long long d, long long row_begin, long long n_rows, void* ws, long long ws_bytes, cudaStream_t st);
+int tc_svgd_prepare(const float* x, long long n, long long d, long long row_begin, long long n_rows, void* ws, long long ws_bytes, unsigned* hist0,
+                    bool* hist0_done, cudaStream_t st);
 int tc_svgd_hist(long long n, long long d, long long row_begin, long long n_rows, int pass, unsigned* hist, const unsigned long long* state, void* ws,
                  cudaStream_t st);
 int tc_svgd_phi(const float* g, const float* h, long long n, long long d, long long row_begin, long long n_rows, float* phi, void* ws, cudaStream_t st);
@@ -356,7 +380,7 @@ extern "C" OCBNN_API int ocbnn_svgd_prepare(const float* x, int64_t n, int64_t d
                                             void* workspace, int64_t workspace_bytes, void* stream) {
     OCBNN_REQUIRE(x && n >= 2 && d >= 1 && row_begin >= 0 && row_begin + n_rows <= n, OCBNN_EINVAL, "ocbnn_svgd_prepare: bad argument");
     if (!want_tensor(use_tensor, n) || n_rows == 0) return OCBNN_OK;
-    return tc::tc_svgd_prepare(x, n, d, row_begin, n_rows, workspace, workspace_bytes, (cudaStream_t)stream);
+    return tc::tc_svgd_prepare(x, n, d, row_begin, n_rows, workspace, workspace_bytes, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" OCBNN_API int ocbnn_svgd_hist_pass_prepared(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t pass, uint32_t* hist,
@@ -380,10 +404,19 @@ extern "C" OCBNN_API int ocbnn_svgd_bandwidth(const float* x, int64_t n, int64_t
     void* tcws = reinterpret_cast<char*>(workspace) + 3 * kBins * sizeof(uint32_t) + 256;
     const bool tensor = want_tensor(use_tensor, n);
     int rc;
-    if (tensor && (rc = tc::tc_svgd_prepare(x, n, d, 0, n, tcws, workspace_bytes - (3 * kBins * sizeof(uint32_t) + 256), (cudaStream_t)stream))) return rc;
+    bool hist0_done = false;
+    if (tensor) {                       // the pass-0 histogram rides on the distance pass when the direct kernel forms the distances
+        k_zero_u32<<<(3 * kBins + 255) / 256, 256, 0, (cudaStream_t)stream>>>(hist, 3 * kBins);
+        OCBNN_LAUNCH_CHECK();
+        if ((rc = tc::tc_svgd_prepare(x, n, d, 0, n, tcws, workspace_bytes - (3 * kBins * sizeof(uint32_t) + 256), hist, &hist0_done,
+                                      (cudaStream_t)stream)))
+            return rc;
+    }
     for (int pass = 0; pass < 3; ++pass) {
-        rc = tensor ? ocbnn_svgd_hist_pass_prepared(n, d, 0, n, pass, hist, state, tcws, stream)
-                    : ocbnn_svgd_hist_pass(x, n, d, 0, 1, n, pass, hist, state, stream);
+        if (pass == 0 && hist0_done) rc = OCBNN_OK;
+        else if (tensor && pass == 0) rc = tc::tc_svgd_hist(n, d, 0, n, 0, hist, reinterpret_cast<const unsigned long long*>(state), tcws, (cudaStream_t)stream);
+        else rc = tensor ? ocbnn_svgd_hist_pass_prepared(n, d, 0, n, pass, hist, state, tcws, stream)
+                         : ocbnn_svgd_hist_pass(x, n, d, 0, 1, n, pass, hist, state, stream);
         if (rc) return rc;
         rc = ocbnn_svgd_select_update(pass, hist, state, n, pass == 2 ? out_h : nullptr, stream);
         if (rc) return rc;
@@ -404,7 +437,7 @@ extern "C" OCBNN_API int ocbnn_svgd_phi(const float* x, const float* g, int64_t 
                       "ocbnn_svgd_phi: workspace too small for the tensor path (see ocbnn_svgd_workspace_bytes)");
         void* tcws = reinterpret_cast<char*>(workspace) + 3 * kBins * sizeof(uint32_t) + 256;
         if (use_tensor != 2) {
-            int rc = tc::tc_svgd_prepare(x, n, d, row_begin, n_rows, tcws, workspace_bytes - (3 * kBins * sizeof(uint32_t) + 256), st);
+            int rc = tc::tc_svgd_prepare(x, n, d, row_begin, n_rows, tcws, workspace_bytes - (3 * kBins * sizeof(uint32_t) + 256), nullptr, nullptr, st);
             if (rc) return rc;
         }
         return tc::tc_svgd_phi(g, h, n, d, row_begin, n_rows, out_phi, tcws, st);

@@ -199,37 +199,73 @@ k_center_split(const float* __restrict__ x, const float* __restrict__ mean, long
     if (lane == 0) { r[row] = (float)rr; ssum[row] = (float)ss; }
 }
 
-// exact squared distances for small D (dp <= 64): d2[t][j] = ||xc_i - xc_j||^2 by direct differences
+__device__ __forceinline__ void hist_add_warp(unsigned* sh, unsigned bin) {
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (bin != 0xFFFFFFFFu && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[bin], (unsigned)__popc(peers));
+}
+
+// exact squared distances for small D (dp <= 64): d2[t][j] = ||xc_i - xc_j||^2 by direct differences.
+// 64 x 64 tile per CTA, 4 x 4 per thread, float4 shared-memory operands.  When hist0 != NULL the first radix-select
+// histogram (top 11 bits of the eps-perturbed distance, pairs i < j) is accumulated in the same pass.
 template <int DP>
 __global__ void __launch_bounds__(256)
-k_d2_direct(const float* __restrict__ hi, const float* __restrict__ lo, long long n, long long n4, long long row_begin, long long n_rows,
-            float* __restrict__ d2) {
-    __shared__ float xi[16][DP + 1];
-    __shared__ float xj[64][DP + 1];
-    const long long t0 = (long long)blockIdx.y * 16, j0 = (long long)blockIdx.x * 64;
-    for (int idx = threadIdx.x; idx < 16 * DP; idx += 256) {
-        int rr = idx / DP, c = idx % DP;
-        long long i = row_begin + t0 + rr;
-        xi[rr][c] = (t0 + rr < n_rows) ? hi[i * DP + c] + lo[i * DP + c] : 0.f;
-    }
+k_d2_direct(const float* __restrict__ hi, const float* __restrict__ lo, const float* __restrict__ ssum, long long n, long long n4, int d,
+            long long row_begin, long long n_rows, float* __restrict__ d2, unsigned* __restrict__ hist0) {
+    __shared__ __align__(16) float xi[64][DP + 4];
+    __shared__ __align__(16) float xj[64][DP + 4];
+    __shared__ unsigned sh[2048];
+    const long long t0 = (long long)blockIdx.y * 64, j0 = (long long)blockIdx.x * 64;
+    if (hist0) for (int i = threadIdx.x; i < 2048; i += 256) sh[i] = 0u;
     for (int idx = threadIdx.x; idx < 64 * DP; idx += 256) {
-        int rr = idx / DP, c = idx % DP;
-        long long j = j0 + rr;
+        const int rr = idx / DP, c = idx % DP;
+        const long long i = row_begin + t0 + rr, j = j0 + rr;
+        xi[rr][c] = (t0 + rr < n_rows) ? hi[i * DP + c] + lo[i * DP + c] : 0.f;
         xj[rr][c] = j < n ? hi[j * DP + c] + lo[j * DP + c] : 0.f;
     }
     __syncthreads();
-    const int jj = threadIdx.x & 63, tq = threadIdx.x >> 6;      // 4 rows per thread
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // columns tx + 16 q, rows ty + 16 p (interleaved: conflict-free rows)
+    float acc[4][4] = {};
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int rr = tq * 4 + a;
-        float acc = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < DP; ++c) {
-            const float df = xi[rr][c] - xj[jj][c];
-            acc = fmaf(df, df, acc);
+    for (int c = 0; c < DP; c += 4) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) a[p] = *reinterpret_cast<const float4*>(&xi[ty + 16 * p][c]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4*>(&xj[tx + 16 * q][c]);
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float e;
+                e = a[p].x - b[q].x; acc[p][q] = fmaf(e, e, acc[p][q]);
+                e = a[p].y - b[q].y; acc[p][q] = fmaf(e, e, acc[p][q]);
+                e = a[p].z - b[q].z; acc[p][q] = fmaf(e, e, acc[p][q]);
+                e = a[p].w - b[q].w; acc[p][q] = fmaf(e, e, acc[p][q]);
+            }
+    }
+    const float eps = 1e-6f, deps2 = (float)d * 1e-12f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const long long t = t0 + ty + 16 * p, i = row_begin + t;
+        const float si = (hist0 && t < n_rows) ? ssum[i] : 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long j = j0 + tx + 16 * q;
+            if (t < n_rows && j < n4) d2[t * n4 + j] = j < n ? acc[p][q] : 0.f;
+            if (hist0) {
+                unsigned bin = 0xFFFFFFFFu;
+                if (t < n_rows && j > i && j < n) {
+                    const unsigned bits = __float_as_uint(sqrtf(fmaxf(acc[p][q] + 2.f * eps * (si - ssum[j]) + deps2, 0.f)));
+                    if (bits != 0u) bin = bits >> 21;
+                }
+                hist_add_warp(sh, bin);
+            }
         }
-        const long long t = t0 + rr, j = j0 + jj;
-        if (t < n_rows && j < n4) d2[t * n4 + j] = j < n ? acc : 0.f;
+    }
+    if (hist0) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < 2048; b += 256)
+            if (sh[b]) atomicAdd(&hist0[b], sh[b]);
     }
 }
 
@@ -259,8 +295,7 @@ k_hist_d2(const float* __restrict__ d2, const float* __restrict__ ssum, long lon
                     else if ((b >> 10) == (prefix >> 10)) bin = b & 1023u;
                 }
             }
-            const unsigned peers = __match_any_sync(0xffffffffu, bin);
-            if (bin != 0xFFFFFFFFu && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[bin], (unsigned)__popc(peers));
+            hist_add_warp(sh, bin);
         }
     }
     __syncthreads();
@@ -358,16 +393,19 @@ k_phi_finalize(const float* __restrict__ o, int splits, const float* __restrict_
 }
 
 // centre + split X, squared distances of rows [row_begin, row_begin + n_rows) into the workspace
-static int tc_prepare(const TcWs& w, const float* x, cudaStream_t st) {
+// hist0: when non-NULL (and the distances are formed by the direct kernel) the pass-0 select histogram is fused into the pass
+static int tc_prepare(const TcWs& w, const float* x, unsigned* hist0, bool* hist0_done, cudaStream_t st) {
+    if (hist0_done) *hist0_done = false;
     k_colmean<<<(unsigned)w.dp, 256, 0, st>>>(x, w.n, (int)w.d, (int)w.dp, w.mean);
     OCBNN_LAUNCH_CHECK();
     k_center_split<<<(unsigned)((w.n * 32 + 255) / 256), 256, 0, st>>>(x, w.mean, w.n, (int)w.d, (int)w.dp, w.xc_hi, w.xc_lo, w.r, w.s);
     OCBNN_LAUNCH_CHECK();
     if (w.dp <= 64) {
-        dim3 grid((unsigned)((w.n4 + 63) / 64), (unsigned)((w.n_rows + 15) / 16));
-        if (w.dp == 32) k_d2_direct<32><<<grid, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.n, w.n4, w.row_begin, w.n_rows, w.d2);
-        else k_d2_direct<64><<<grid, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.n, w.n4, w.row_begin, w.n_rows, w.d2);
+        dim3 grid((unsigned)((w.n4 + 63) / 64), (unsigned)((w.n_rows + 63) / 64));
+        if (w.dp == 32) k_d2_direct<32><<<grid, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.s, w.n, w.n4, (int)w.d, w.row_begin, w.n_rows, w.d2, hist0);
+        else k_d2_direct<64><<<grid, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.s, w.n, w.n4, (int)w.d, w.row_begin, w.n_rows, w.d2, hist0);
         OCBNN_LAUNCH_CHECK();
+        if (hist0_done) *hist0_done = hist0 != nullptr;
         return OCBNN_OK;
     }
     // Gram on tensor cores: A = rows of this rank, B = all rows
@@ -405,9 +443,10 @@ static int tc_phi(const TcWs& w, const float* g, const float* h, float* phi, cud
 
 long long tc_workspace_bytes(long long n, long long d, long long n_rows) { return carve(nullptr, n, d, 0, n_rows).bytes + 512; }
 
-int tc_svgd_prepare(const float* x, long long n, long long d, long long row_begin, long long n_rows, void* ws, long long ws_bytes, cudaStream_t st) {
+int tc_svgd_prepare(const float* x, long long n, long long d, long long row_begin, long long n_rows, void* ws, long long ws_bytes, unsigned* hist0,
+                    bool* hist0_done, cudaStream_t st) {
     OCBNN_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(n, d, n_rows), OCBNN_EINVAL, "SVGD tensor path: workspace too small");
-    return tc_prepare(carve(ws, n, d, row_begin, n_rows), x, st);
+    return tc_prepare(carve(ws, n, d, row_begin, n_rows), x, hist0, hist0_done, st);
 }
 int tc_svgd_hist(long long n, long long d, long long row_begin, long long n_rows, int pass, unsigned* hist, const unsigned long long* state, void* ws,
                  cudaStream_t st) {

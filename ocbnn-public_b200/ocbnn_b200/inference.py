@@ -223,16 +223,17 @@ class SVGDMixin:
         tensor = E.svgd_use_tensor(int(use_tensor), n)
         ws = E.svgd_workspace(n, self.nweights, dev, n_rows=(n if D.world() == 1 else hi - lo), use_tensor=1 if tensor else 0)
         hist, state = E.svgd_ws_views(ws)
-        return {"n": n, "lo": lo, "hi": hi, "tensor": tensor, "ws": ws, "hist": hist, "state": state,
+        return {"n": n, "lo": lo, "hi": hi, "tensor": tensor, "ws": ws, "hist": hist, "state": state, "prob": self.engine_problem(),
                 "X": particles[lo:hi].to(dev, torch.float32).contiguous(),
+                "G": torch.empty(hi - lo, self.nweights, device=dev), "phi": torch.empty(hi - lo, self.nweights, device=dev),
                 "acc": torch.zeros(hi - lo, self.nweights, device=dev), "h": torch.empty(1, device=dev)}
 
     def svgd_epoch(self, st, epoch, with_data, use_tensor=None):
         """One SVGD epoch on the device: gradients (K1), all-gather, bandwidth (K3a), phi (K3b), Adagrad (K3c)."""
-        prob = self.engine_problem()
+        prob = st["prob"]                      # compiled once per infer(): the reference also fixes data and constraints per infer()
         X = st["X"]
         tensor = st["tensor"] if use_tensor is None else E.svgd_use_tensor(int(use_tensor), st["n"]) and st["tensor"]
-        _, G = prob.logpost_grad(X, _batch_for(self, epoch), with_data, want_lp=False)
+        _, G = prob.logpost_grad(X, _batch_for(self, epoch), with_data, want_lp=False, out_grad=st["G"])
         Xall, Gall = D.gather_cat(X, dim=0), D.gather_cat(G, dim=0)
         n, lo, rows = st["n"], st["lo"], st["hi"] - st["lo"]
         if D.world() == 1:
@@ -247,7 +248,7 @@ class SVGDMixin:
                     E.svgd_hist_pass(Xall, D.rank(), D.world(), len(range(D.rank(), n, D.world())), p, st["hist"], st["state"])
                 D.all_sum_(st["hist"][p * 2048:(p + 1) * 2048])
                 E.svgd_select_update(p, st["hist"], st["state"], n, st["h"])
-        phi = E.svgd_phi(Xall, Gall, st["h"], lo, rows, st["ws"], 2 if tensor else 0)
+        phi = E.svgd_phi(Xall, Gall, st["h"], lo, rows, st["ws"], 2 if tensor else 0, out=st["phi"])
         E.adagrad_step(X, st["acc"], phi, self.svgd_init_lr, -1.0)      # particles.grad = -update (inference.py:280)
         st["phi"] = phi
         return st
