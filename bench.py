@@ -288,12 +288,25 @@ def main():
     peak_mufu = engine.probe_peak(2)
     ker_s = ms_total * 1e-3 / K                      # one launch per step: the event brackets exactly that kernel
     ach_flops = M * L * flop_step / ker_s
-    roofline = {"bound": "fp32-simt", "kernel": "k_hmc_small", "achieved": ach_flops / 1e12, "peak": peak_ffma2 / 1e12, "unit": "TFLOP/s",
-                "frac": ach_flops / peak_ffma2, "traffic": None,
-                "peak_source": "packed FFMA2 probe kernel measured in this run (MEASURED_PEAKS.json has HBM and bf16 tensor peaks only)",
+    ach_mufu = M * L * mufu_step / ker_s
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_hmc_ncu.json")
+    if os.path.exists(tp):
+        t = json.load(open(tp))
+        if t.get("chains") == M and t.get("leapfrog_l") == L:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]         # per launch, from the committed ncu --set full capture
+    # The toy nets keep all state on chip: ~7 B of HBM traffic per chain-step, so neither the HBM nor the tensor roofline binds.
+    # The binding pipe is the one with the larger fraction of its measured peak: MUFU (exp2/rcp, 16 op/clk/SM) vs fp32 FMA.
+    mufu_frac, fp32_frac = ach_mufu / peak_mufu, ach_flops / peak_ffma2
+    mufu_bound = mufu_frac >= fp32_frac
+    roofline = {"bound": "mufu" if mufu_bound else "fp32-simt", "kernel": "k_hmc_small_sm" if True else "k_hmc_small",
+                "achieved": (ach_mufu if mufu_bound else ach_flops) / 1e12, "peak": (peak_mufu if mufu_bound else peak_ffma2) / 1e12,
+                "unit": "Top/s" if mufu_bound else "TFLOP/s", "frac": mufu_frac if mufu_bound else fp32_frac, "traffic": traffic,
+                "peak_source": "instruction-pipe probes measured in this run (ocbnn_probe_peak: MUFU.EX2, packed FFMA2); MEASURED_PEAKS.json has HBM and bf16 tensor peaks only",
                 "flop_per_chain_step": flop_step, "mufu_per_chain_step": mufu_step, "hbm_bytes_per_chain_step": bytes_step,
-                "scalar_ffma_peak_tflops": peak_ffma / 1e12, "mufu_peak_tops": peak_mufu / 1e12,
-                "mufu_frac": (M * L * mufu_step / ker_s) / peak_mufu,
+                "algorithmic_hbm_bytes_per_launch": M * L * bytes_step,
+                "fp32_frac": fp32_frac, "fp32_achieved_tflops": ach_flops / 1e12, "fp32_peak_tflops": peak_ffma2 / 1e12,
+                "scalar_ffma_peak_tflops": peak_ffma / 1e12, "mufu_frac": mufu_frac, "mufu_peak_tops": peak_mufu / 1e12,
                 "hbm_frac_for_context": (M * L * bytes_step / ker_s) / (hbm_gbs * 1e9), "hbm_peak_gbs": hbm_gbs, "hbm_peak_source": src}
 
     cpu = None

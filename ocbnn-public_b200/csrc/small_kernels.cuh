@@ -7,7 +7,8 @@
 namespace ocbnn {
 
 constexpr int kSmallThreads = 128;
-constexpr int kDefaultHmcMb = 2;   // measured on B200: 2 resident CTAs (no spills, 2 points in flight per thread) beats 3 and 4
+constexpr bool kDefaultHmcSmem = true;    // measured on B200 (W2, 262144 chains): smem state, 4 CTAs/SM 1.34 G steps/s vs register state, 2 CTAs/SM 1.21 G
+constexpr int kDefaultHmcMb = 4;
 
 __host__ __device__ constexpr int kSmemFixedFloats(int ns) { return 4 * ns; }   // float4 prior table per slot
 
@@ -28,7 +29,7 @@ k_logpost_small(EvalArgs a, const float* __restrict__ w, long long m, float* __r
     float2 wv[N::NS], g[N::NS];
     load_state<N>(wv, w + chain * N::D);
     float lp;
-    evaluate<N, G>(a, c, /*restage=*/true, wv, g, lp, lane);
+    evaluate<N, G>(a, c, /*restage=*/true, RegView<N::NS>{wv}, g, lp, lane);
     if (active && lane == 0) {
         if (out_lp) out_lp[chain] = lp;
         if (out_grad) store_state<N>(g, out_grad + chain * N::D);
@@ -77,12 +78,12 @@ k_hmc_small(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, 
     float2 q[N::NS], p[N::NS], g[N::NS];
     load_state<N>(q, q_io + chain * N::D);
     float lp;
-    evaluate<N, G>(a, c, /*restage=*/true, q, g, lp, lane);   // stages the (fixed) point set once
+    evaluate<N, G>(a, c, /*restage=*/true, RegView<N::NS>{q}, g, lp, lane);   // stages the (fixed) point set once
     int nan_flag = 0;
     bool need_eval = false;
 
     for (int it = 0; it < n_it; ++it) {
-        if (__any_sync(0xffffffffu, need_eval)) evaluate<N, G>(a, c, false, q, g, lp, lane);
+        if (__any_sync(0xffffffffu, need_eval)) evaluate<N, G>(a, c, false, RegView<N::NS>{q}, g, lp, lane);
         need_eval = false;
         load_state<N>(p, p0 + ((long long)it * m + chain) * N::D);
         const float U0 = -lp;
@@ -94,7 +95,7 @@ k_hmc_small(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, 
         axpy_rn<N>(p, eps_half, g);
         for (int l = 1; l <= L; ++l) {
             axpy_rn<N>(q, eps, p);
-            evaluate<N, G>(a, c, false, q, g, lp, lane);
+            evaluate<N, G>(a, c, false, RegView<N::NS>{q}, g, lp, lane);
             axpy_rn<N>(p, (l < L) ? eps : eps_half, g);
         }
         bool isn = false;
@@ -124,6 +125,108 @@ k_hmc_small(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, 
     }
 }
 
+// K2, shared-memory state variant: q and p of every thread live in its own column of shared memory (slot-major,
+// float2), only the gradient accumulators and the per-point temporaries stay in registers.  Fewer registers per thread ->
+// more resident warps to hide the MUFU / FMA latencies of the evaluator.  Same arithmetic, same rounding as k_hmc_small.
+template <class N, int G, int MB>
+__global__ void __launch_bounds__(kSmallThreads, MB)
+k_hmc_small_sm(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, const double* __restrict__ u, long long m, int n_it,
+               float eps, float eps_half, int L, int restore, uint8_t* __restrict__ out_acc, float* __restrict__ out_h,
+               int* __restrict__ out_flags, float* __restrict__ out_samples, int thin, int tile_cap) {
+    extern __shared__ __align__(16) float smem[];
+    float4* pri_s = reinterpret_cast<float4*>(smem);
+    float2* qs = reinterpret_cast<float2*>(smem + kSmemFixedFloats(N::NS)) + threadIdx.x;     // [NS][kSmallThreads]
+    float2* ps = qs + N::NS * kSmallThreads;
+    float* tab = smem + kSmemFixedFloats(N::NS) + 4 * N::NS * kSmallThreads;
+    EvalCtx c = make_ctx(a, tab, pri_s, tile_cap);
+    load_pri_slots<N>(pri_s, a);
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    const bool active = gid < m;
+    const long long chain = active ? gid : m - 1;
+    const bool writer = active && lane == 0;
+    const SmemView qv{qs, kSmallThreads};
+
+    auto load_to = [&](float2* dst, const float* __restrict__ src) {
+#pragma unroll
+        for (int s = 0; s < N::NS; ++s)
+            dst[s * kSmallThreads] = make_float2(N::cidx(s, 0) >= 0 ? __ldg(src + N::cidx(s, 0)) : 0.f, N::cidx(s, 1) >= 0 ? __ldg(src + N::cidx(s, 1)) : 0.f);
+    };
+    auto store_from = [&](const float2* srcv, float* __restrict__ dst) {
+#pragma unroll
+        for (int s = 0; s < N::NS; ++s) {
+            const float2 v = srcv[s * kSmallThreads];
+            if (N::cidx(s, 0) >= 0) dst[N::cidx(s, 0)] = v.x;
+            if (N::cidx(s, 1) >= 0) dst[N::cidx(s, 1)] = v.y;
+        }
+    };
+    auto kinetic_s = [&]() {
+        double ks = 0.0;
+#pragma unroll
+        for (int s = 0; s < N::NS; ++s) {
+            const float2 pv = ps[s * kSmallThreads];
+            const float2 e = __fmul2_rn(pv, pv);
+            ks += (double)e.x + (double)e.y;
+        }
+        return 0.5f * (float)ks;
+    };
+
+    float2 g[N::NS];
+    load_to(qs, q_io + chain * N::D);
+    float lp;
+    evaluate<N, G>(a, c, /*restage=*/true, qv, g, lp, lane);
+    int nan_flag = 0;
+    bool need_eval = false;
+    for (int it = 0; it < n_it; ++it) {
+        if (__any_sync(0xffffffffu, need_eval)) evaluate<N, G>(a, c, false, qv, g, lp, lane);
+        need_eval = false;
+        load_to(ps, p0 + ((long long)it * m + chain) * N::D);
+        const float U0 = -lp;
+        const float K0 = kinetic_s();
+        if (restore) {
+            if (writer) store_from(qs, q_io + chain * N::D);
+            __syncwarp();
+        }
+#pragma unroll
+        for (int s = 0; s < N::NS; ++s) ps[s * kSmallThreads] = __fadd2_rn(ps[s * kSmallThreads], __fmul2_rn(f2(eps_half), g[s]));
+        for (int l = 1; l <= L; ++l) {
+#pragma unroll
+            for (int s = 0; s < N::NS; ++s) qs[s * kSmallThreads] = __fadd2_rn(qs[s * kSmallThreads], __fmul2_rn(f2(eps), ps[s * kSmallThreads]));
+            evaluate<N, G>(a, c, false, qv, g, lp, lane);
+            const float2 e2 = f2((l < L) ? eps : eps_half);
+#pragma unroll
+            for (int s = 0; s < N::NS; ++s) ps[s * kSmallThreads] = __fadd2_rn(ps[s * kSmallThreads], __fmul2_rn(e2, g[s]));
+        }
+        bool isn = false;
+#pragma unroll
+        for (int s = 0; s < N::NS; ++s) {
+            const float2 v = qs[s * kSmallThreads];
+            isn |= isnan(v.x) | isnan(v.y);
+        }
+        nan_flag |= isn ? 1 : 0;
+        const float U1 = -lp;
+        const float K1 = kinetic_s();
+        const float dH = __fsub_rn(__fadd_rn(__fsub_rn(U0, U1), K0), K1);
+        const double alpha = (double)expf(dH);
+        const double ui = __ldg(u + (long long)it * m + chain);
+        const bool acc = ui < alpha;
+        if (writer) {
+            if (out_acc) out_acc[(long long)it * m + chain] = acc ? 1 : 0;
+            if (out_h) reinterpret_cast<float4*>(out_h)[(long long)it * m + chain] = make_float4(U0, K0, U1, K1);
+        }
+        if (restore && !acc) {
+            load_to(qs, q_io + chain * N::D);
+            need_eval = true;
+        }
+        if (out_samples && thin > 0 && ((it + 1) % thin == 0) && writer)
+            store_from(qs, out_samples + ((long long)((it + 1) / thin - 1) * m + chain) * N::D);
+    }
+    if (writer) {
+        store_from(qs, q_io + chain * N::D);
+        if (out_flags) out_flags[chain] = nan_flag;
+    }
+}
+
 // ---- K4 ------------------------------------------------------------------------------------------------
 // SGLD (bnn/inference.py:304-340): upd = (grad log prior + grad log lik) * (eps_t/2) + noise_t ; w += upd.
 template <class N, int G>
@@ -149,7 +252,7 @@ k_sgld_small(EvalArgs a, float* __restrict__ w_io, const float* __restrict__ noi
             c = make_ctx(a, tab, pri_s, tile_cap);
         }
         float lp;
-        evaluate<N, G>(a, c, /*restage=*/batched || t == 0, w, g, lp, lane);
+        evaluate<N, G>(a, c, /*restage=*/batched || t == 0, RegView<N::NS>{w}, g, lp, lane);
         const float2 he = f2(half_eps[t]);
         load_state<N>(nz, noise + ((long long)t * m + chain) * N::D);
 #pragma unroll
@@ -181,11 +284,11 @@ k_forward_small(const float* __restrict__ w, long long m, const float* __restric
 // ---- host-side launchers for one net shape ---------------------------------------------------------------
 template <class N>
 struct SmallLaunch {
-    static size_t smem_bytes(const Problem& p, int npts, int& tile_cap) {
-        size_t fixed = sizeof(float) * kSmemFixedFloats(N::NS);
+    static size_t smem_bytes(const Problem& p, int npts, int& tile_cap, size_t reserved = 0) {
+        size_t fixed = sizeof(float) * kSmemFixedFloats(N::NS) + reserved;
         int cap = (int)((kMaxSmemTable - fixed) / (sizeof(float) * p.rs));
         tile_cap = npts < cap ? (npts > 0 ? npts : 1) : cap;
-        return fixed + sizeof(float) * (size_t)tile_cap * p.rs;
+        return fixed - reserved + sizeof(float) * (size_t)tile_cap * p.rs;
     }
     static int npts(const EvalArgs& a) {
         return (a.with_data ? batch_count(a.n_train, 0, a.batch_stride) : 0) + a.n_cpoints;   // largest batch: offset 0
@@ -202,12 +305,13 @@ struct SmallLaunch {
         OCBNN_LAUNCH_CHECK();
         return OCBNN_OK;
     }
-    template <int G, int MB>
+    template <int G, int MB, bool SM>
     static int hmc_mb(const Problem& p, const EvalArgs& a, float* q, const float* p0, const double* u, long long m, int n_it, float eps,
                       float eps_half, int L, int restore, uint8_t* acc, float* h, int* flags, float* samples, int thin, cudaStream_t st) {
         int tile_cap;
-        size_t sm = smem_bytes(p, npts(a), tile_cap);
-        auto k = k_hmc_small<N, G, MB>;
+        const size_t extra = SM ? sizeof(float) * 4 * N::NS * kSmallThreads : 0;        // q and p columns of every thread
+        size_t sm = smem_bytes(p, npts(a), tile_cap, extra) + extra;
+        auto k = SM ? k_hmc_small_sm<N, G, MB> : k_hmc_small<N, G, MB>;
         OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         long long blocks = (m * G + kSmallThreads - 1) / kSmallThreads;
         k<<<(unsigned)blocks, kSmallThreads, sm, st>>>(a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin,
@@ -215,14 +319,23 @@ struct SmallLaunch {
         OCBNN_LAUNCH_CHECK();
         return OCBNN_OK;
     }
-    // MB = resident CTAs per SM the kernel is compiled for (register cap 65536/(128*MB)); tuning knob OCBNN_HMC_MB
+    // Variant knobs (measured defaults in kDefaultHmc*): OCBNN_HMC_MB = resident CTAs per SM the kernel is compiled for,
+    // OCBNN_HMC_STATE = reg | smem (where q and p live).
     template <int G>
     static int hmc(const Problem& p, const EvalArgs& a, float* q, const float* p0, const double* u, long long m, int n_it, float eps,
                    float eps_half, int L, int restore, uint8_t* acc, float* h, int* flags, float* samples, int thin, cudaStream_t st) {
         static const int mb = [] { const char* e = getenv("OCBNN_HMC_MB"); return e ? atoi(e) : kDefaultHmcMb; }();
-        if (mb == 2) return hmc_mb<G, 2>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
-        if (mb == 4) return hmc_mb<G, 4>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
-        return hmc_mb<G, 3>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
+        static const bool smst = [] { const char* e = getenv("OCBNN_HMC_STATE"); return e ? e[0] == 's' : kDefaultHmcSmem; }();
+#define OCBNN_HMC_GO(MBV, SMV) return hmc_mb<G, MBV, SMV>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st)
+        if (smst) {
+            if (mb <= 3) OCBNN_HMC_GO(3, true);
+            if (mb == 4) OCBNN_HMC_GO(4, true);
+            OCBNN_HMC_GO(5, true);
+        }
+        if (mb <= 2) OCBNN_HMC_GO(2, false);
+        if (mb == 3) OCBNN_HMC_GO(3, false);
+        OCBNN_HMC_GO(4, false);
+#undef OCBNN_HMC_GO
     }
     template <int G>
     static int sgld(const Problem& p, const EvalArgs& a, float* w, const float* noise, const float* he, const int* offs, long long m,

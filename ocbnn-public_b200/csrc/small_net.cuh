@@ -94,6 +94,27 @@ __device__ __forceinline__ void act_pair(float2 z, float2& a, float2& m) {
 template <int ACT>
 __device__ __forceinline__ constexpr float act_scale() { return ACT == OCBNN_ACT_RBF ? -2.f : 1.f; }
 
+// Weight views: the evaluator reads weights through operator[] so that they can live in registers (RegView) or in a
+// per-thread column of shared memory (SmemView: slot s of thread t at base[s * stride], conflict-free float2 loads), which
+// frees 2 x NS registers per thread for occupancy.
+template <int NS>
+struct RegView {
+    const float2 (&a)[NS];
+    __device__ __forceinline__ float2 operator[](int s) const { return a[s]; }
+};
+struct SmemView {
+    const float2* base;
+    int stride;
+    // volatile asm: the loads must stay inside the point loop (a plain load is loop invariant and would be hoisted back
+    // into 2 x NS registers, which is exactly what this view is meant to avoid)
+    __device__ __forceinline__ float2 operator[](int s) const {
+        float2 v;
+        const unsigned addr = (unsigned)__cvta_generic_to_shared(base + s * stride);
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+        return v;
+    }
+};
+
 // ---- fast heads for the register kernels (same formulas as heads.cuh, MUFU approximations) ----------------------
 struct FastConsts {
     float2 tau_l2e;      // 2*tau_i*log2(e)
@@ -263,8 +284,8 @@ struct FastHead<OCBNN_HEAD_LIK_BERNOULLI, SK> {
 // value + gradient contribution of U point records with a compile-time head.  The U points are independent until the
 // gradient accumulation, which gives the scheduler U forward/head dependency chains to interleave (the head is a long
 // serial chain of MUFU ops).  Records beyond the segment are passed with live[u] = 0 and contribute nothing.
-template <class N, int KIND, int U>
-__device__ __forceinline__ void point_eval(const float2 (&w)[N::NS], float2 (&g)[N::NS], double& lp, const float* const (&rec)[U],
+template <class N, int KIND, int U, class WV>
+__device__ __forceinline__ void point_eval(const WV& w, float2 (&g)[N::NS], double& lp, const float* const (&rec)[U],
                                            const float (&live)[U], const FastConsts& fc) {
     float2 xx[U][N::S0], a[U][N::HP], m[U][N::HP];
     float f[U][N::SK], df[U][N::SK], val[U];
@@ -416,8 +437,8 @@ __device__ __forceinline__ void load_pri_slots(float4* pri_s, const EvalArgs& a)
     }
 }
 
-template <class N, int G, int KIND>
-__device__ __forceinline__ void eval_segment(const EvalCtx& c, int rs, int lo, int hi, const float2 (&w)[N::NS], float2 (&g)[N::NS],
+template <class N, int G, int KIND, class WV>
+__device__ __forceinline__ void eval_segment(const EvalCtx& c, int rs, int lo, int hi, const WV& w, float2 (&g)[N::NS],
                                              double& lp, int lane) {
     constexpr int U = OCBNN_POINT_UNROLL;
     for (int j = lo + lane; j < hi; j += U * G) {
@@ -429,14 +450,14 @@ __device__ __forceinline__ void eval_segment(const EvalCtx& c, int rs, int lo, i
             rec[u] = c.tab + (ok ? j + u * G : j) * rs;
             live[u] = ok ? 1.f : 0.f;
         }
-        point_eval<N, KIND, U>(w, g, lp, rec, live, c.fc);
+        point_eval<N, KIND, U, WV>(w, g, lp, rec, live, c.fc);
     }
 }
 
 // log posterior value and gradient at w.  Block-uniform control flow (contains __syncthreads when the point set
 // does not fit one tile or `restage` is set).  On return every lane of the group holds the full g and lp.
-template <class N, int G>
-__device__ __forceinline__ void evaluate(const EvalArgs& a, const EvalCtx& c, bool restage, const float2 (&w)[N::NS], float2 (&g)[N::NS],
+template <class N, int G, class WV>
+__device__ __forceinline__ void evaluate(const EvalArgs& a, const EvalCtx& c, bool restage, const WV& w, float2 (&g)[N::NS],
                                          float& lp_out, int lane) {
 #pragma unroll
     for (int s = 0; s < N::NS; ++s) g[s] = f2(0.f);
@@ -456,15 +477,15 @@ __device__ __forceinline__ void evaluate(const EvalArgs& a, const EvalCtx& c, bo
             seg_lo = c.seg_end[sg];
             if (lo >= hi) continue;
             if (sg == 0) {
-                if (a.lik_head == OCBNN_HEAD_LIK_GAUSS) eval_segment<N, G, OCBNN_HEAD_LIK_GAUSS>(c, a.rs, lo, hi, w, g, lp, lane);
-                else if (a.lik_head == OCBNN_HEAD_LIK_SOFTMAX) eval_segment<N, G, OCBNN_HEAD_LIK_SOFTMAX>(c, a.rs, lo, hi, w, g, lp, lane);
-                else eval_segment<N, G, OCBNN_HEAD_LIK_BERNOULLI>(c, a.rs, lo, hi, w, g, lp, lane);
+                if (a.lik_head == OCBNN_HEAD_LIK_GAUSS) eval_segment<N, G, OCBNN_HEAD_LIK_GAUSS, WV>(c, a.rs, lo, hi, w, g, lp, lane);
+                else if (a.lik_head == OCBNN_HEAD_LIK_SOFTMAX) eval_segment<N, G, OCBNN_HEAD_LIK_SOFTMAX, WV>(c, a.rs, lo, hi, w, g, lp, lane);
+                else eval_segment<N, G, OCBNN_HEAD_LIK_BERNOULLI, WV>(c, a.rs, lo, hi, w, g, lp, lane);
             } else if (sg == 1) {
-                eval_segment<N, G, OCBNN_HEAD_POS_GAUSS>(c, a.rs, lo, hi, w, g, lp, lane);
+                eval_segment<N, G, OCBNN_HEAD_POS_GAUSS, WV>(c, a.rs, lo, hi, w, g, lp, lane);
             } else if (sg == 2) {
-                eval_segment<N, G, OCBNN_HEAD_NEG_EXP>(c, a.rs, lo, hi, w, g, lp, lane);
+                eval_segment<N, G, OCBNN_HEAD_NEG_EXP, WV>(c, a.rs, lo, hi, w, g, lp, lane);
             } else {
-                eval_segment<N, G, OCBNN_HEAD_DIRICHLET>(c, a.rs, lo, hi, w, g, lp, lane);
+                eval_segment<N, G, OCBNN_HEAD_DIRICHLET, WV>(c, a.rs, lo, hi, w, g, lp, lane);
             }
         }
     }
