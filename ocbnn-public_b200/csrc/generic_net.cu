@@ -74,7 +74,7 @@ static size_t gen_smem_bytes(const GenLayout& L, int rs) {
 }
 
 __device__ __forceinline__ float act_rt(int act, float z) {
-    if (act == OCBNN_ACT_RBF) return expf(-z * z);
+    if (act == OCBNN_ACT_RBF) return ex2_approx(z * z * -1.4426950408889634f);     // exp(-z^2), MUFU.EX2 (2^-22 relative)
     if (act == OCBNN_ACT_RELU) return fmaxf(z, 0.f);
     return z;
 }
@@ -173,7 +173,8 @@ __device__ __forceinline__ void gen_backward_input(const float* __restrict__ W, 
                                                    int ts, int act) {
     // wsp: padded width of the previous layer (rows of dZprev to produce, rows >= s_in are written as zero)
     const int ND = wsp >> 2, npt = tp >> 2, ntile = ND * npt;
-    for (int tile = threadIdx.x; tile < ntile; tile += blockDim.x) {
+    // handed out from the last thread downwards: the weight-gradient tiles of the same phase start at thread 0
+    for (int tile = (int)blockDim.x - 1 - (int)threadIdx.x; tile < ntile; tile += blockDim.x) {
         const int dt = tile % ND, pt = tile / ND;
         float acc[4][4];
 #pragma unroll
@@ -391,12 +392,19 @@ k_forward_generic(GenLayout L, const float* __restrict__ w, long long m, const f
     }
 }
 
+// Points per tile: resident CTAs per SM matter more than tile size (measured on W6: 32-point tiles with 3 CTAs/SM beat 64-point
+// tiles with 1-2 CTAs/SM by 20 %), so prefer the largest tile that still leaves >= 3 CTAs per SM, then >= 2, then whatever fits.
 static int pick_tp(const Problem& p, GenLayout& L, bool with_grad) {
-    for (int tp : {32, 16, 8, 4}) {
+    auto need_for = [&](int tp) {
         L = make_layout(p, tp);
-        size_t need = with_grad ? gen_smem_bytes(L, p.rs) : sizeof(float) * ((size_t)L.wtot + (size_t)L.rows_tot * L.ts);
-        if ((long long)need <= (long long)p.max_smem_optin) return (int)need;
-    }
+        return with_grad ? gen_smem_bytes(L, p.rs) : sizeof(float) * ((size_t)L.wtot + (size_t)L.rows_tot * L.ts);
+    };
+    const long long cap = p.max_smem_optin;
+    for (int want : {3, 2, 1})
+        for (int tp : {32, 16, 8, 4}) {
+            const size_t need = need_for(tp);
+            if ((long long)need <= cap && cap / (long long)(need + 1024) >= want) return (int)need;
+        }
     return -1;
 }
 
