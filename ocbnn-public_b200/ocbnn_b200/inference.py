@@ -78,28 +78,53 @@ class HMCMixin:
             q[c] = prev[c] if prev is not None and prev.shape[0] > c else Normal(0, self.sigma_w).sample(torch.Size([self.nweights]))
         return q.to(dev).contiguous()
 
-    def hmc_run(self, q, n_it, with_data, collect_every=0):
-        """n_it iterations from state q (M,D, device; updated in place).  Returns (accepts (M,), samples or None)."""
+    def hmc_run(self, q, n_it, with_data, collect_every=0, chunk=None):
+        """n_it iterations from state q (M,D, device; updated in place).  Returns (accepts (M,), samples or None).
+
+        The iterations run in chunks (one kernel launch each).  The momenta / uniforms of chunk k+1 are drawn and uploaded
+        on a side stream while the kernel of chunk k runs, so host RNG and H2D copies overlap the compute."""
         prob = self.engine_problem()
         M = q.shape[0]
         acc_total = torch.zeros(M, dtype=torch.int64, device=q.device)
         nsamp = n_it // collect_every if collect_every else 0
         samples = torch.empty(nsamp, M, self.nweights, device=q.device) if nsamp else None
-        chunk = self._hmc_chunk()
+        chunk = self._hmc_chunk() if chunk is None else int(chunk)
         if collect_every:
             chunk = max(collect_every, chunk - chunk % collect_every)
+        main = torch.cuda.current_stream()
+        side = getattr(self, "_hmc_side_stream", None)
+        if side is None or side.device != q.device:
+            side = self._hmc_side_stream = torch.cuda.Stream(device=q.device)
+
+        side.wait_stream(main)                           # everything queued so far (q, the problem upload) is visible to the side stream
+
+        def draw(n):
+            with torch.cuda.stream(side):
+                p0, u = self._hmc_draw(n, M, q.device)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return p0, u, ev
+
+        nan_seen = torch.zeros((), dtype=torch.int32, device=q.device)
         done = 0
+        nxt = draw(min(chunk, n_it)) if n_it > 0 else None
         while done < n_it:
-            n = min(chunk, n_it - done)
-            p0, u = self._hmc_draw(n, M, q.device)
+            p0, u, ev = nxt
+            n = p0.shape[0]
+            main.wait_event(ev)
+            p0.record_stream(main)
+            u.record_stream(main)
             sl = samples[done // collect_every:(done + n) // collect_every] if collect_every else None
             acc, _, flags = prob.hmc_iterate(q, p0, u, self.hmc_epsilon, self.hmc_l, with_data,
                                              bool(getattr(self, "restore_on_reject", False)), samples=sl, thin=collect_every,
                                              lanes=int(getattr(self, "lanes", 0) or 0))
-            acc_total += acc.sum(dim=0)
-            if int(flags.max()) != 0:
-                _raise_nan(self)
             done += n
+            if done < n_it:
+                nxt = draw(min(chunk, n_it - done))      # overlaps the kernel just launched
+            acc_total += acc.sum(dim=0)
+            nan_seen = torch.maximum(nan_seen, flags.max())
+        if int(nan_seen) != 0:                           # one host sync per run (the reference checks every iteration)
+            _raise_nan(self)
         return acc_total, samples
 
     def infer(self, verbose=True, with_data=True):
