@@ -17,7 +17,7 @@ chains, there is no data-path collective ("scaling": "weak", per-GPU chain count
 `roofline`: the HMC kernel against the fp32 instruction roofline measured in the same run (packed FFMA2 probe); the toy
            nets keep all state in registers, so HBM traffic is ~7 B per chain-step and neither the HBM nor the tensor
            roofline binds (fractions of those are reported for context).
-`cpu_baseline`: the numpy oracle port on the host cores (bounded sample).
+`cpu_baseline`: the oracle port (the faster of its C and numpy restatements) on all host cores (bounded sample).
 """
 import argparse
 import json
@@ -59,7 +59,7 @@ def parse():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (numpy restatement, oracle/ocbnn_oracle.py) on the host cores
+# CPU arm: the oracle port (C restatement oracle/ocbnn_oracle.c, pinned to the numpy oracle and the reference's golden vectors)
 # ---------------------------------------------------------------------------------------------------------------------
 
 def _oracle_spec_arrays(m):
@@ -70,11 +70,16 @@ def _oracle_spec_arrays(m):
                 gamma=float(m.cocp_expo_gamma), tau=[float(t) for t in m.cocp_expo_tau], eps=float(m.hmc_epsilon))
 
 
-def _cpu_worker(args):
+def _oracle_spec(arr):
+    import ocbnn_oracle as orc
+    return orc.Spec(arr["sizes"], arr["act"], "regression", arr["X"], arr["Y"], sigma_w=arr["sigma_w"], sigma_noise=arr["sigma_noise"],
+                    use_ocbnn=True, neg=dict(xs=arr["xs"], intervals=[arr["iv"]], S=arr["S"], gamma=arr["gamma"], tau=arr["tau"]))
+
+
+def _np_worker(args):
     arr, M, L, seed = args
     import ocbnn_oracle as orc
-    spec = orc.Spec(arr["sizes"], arr["act"], "regression", arr["X"], arr["Y"], sigma_w=arr["sigma_w"], sigma_noise=arr["sigma_noise"],
-                    use_ocbnn=True, neg=dict(xs=arr["xs"], intervals=[arr["iv"]], S=arr["S"], gamma=arr["gamma"], tau=arr["tau"]))
+    spec = _oracle_spec(arr)
     rng = np.random.default_rng(seed)
     q = (0.5 * rng.standard_normal((M, spec.nweights))).astype(np.float32)
     p0 = rng.standard_normal((1, M, spec.nweights)).astype(np.float32)
@@ -85,24 +90,44 @@ def _cpu_worker(args):
 
 
 def cpu_hmc_rate(arr, L, seconds, steps=1, warmup=0):
-    """chain-leapfrog-steps/s of the oracle port with one worker process per host core; each step is one HMC iteration of a
-    bounded number of chains sized for ~`seconds` of wall time in total."""
+    """chain-leapfrog-steps/s of the oracle port on all host cores.  Two restatements exist: the C one (oracle/ocbnn_oracle.c ->
+    oracle/_ref/libocbnn_oracle.so, scalar libm, one host thread per core via ctypes, GIL released) and the numpy one
+    (oracle/ocbnn_oracle.py, vectorised over chains, one process per core).  Both are calibrated on a small sample and the
+    FASTER one is timed and reported (the stronger baseline).  Each step is one HMC iteration (L leapfrog steps + MH) of a
+    bounded number of chains sized for ~`seconds` of wall time in total.  Returns (rate, cores, chains per step, s per step, how)."""
     import concurrent.futures as cf
+    import c_port
+    cs = c_port.CSpec(_oracle_spec(arr))
     cores = os.cpu_count() or 1
+    D = cs.D
+
+    def run_c(M, seed):
+        r = np.random.default_rng(seed)
+        q = (0.5 * r.standard_normal((M, D))).astype(np.float32)
+        p0 = r.standard_normal((1, M, D)).astype(np.float32)
+        u = r.random((1, M))
+        t0 = time.perf_counter()
+        cs.hmc_iterate(q, p0, u, arr["eps"], L, threads=cores)
+        return time.perf_counter() - t0
+
+    n = max(1, steps + warmup)
     with cf.ProcessPoolExecutor(max_workers=cores) as ex:
-        t_small = max(list(ex.map(_cpu_worker, [(arr, 16, L, s) for s in range(cores)])))
-        per_chain = t_small / 16.0
-        n = max(1, steps + warmup)
-        M = int(max(16, min(4096, seconds / n / max(per_chain, 1e-9))))
-        times = []
-        for s in range(n):
+        def run_np(M, seed):
             t0 = time.perf_counter()
-            list(ex.map(_cpu_worker, [(arr, M, L, 100 * s + c) for c in range(cores)]))
-            if s >= warmup:
-                times.append(time.perf_counter() - t0)
+            list(ex.map(_np_worker, [(arr, M // cores, L, seed * 1000 + c) for c in range(cores)]))
+            return time.perf_counter() - t0
+        run_np(cores, 0)                                   # start the workers, import numpy there
+        cal = {"c": run_c(4 * cores, 1) / (4 * cores), "numpy": run_np(256 * cores, 1) / (256 * cores)}
+        how = min(cal, key=cal.get)
+        run = run_c if how == "c" else run_np
+        M = int(max(cores, min(1 << 20, seconds / n / max(cal[how], 1e-9))))
+        M -= M % cores
+        times = [run(M, 100 + s) for s in range(n)][warmup:]
     tot = sum(times)
-    rate = cores * M * L * len(times) / tot
-    return rate, cores, M, tot / len(times)
+    desc = ("C restatement of the oracle (gcc -O3 AVX2, scalar libm), one thread per core" if how == "c" else
+            "numpy restatement of the oracle (vectorised over chains), one process per core")
+    desc += f"; faster of the two ports here (calibration s/chain-iteration: C {cal['c']:.2e}, numpy {cal['numpy']:.2e})"
+    return M * L * len(times) / tot, cores, M, tot / len(times), desc
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -165,13 +190,13 @@ def run_reference(args):
         m = workloads.build(args.workload, seed=0)
         arr = _oracle_spec_arrays(m)
         os.chdir(cwd)
-    rate, cores, M, t_step = cpu_hmc_rate(arr, args.leapfrog, seconds=max(20.0, 8.0 * (args.steps + args.warmup)), steps=args.steps, warmup=args.warmup)
+    rate, cores, M, t_step, how = cpu_hmc_rate(arr, args.leapfrog, seconds=max(20.0, 8.0 * (args.steps + args.warmup)), steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "W2 repro/F1a.yaml HMC + negative-exponential COCP, toy1, [1,10,1] rbf", "chains": cores * M,
+            "config": {"workload": "W2 repro/F1a.yaml HMC + negative-exponential COCP, toy1, [1,10,1] rbf", "chains": M,
                        "leapfrog_l": args.leapfrog},
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{cores} processes x {M} chains x 1 HMC iteration (L={args.leapfrog}) per step, numpy oracle port"},
+                             "sample": f"{M} chains x 1 HMC iteration (L={args.leapfrog}) per step on {cores} host cores; {how}"},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -323,9 +348,9 @@ def main():
         os.chdir(scratch)
         arr = _oracle_spec_arrays(m)
         os.chdir(cwd)
-        rate, cores, Mc, _ = cpu_hmc_rate(arr, L, seconds=args.cpu_seconds)
+        rate, cores, Mc, _, how = cpu_hmc_rate(arr, L, seconds=args.cpu_seconds)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{cores} processes x {Mc} chains x 1 HMC iteration (L={L}), numpy oracle port of the same workload"}
+               "sample": f"{Mc} chains x 1 HMC iteration (L={L}) of the same workload on {cores} host cores; {how}"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
