@@ -194,6 +194,7 @@ extern "C" OCBNN_API int ocbnn_problem_create(const ocbnn_desc* desc, ocbnn_prob
     // constraint rows grouped by head kind (positive | negative | Dirichlet) so that the kernels run one compile-time
     // head per segment; the order inside a group is the caller's
     int seg_n[3] = {0, 0, 0};
+    int neg_n1 = -2, neg_n2 = -2;       // -2: no negative row seen yet, -1: rows differ
     {
         const int order[3] = {OCBNN_HEAD_POS_GAUSS, OCBNN_HEAD_NEG_EXP, OCBNN_HEAD_DIRICHLET};
         long long out_row = desc->n_train;
@@ -207,7 +208,7 @@ extern "C" OCBNN_API int ocbnn_problem_create(const ocbnn_desc* desc, ocbnn_prob
                 r[s0 + 1] = desc->cweight[c];
                 const float* src = desc->cparam_stride ? desc->cparam + c * desc->cparam_stride : nullptr;
                 if (kind == OCBNN_HEAD_NEG_EXP) {
-                    // ABI: ngaps, (a,b)...  ->  internal: n1, n2, one-sided (c, s) terms, two-sided (a, b) terms
+                    // ABI: ngaps, (a,b)...  ->  internal: n1, n2, one-sided (s c, s) terms Phi(s f - s c), two-sided (a, b) terms
                     const int ngaps = src ? (int)src[0] : 0;
                     if (ngaps < 0 || 1 + 2 * ngaps > desc->cparam_stride) {
                         delete p;
@@ -219,8 +220,8 @@ extern "C" OCBNN_API int ocbnn_problem_create(const ocbnn_desc* desc, ocbnn_prob
                     float* w1 = dst + 2;
                     for (int k = 0; k < ngaps; ++k) {
                         const float a = src[1 + 2 * k], b = src[2 + 2 * k];
-                        if (std::isinf(a) && a < 0) { w1[2 * n1] = b; w1[2 * n1 + 1] = 1.f; ++n1; }        // Phi(f - b)
-                        else if (std::isinf(b) && b > 0) { w1[2 * n1] = a; w1[2 * n1 + 1] = -1.f; ++n1; }  // Phi(a - f)
+                        if (std::isinf(a) && a < 0) { w1[2 * n1] = b; w1[2 * n1 + 1] = 1.f; ++n1; }         // Phi(f - b)  = Phi(s f - s c), (s c, s) = (b, 1)
+                        else if (std::isinf(b) && b > 0) { w1[2 * n1] = -a; w1[2 * n1 + 1] = -1.f; ++n1; }  // Phi(a - f)  = Phi(s f - s c), (s c, s) = (-a, -1)
                     }
                     float* w2 = dst + 2 + 2 * n1;
                     for (int k = 0; k < ngaps; ++k) {
@@ -229,6 +230,8 @@ extern "C" OCBNN_API int ocbnn_problem_create(const ocbnn_desc* desc, ocbnn_prob
                     }
                     memcpy(&dst[0], &n1, sizeof(int));
                     memcpy(&dst[1], &n2, sizeof(int));
+                    if (neg_n1 == -2) { neg_n1 = n1; neg_n2 = n2; }
+                    else if (neg_n1 != n1 || neg_n2 != n2) neg_n1 = neg_n2 = -1;
                 } else {
                     for (int k = 0; k < desc->cparam_stride; ++k) r[s0 + 2 + k] = src[k];
                 }
@@ -271,6 +274,8 @@ extern "C" OCBNN_API int ocbnn_problem_create(const ocbnn_desc* desc, ocbnn_prob
     a.n_pos = seg_n[0];
     a.n_neg = seg_n[1];
     a.n_dir = seg_n[2];
+    a.neg_n1 = neg_n1 < 0 ? -1 : neg_n1;
+    a.neg_n2 = neg_n2 < 0 ? -1 : neg_n2;
     a.lik_head = desc->lik_head;
     a.rs = rs;
     a.s0 = s0;

@@ -49,6 +49,7 @@ struct EvalArgs {
     long long n_train;
     int n_cpoints;
     int n_pos, n_neg, n_dir;   // constraint rows are grouped: positive-Gaussian | negative-exponential | Dirichlet
+    int neg_n1, neg_n2;        // term structure shared by every negative row (one-sided, two-sided terms), -1 if the rows differ
     int lik_head;          // OCBNN_HEAD_LIK_* of the training rows
     int rs;                // record stride
     int s0;

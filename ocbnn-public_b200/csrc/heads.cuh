@@ -25,7 +25,7 @@ __device__ __forceinline__ void phi_classifier(float z, const HeadConsts& c, flo
 }
 
 // negative_exponential_cocp (base.py:364-388): sum over the forbidden gaps (a,b) of Phi(a-f) Phi(f-b).
-// Internal row layout (built by ocbnn_problem_create from the ABI's gap list): n1, n2 (int bits), n1 x (c, s) one-sided terms
+// Internal row layout (built by ocbnn_problem_create from the ABI's gap list): n1, n2 (int bits), n1 x (s c, s) one-sided terms
 // Phi(s (f - c)) [gaps with one infinite end], n2 x (a, b) two-sided terms.
 __device__ __forceinline__ void head_neg_exp(float f, const float* __restrict__ prm, const HeadConsts& c, float& val, float& df) {
     const int n1 = __float_as_int(prm[0]), n2 = __float_as_int(prm[1]);
@@ -34,7 +34,7 @@ __device__ __forceinline__ void head_neg_exp(float f, const float* __restrict__ 
     const float* q = prm + 2;
     for (int k = 0; k < n1; ++k, q += 2) {
         float P, D;
-        phi_classifier(q[1] * (f - q[0]), c, P, D);
+        phi_classifier(fmaf(q[1], f, -q[0]), c, P, D);
         val += P;
         df = fmaf(q[1], D, df);
     }

@@ -7,8 +7,8 @@
 namespace ocbnn {
 
 constexpr int kSmallThreads = 128;
-constexpr bool kDefaultHmcSmem = true;    // measured on B200 (W2, 262144 chains): smem state, 4 CTAs/SM 1.34 G steps/s vs register state, 2 CTAs/SM 1.21 G
-constexpr int kDefaultHmcMb = 4;
+constexpr int kPointUnroll = OCBNN_POINT_UNROLL;
+constexpr int kDefaultHmcMb = 4, kDefaultHmcU = 2;   // measured defaults of the one-chain-per-thread HMC kernel   // points in flight per thread in K1 / K4
 
 __host__ __device__ constexpr int kSmemFixedFloats(int ns) { return 4 * ns; }   // float4 prior table per slot
 
@@ -29,110 +29,31 @@ k_logpost_small(EvalArgs a, const float* __restrict__ w, long long m, float* __r
     float2 wv[N::NS], g[N::NS];
     load_state<N>(wv, w + chain * N::D);
     float lp;
-    evaluate<N, G>(a, c, /*restage=*/true, RegView<N::NS>{wv}, g, lp, lane);
+    evaluate<N, G, kPointUnroll>(a, c, /*restage=*/true, RegView<N::NS>{wv}, g, lp, lane);
     if (active && lane == 0) {
         if (out_lp) out_lp[chain] = lp;
         if (out_grad) store_state<N>(g, out_grad + chain * N::D);
     }
 }
 
-template <class N>
-__device__ __forceinline__ float kinetic(const float2 (&p)[N::NS]) {
-    double ks = 0.0;
-#pragma unroll
-    for (int s = 0; s < N::NS; ++s) {
-        const float2 e = __fmul2_rn(p[s], p[s]);
-        ks += (double)e.x + (double)e.y;
-    }
-    return 0.5f * (float)ks;
-}
-// y += fl(c * x), elementwise, two roundings like the reference's `y += c * x` on fp32 tensors
-template <class N>
-__device__ __forceinline__ void axpy_rn(float2 (&y)[N::NS], float c, const float2 (&x)[N::NS]) {
-    const float2 cc = f2(c);
-#pragma unroll
-    for (int s = 0; s < N::NS; ++s) y[s] = __fadd2_rn(y[s], __fmul2_rn(cc, x[s]));
-}
-
 // ---- K2 ------------------------------------------------------------------------------------------------
-// One HMC iteration (bnn/inference.py:39-78):  p ~ injected;  U0,K0;  p -= eps/2 dU;  L x { q += eps p ; [l<L] p -= eps dU };
+// HMC (bnn/inference.py:39-78):  p ~ injected;  U0,K0;  p -= eps/2 dU;  L x { q += eps p ; [l<L] p -= eps dU };
 // p -= eps/2 dU;  U1,K1;  accept iff u < exp(U0 - U1 + K0 - K1)  (fp32 exp, float64 compare, strict <).
-// dU = -grad log posterior, so "p -= c*dU" is "p += c*g" with identical rounding (fl(c*g) then one add).
-// The value+gradient at q_L is reused as U0/grad of the next iteration (the reference recomputes both).
-template <class N, int G, int MB>
+// dU = -grad log posterior, so "p -= c*dU" is "p += c*g" with identical rounding (fl(c*g) then one add, like the
+// reference's `y += c * x` on fp32 tensors).  The value+gradient at q_L is reused as U0/grad of the next iteration (the
+// reference recomputes both).
+//
+// One launch runs n_it iterations x L leapfrog steps of every chain.  The master copies of q and p of every thread live in
+// its own column of shared memory (slot-major float2, conflict-free): they are touched once per leapfrog step, while the
+// evaluator keeps its own (scaled) copy of the weights, the gradient accumulators and the per-point temporaries in
+// registers.  The trajectory is a single loop around ONE inlined evaluate() (phase l = 0 is the evaluation at the start
+// of an iteration, needed at launch and after a restore-on-reject), which keeps the kernel small enough for the
+// instruction cache and the register allocator.
+template <class N, int G, int MB, int U>
 __global__ void __launch_bounds__(kSmallThreads, MB)
 k_hmc_small(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, const double* __restrict__ u, long long m, int n_it,
             float eps, float eps_half, int L, int restore, uint8_t* __restrict__ out_acc, float* __restrict__ out_h,
             int* __restrict__ out_flags, float* __restrict__ out_samples, int thin, int tile_cap) {
-    extern __shared__ __align__(16) float smem[];
-    float4* pri_s = reinterpret_cast<float4*>(smem);
-    float* tab = smem + kSmemFixedFloats(N::NS);
-    EvalCtx c = make_ctx(a, tab, pri_s, tile_cap);
-    load_pri_slots<N>(pri_s, a);
-    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const int lane = threadIdx.x % G;
-    const bool active = gid < m;
-    const long long chain = active ? gid : m - 1;
-    const bool writer = active && lane == 0;
-
-    float2 q[N::NS], p[N::NS], g[N::NS];
-    load_state<N>(q, q_io + chain * N::D);
-    float lp;
-    evaluate<N, G>(a, c, /*restage=*/true, RegView<N::NS>{q}, g, lp, lane);   // stages the (fixed) point set once
-    int nan_flag = 0;
-    bool need_eval = false;
-
-    for (int it = 0; it < n_it; ++it) {
-        if (__any_sync(0xffffffffu, need_eval)) evaluate<N, G>(a, c, false, RegView<N::NS>{q}, g, lp, lane);
-        need_eval = false;
-        load_state<N>(p, p0 + ((long long)it * m + chain) * N::D);
-        const float U0 = -lp;
-        const float K0 = kinetic<N>(p);
-        if (restore) {   // keep q0 for a possible restore
-            if (writer) store_state<N>(q, q_io + chain * N::D);
-            __syncwarp();
-        }
-        axpy_rn<N>(p, eps_half, g);
-        for (int l = 1; l <= L; ++l) {
-            axpy_rn<N>(q, eps, p);
-            evaluate<N, G>(a, c, false, RegView<N::NS>{q}, g, lp, lane);
-            axpy_rn<N>(p, (l < L) ? eps : eps_half, g);
-        }
-        bool isn = false;
-#pragma unroll
-        for (int s = 0; s < N::NS; ++s) isn |= isnan(q[s].x) | isnan(q[s].y);
-        nan_flag |= isn ? 1 : 0;
-        const float U1 = -lp;
-        const float K1 = kinetic<N>(p);
-        const float dH = __fsub_rn(__fadd_rn(__fsub_rn(U0, U1), K0), K1);
-        const double alpha = (double)expf(dH);
-        const double ui = __ldg(u + (long long)it * m + chain);
-        const bool acc = ui < alpha;
-        if (writer) {
-            if (out_acc) out_acc[(long long)it * m + chain] = acc ? 1 : 0;
-            if (out_h) reinterpret_cast<float4*>(out_h)[(long long)it * m + chain] = make_float4(U0, K0, U1, K1);
-        }
-        if (restore && !acc) {
-            load_state<N>(q, q_io + chain * N::D);
-            need_eval = true;
-        }
-        if (out_samples && thin > 0 && ((it + 1) % thin == 0) && writer)
-            store_state<N>(q, out_samples + ((long long)((it + 1) / thin - 1) * m + chain) * N::D);
-    }
-    if (writer) {
-        store_state<N>(q, q_io + chain * N::D);
-        if (out_flags) out_flags[chain] = nan_flag;
-    }
-}
-
-// K2, shared-memory state variant: q and p of every thread live in its own column of shared memory (slot-major,
-// float2), only the gradient accumulators and the per-point temporaries stay in registers.  Fewer registers per thread ->
-// more resident warps to hide the MUFU / FMA latencies of the evaluator.  Same arithmetic, same rounding as k_hmc_small.
-template <class N, int G, int MB>
-__global__ void __launch_bounds__(kSmallThreads, MB)
-k_hmc_small_sm(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, const double* __restrict__ u, long long m, int n_it,
-               float eps, float eps_half, int L, int restore, uint8_t* __restrict__ out_acc, float* __restrict__ out_h,
-               int* __restrict__ out_flags, float* __restrict__ out_samples, int thin, int tile_cap) {
     extern __shared__ __align__(16) float smem[];
     float4* pri_s = reinterpret_cast<float4*>(smem);
     float2* qs = reinterpret_cast<float2*>(smem + kSmemFixedFloats(N::NS)) + threadIdx.x;     // [NS][kSmallThreads]
@@ -145,6 +66,7 @@ k_hmc_small_sm(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p
     const bool active = gid < m;
     const long long chain = active ? gid : m - 1;
     const bool writer = active && lane == 0;
+    const bool multi = c.npts > c.tile_cap;
     const SmemView qv{qs, kSmallThreads};
 
     auto load_to = [&](float2* dst, const float* __restrict__ src) {
@@ -160,52 +82,67 @@ k_hmc_small_sm(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p
             if (N::cidx(s, 1) >= 0) dst[N::cidx(s, 1)] = v.y;
         }
     };
-    auto kinetic_s = [&]() {
-        double ks = 0.0;
-#pragma unroll
-        for (int s = 0; s < N::NS; ++s) {
-            const float2 pv = ps[s * kSmallThreads];
-            const float2 e = __fmul2_rn(pv, pv);
-            ks += (double)e.x + (double)e.y;
-        }
-        return 0.5f * (float)ks;
-    };
 
     float2 g[N::NS];
+    float lp = 0.f, U0 = 0.f, K0 = 0.f;
+    int nan_flag = 0, it = 0, l = 0;
+    bool first = true;
     load_to(qs, q_io + chain * N::D);
-    float lp;
-    evaluate<N, G>(a, c, /*restage=*/true, qv, g, lp, lane);
-    int nan_flag = 0;
-    bool need_eval = false;
-    for (int it = 0; it < n_it; ++it) {
-        if (__any_sync(0xffffffffu, need_eval)) evaluate<N, G>(a, c, false, qv, g, lp, lane);
-        need_eval = false;
-        load_to(ps, p0 + ((long long)it * m + chain) * N::D);
-        const float U0 = -lp;
-        const float K0 = kinetic_s();
+
+    // start of iteration `it`: momenta in, U0/K0, backup of q for restore-on-reject, first half kick
+    auto begin_iteration = [&]() {
+        const float* __restrict__ src = p0 + ((long long)it * m + chain) * N::D;
+        U0 = -lp;
         if (restore) {
             if (writer) store_from(qs, q_io + chain * N::D);
             __syncwarp();
         }
+        double ks = 0.0;
 #pragma unroll
-        for (int s = 0; s < N::NS; ++s) ps[s * kSmallThreads] = __fadd2_rn(ps[s * kSmallThreads], __fmul2_rn(f2(eps_half), g[s]));
-        for (int l = 1; l <= L; ++l) {
+        for (int s = 0; s < N::NS; ++s) {
+            const float2 pv = make_float2(N::cidx(s, 0) >= 0 ? __ldg(src + N::cidx(s, 0)) : 0.f, N::cidx(s, 1) >= 0 ? __ldg(src + N::cidx(s, 1)) : 0.f);
+            const float2 e = __fmul2_rn(pv, pv);
+            ks += (double)e.x + (double)e.y;
+            ps[s * kSmallThreads] = __fadd2_rn(pv, __fmul2_rn(f2(eps_half), g[s]));
+        }
+        K0 = 0.5f * (float)ks;
+    };
+
+    for (;;) {
+        if (l >= 1) {
 #pragma unroll
             for (int s = 0; s < N::NS; ++s) qs[s * kSmallThreads] = __fadd2_rn(qs[s * kSmallThreads], __fmul2_rn(f2(eps), ps[s * kSmallThreads]));
-            evaluate<N, G>(a, c, false, qv, g, lp, lane);
+        }
+        evaluate<N, G, U>(a, c, first, qv, g, lp, lane);      // the first call stages the (fixed) point set
+        first = false;
+        if (l == 0) {
+            begin_iteration();
+            l = 1;
+            continue;
+        }
+        {
             const float2 e2 = f2((l < L) ? eps : eps_half);
 #pragma unroll
             for (int s = 0; s < N::NS; ++s) ps[s * kSmallThreads] = __fadd2_rn(ps[s * kSmallThreads], __fmul2_rn(e2, g[s]));
         }
+        if (l < L) {
+            ++l;
+            continue;
+        }
+        // end of the trajectory: Metropolis-Hastings
         bool isn = false;
+        double ks = 0.0;
 #pragma unroll
         for (int s = 0; s < N::NS; ++s) {
             const float2 v = qs[s * kSmallThreads];
             isn |= isnan(v.x) | isnan(v.y);
+            const float2 pv = ps[s * kSmallThreads];
+            const float2 e = __fmul2_rn(pv, pv);
+            ks += (double)e.x + (double)e.y;
         }
         nan_flag |= isn ? 1 : 0;
         const float U1 = -lp;
-        const float K1 = kinetic_s();
+        const float K1 = 0.5f * (float)ks;
         const float dH = __fsub_rn(__fadd_rn(__fsub_rn(U0, U1), K0), K1);
         const double alpha = (double)expf(dH);
         const double ui = __ldg(u + (long long)it * m + chain);
@@ -214,12 +151,20 @@ k_hmc_small_sm(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p
             if (out_acc) out_acc[(long long)it * m + chain] = acc ? 1 : 0;
             if (out_h) reinterpret_cast<float4*>(out_h)[(long long)it * m + chain] = make_float4(U0, K0, U1, K1);
         }
-        if (restore && !acc) {
-            load_to(qs, q_io + chain * N::D);
-            need_eval = true;
-        }
+        const bool need_eval = restore && !acc;
+        if (need_eval) load_to(qs, q_io + chain * N::D);
         if (out_samples && thin > 0 && ((it + 1) % thin == 0) && writer)
             store_from(qs, out_samples + ((long long)((it + 1) / thin - 1) * m + chain) * N::D);
+        if (++it == n_it) break;
+        // a restored chain needs lp and g at the restored state; with a multi-tile point set evaluate() contains
+        // __syncthreads, so the decision must then be block-uniform
+        const bool again = multi ? (__syncthreads_or(need_eval ? 1 : 0) != 0) : (__any_sync(0xffffffffu, need_eval) != 0);
+        if (again) {
+            l = 0;
+            continue;
+        }
+        begin_iteration();
+        l = 1;
     }
     if (writer) {
         store_from(qs, q_io + chain * N::D);
@@ -242,7 +187,7 @@ k_sgld_small(EvalArgs a, float* __restrict__ w_io, const float* __restrict__ noi
     const bool active = gid < m;
     const long long chain = active ? gid : m - 1;
     const bool writer = active && lane == 0;
-    float2 w[N::NS], g[N::NS], nz[N::NS];
+    float2 w[N::NS], g[N::NS];
     load_state<N>(w, w_io + chain * N::D);
     const bool batched = a.batch_stride > 1;
     EvalCtx c = make_ctx(a, tab, pri_s, tile_cap);
@@ -252,11 +197,14 @@ k_sgld_small(EvalArgs a, float* __restrict__ w_io, const float* __restrict__ noi
             c = make_ctx(a, tab, pri_s, tile_cap);
         }
         float lp;
-        evaluate<N, G>(a, c, /*restage=*/batched || t == 0, RegView<N::NS>{w}, g, lp, lane);
+        evaluate<N, G, kPointUnroll>(a, c, /*restage=*/batched || t == 0, RegView<N::NS>{w}, g, lp, lane);
         const float2 he = f2(half_eps[t]);
-        load_state<N>(nz, noise + ((long long)t * m + chain) * N::D);
+        const float* __restrict__ nz = noise + ((long long)t * m + chain) * N::D;
 #pragma unroll
-        for (int s = 0; s < N::NS; ++s) w[s] = __fadd2_rn(w[s], __fadd2_rn(__fmul2_rn(g[s], he), nz[s]));
+        for (int s = 0; s < N::NS; ++s) {
+            const float2 nv = make_float2(N::cidx(s, 0) >= 0 ? __ldg(nz + N::cidx(s, 0)) : 0.f, N::cidx(s, 1) >= 0 ? __ldg(nz + N::cidx(s, 1)) : 0.f);
+            w[s] = __fadd2_rn(w[s], __fadd2_rn(__fmul2_rn(g[s], he), nv));
+        }
         if (out_samples && thin > 0 && ((t + 1) % thin == 0) && writer)
             store_state<N>(w, out_samples + ((long long)((t + 1) / thin - 1) * m + chain) * N::D);
     }
@@ -305,13 +253,13 @@ struct SmallLaunch {
         OCBNN_LAUNCH_CHECK();
         return OCBNN_OK;
     }
-    template <int G, int MB, bool SM>
+    template <int G, int MB, int U>
     static int hmc_mb(const Problem& p, const EvalArgs& a, float* q, const float* p0, const double* u, long long m, int n_it, float eps,
                       float eps_half, int L, int restore, uint8_t* acc, float* h, int* flags, float* samples, int thin, cudaStream_t st) {
         int tile_cap;
-        const size_t extra = SM ? sizeof(float) * 4 * N::NS * kSmallThreads : 0;        // q and p columns of every thread
+        const size_t extra = sizeof(float) * 4 * N::NS * kSmallThreads;        // q and p columns of every thread
         size_t sm = smem_bytes(p, npts(a), tile_cap, extra) + extra;
-        auto k = SM ? k_hmc_small_sm<N, G, MB> : k_hmc_small<N, G, MB>;
+        auto k = k_hmc_small<N, G, MB, U>;
         OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         long long blocks = (m * G + kSmallThreads - 1) / kSmallThreads;
         k<<<(unsigned)blocks, kSmallThreads, sm, st>>>(a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin,
@@ -319,22 +267,26 @@ struct SmallLaunch {
         OCBNN_LAUNCH_CHECK();
         return OCBNN_OK;
     }
-    // Variant knobs (measured defaults in kDefaultHmc*): OCBNN_HMC_MB = resident CTAs per SM the kernel is compiled for,
-    // OCBNN_HMC_STATE = reg | smem (where q and p live).
+    // One chain per thread (G = 1, the large-M case) has tuning variants selected by OCBNN_HMC_MB (resident CTAs per SM
+    // the kernel is compiled for: register cap 65536 / (128 MB)) and OCBNN_HMC_U (points in flight per thread); measured
+    // defaults in kDefaultHmc*.  Lane-split chains (G > 1, few chains) use one configuration.
     template <int G>
     static int hmc(const Problem& p, const EvalArgs& a, float* q, const float* p0, const double* u, long long m, int n_it, float eps,
                    float eps_half, int L, int restore, uint8_t* acc, float* h, int* flags, float* samples, int thin, cudaStream_t st) {
-        static const int mb = [] { const char* e = getenv("OCBNN_HMC_MB"); return e ? atoi(e) : kDefaultHmcMb; }();
-        static const bool smst = [] { const char* e = getenv("OCBNN_HMC_STATE"); return e ? e[0] == 's' : kDefaultHmcSmem; }();
-#define OCBNN_HMC_GO(MBV, SMV) return hmc_mb<G, MBV, SMV>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st)
-        if (smst) {
-            if (mb <= 3) OCBNN_HMC_GO(3, true);
-            if (mb == 4) OCBNN_HMC_GO(4, true);
-            OCBNN_HMC_GO(5, true);
+#define OCBNN_HMC_GO(MBV, UV) return hmc_mb<G, MBV, UV>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st)
+        if (G == 1) {
+            static const int mb = [] { const char* e = getenv("OCBNN_HMC_MB"); return e ? atoi(e) : kDefaultHmcMb; }();
+            static const int uu = [] { const char* e = getenv("OCBNN_HMC_U"); return e ? atoi(e) : kDefaultHmcU; }();
+            constexpr int G1 = G == 1 ? 1 : 0;      // instantiate the variants for G = 1 only
+            if (G1) {
+                if (uu <= 1) OCBNN_HMC_GO(G1 ? 5 : 4, G1 ? 1 : 2);
+                if (uu == 3) OCBNN_HMC_GO(G1 ? 3 : 4, G1 ? 3 : 2);
+                if (uu >= 4) OCBNN_HMC_GO(G1 ? 3 : 4, G1 ? 4 : 2);
+                if (mb <= 3) OCBNN_HMC_GO(G1 ? 3 : 4, 2);
+                if (mb >= 5) OCBNN_HMC_GO(G1 ? 5 : 4, 2);
+            }
         }
-        if (mb <= 2) OCBNN_HMC_GO(2, false);
-        if (mb == 3) OCBNN_HMC_GO(3, false);
-        OCBNN_HMC_GO(4, false);
+        OCBNN_HMC_GO(4, 2);
 #undef OCBNN_HMC_GO
     }
     template <int G>

@@ -75,28 +75,35 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 
-// activation on a pair; returns a and m with da/dz = kActScale<ACT> * m (the constant is folded into the upstream gradient)
+// ---- activation, evaluated in SCALED pre-activation units --------------------------------------------------------
+// The evaluator works on z' = c z with c = sqrt(log2 e) folded into W1 and b1 once per evaluation, so that the rbf
+// activation exp(-z^2) = 2^(-z'^2) is one FMUL2 + two MUFU.EX2 (the negation is an operand modifier) and its derivative
+// d/dz = -2 z a = -(2/c) z' a.  The constant -(2/c) c = ... is applied once to the accumulated W1/b1 gradients:
+// dL/dW1 = act_grad_scale * sum_points dL/da * (z' a) * x   with act_grad_scale = -2 sqrt(ln 2).
 template <int ACT>
-__device__ __forceinline__ void act_pair(float2 z, float2& a, float2& m) {
-    if (ACT == OCBNN_ACT_RBF) {                       // exp(-z^2), base.py:84 ; d/dz = -2 z a
-        float2 t = __fmul2_rn(z, z);
-        float2 u = __fmul2_rn(t, f2(-1.4426950408889634f));
-        a = make_float2(ex2_approx(u.x), ex2_approx(u.y));
-        m = __fmul2_rn(z, a);
+__host__ __device__ constexpr float act_in_scale() { return ACT == OCBNN_ACT_RBF ? 1.2011224087864498f : 1.f; }
+template <int ACT>
+__host__ __device__ constexpr float act_grad_scale() { return ACT == OCBNN_ACT_RBF ? -1.6651092223153954f : 1.f; }
+
+// returns a = act(z) and m with da/dz' (up to act_grad_scale) = m
+template <int ACT>
+__device__ __forceinline__ void act_pair(float2 zs, float2& a, float2& m) {
+    if (ACT == OCBNN_ACT_RBF) {                       // exp(-z^2), base.py:84
+        const float2 t = __fmul2_rn(zs, zs);
+        a = make_float2(ex2_approx(-t.x), ex2_approx(-t.y));
+        m = __fmul2_rn(zs, a);
     } else if (ACT == OCBNN_ACT_RELU) {               // max(z,0), base.py:86
-        a = make_float2(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f));
-        m = make_float2(z.x > 0.f ? 1.f : 0.f, z.y > 0.f ? 1.f : 0.f);
+        a = make_float2(fmaxf(zs.x, 0.f), fmaxf(zs.y, 0.f));
+        m = make_float2(zs.x > 0.f ? 1.f : 0.f, zs.y > 0.f ? 1.f : 0.f);
     } else {
-        a = z;
+        a = zs;
         m = f2(1.f);
     }
 }
-template <int ACT>
-__device__ __forceinline__ constexpr float act_scale() { return ACT == OCBNN_ACT_RBF ? -2.f : 1.f; }
 
-// Weight views: the evaluator reads weights through operator[] so that they can live in registers (RegView) or in a
-// per-thread column of shared memory (SmemView: slot s of thread t at base[s * stride], conflict-free float2 loads), which
-// frees 2 x NS registers per thread for occupancy.
+// Weight views: the evaluator reads the chain's packed weights through operator[] so that the master copy can live in
+// registers (RegView) or in a per-thread column of shared memory (SmemView: slot s of thread t at base[s * stride],
+// conflict-free float2 loads).  The evaluation copy (W1, b1 scaled) is always built in registers.
 template <int NS>
 struct RegView {
     const float2 (&a)[NS];
@@ -105,8 +112,8 @@ struct RegView {
 struct SmemView {
     const float2* base;
     int stride;
-    // volatile asm: the loads must stay inside the point loop (a plain load is loop invariant and would be hoisted back
-    // into 2 x NS registers, which is exactly what this view is meant to avoid)
+    // volatile asm: every use is its own load (a plain load at the top of an evaluation would be kept live in 2 x NS
+    // registers until the prior term at the end, which is exactly what this view is meant to avoid)
     __device__ __forceinline__ float2 operator[](int s) const {
         float2 v;
         const unsigned addr = (unsigned)__cvta_generic_to_shared(base + s * stride);
@@ -119,26 +126,28 @@ struct SmemView {
 struct FastConsts {
     float2 tau_l2e;      // 2*tau_i*log2(e)
     float2 tau2;         // 2*tau_i
+    float zmax;          // Phi argument clamp: 40 / (2 max tau)  (Phi < e^-40 beyond; the reference's fp32 tanh form is exactly 0)
     float lik_scale, pos_inv_var;
 };
 
-// Phi(z) = 1/((1+e^{2 tau0 z})(1+e^{2 tau1 z})) and dPhi/dz (see heads.cuh); exponent clamped at 2^57.7 ~ e^40
+// Phi(z) = 1/((1+e^{2 tau0 z})(1+e^{2 tau1 z})) and dPhi/dz (see heads.cuh)
 __device__ __forceinline__ void phi_fast(float z, const FastConsts& c, float& P, float& dP) {
-    float2 u = __fmul2_rn(f2(z), c.tau_l2e);
-    float2 e = make_float2(ex2_approx(fminf(u.x, 57.7f)), ex2_approx(fminf(u.y, 57.7f)));
-    float2 ab = __fadd2_rn(e, f2(1.f));
-    float r = rcp_approx(ab.x * ab.y);
-    float2 t = __fmul2_rn(e, c.tau2);
-    float s = fmaf(t.x, ab.y, t.y * ab.x);
+    const float2 u = __fmul2_rn(f2(fminf(z, c.zmax)), c.tau_l2e);
+    const float2 e = make_float2(ex2_approx(u.x), ex2_approx(u.y));
+    const float2 ab = __fadd2_rn(e, f2(1.f));
+    const float r = rcp_approx(ab.x * ab.y);
+    const float2 t = __fmul2_rn(e, c.tau2);
+    const float s = fmaf(t.x, ab.y, t.y * ab.x);
     P = r;
     dP = -(r * r) * s;
 }
 
 // two Phi evaluations packed in f32x2 lanes: 4 EX2 + 2 RCP, every other op a packed instruction
 __device__ __forceinline__ void phi_fast2(float2 z, const FastConsts& c, float2& P, float2& dP) {
+    z = make_float2(fminf(z.x, c.zmax), fminf(z.y, c.zmax));
     const float2 u0 = __fmul2_rn(z, f2(c.tau_l2e.x)), u1 = __fmul2_rn(z, f2(c.tau_l2e.y));
-    const float2 e0 = make_float2(ex2_approx(fminf(u0.x, 57.7f)), ex2_approx(fminf(u0.y, 57.7f)));
-    const float2 e1 = make_float2(ex2_approx(fminf(u1.x, 57.7f)), ex2_approx(fminf(u1.y, 57.7f)));
+    const float2 e0 = make_float2(ex2_approx(u0.x), ex2_approx(u0.y));
+    const float2 e1 = make_float2(ex2_approx(u1.x), ex2_approx(u1.y));
     const float2 a = __fadd2_rn(e0, f2(1.f)), b = __fadd2_rn(e1, f2(1.f));
     const float2 ab = __fmul2_rn(a, b);
     const float2 r = make_float2(rcp_approx(ab.x), rcp_approx(ab.y));
@@ -147,16 +156,25 @@ __device__ __forceinline__ void phi_fast2(float2 z, const FastConsts& c, float2&
     dP = __fmul2_rn(__fmul2_rn(r, make_float2(-r.x, -r.y)), s);
 }
 
-// Heads are evaluated for U points at once (run_many) so that their long serial MUFU chains interleave.
+// phi_fast2 with ONE reciprocal for the pair: r = 1/(ab.x ab.y), 1/ab.x = r ab.y, 1/ab.y = r ab.x (two FMULs instead of
+// a MUFU op; MUFU is the binding pipe of the toy-net kernels).  ab <= (1+e^40)^2 per lane, so the product can overflow only
+// when both lanes are saturated; then r = 0 and both Phi (< e^-40, exactly 0 in the reference's fp32 form) come out as 0.
+__device__ __forceinline__ void phi_fast2_1r(float2 z, const FastConsts& c, float2& P, float2& dP) {
+    z = make_float2(fminf(z.x, c.zmax), fminf(z.y, c.zmax));
+    const float2 u0 = __fmul2_rn(z, f2(c.tau_l2e.x)), u1 = __fmul2_rn(z, f2(c.tau_l2e.y));
+    const float2 e0 = make_float2(ex2_approx(u0.x), ex2_approx(u0.y));
+    const float2 e1 = make_float2(ex2_approx(u1.x), ex2_approx(u1.y));
+    const float2 a = __fadd2_rn(e0, f2(1.f)), b = __fadd2_rn(e1, f2(1.f));
+    const float2 ab = __fmul2_rn(a, b);
+    const float rx = rcp_approx(ab.x * ab.y);
+    const float2 r = make_float2(rx * ab.y, rx * ab.x);
+    const float2 s = __ffma2_rn(__fmul2_rn(e0, f2(c.tau2.x)), b, __fmul2_rn(__fmul2_rn(e1, f2(c.tau2.y)), a));
+    P = r;
+    dP = __fmul2_rn(__fmul2_rn(r, make_float2(-r.x, -r.y)), s);
+}
+
 template <int KIND, int SK>
 struct FastHead;
-
-template <int KIND, int SK, int U>
-__device__ __forceinline__ void head_many_generic(const float (&f)[U][SK], const float* const (&prm)[U], const FastConsts& c, float (&val)[U],
-                                                  float (&df)[U][SK]) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) FastHead<KIND, SK>::run(f[u], prm[u], c, val[u], df[u]);
-}
 
 template <int SK>
 struct FastHead<OCBNN_HEAD_LIK_GAUSS, SK> {
@@ -171,7 +189,7 @@ struct FastHead<OCBNN_HEAD_LIK_GAUSS, SK> {
     }
 };
 // internal parameter layout of a negative-COCP row (built by ocbnn_problem_create from the ABI's gap list):
-//   n1, n2 (int bits), n1 x (c, s) one-sided terms Phi(s (f - c)), n2 x (a, b) two-sided terms Phi(a - f) Phi(f - b)
+//   n1, n2 (int bits), n1 x (s c, s) one-sided terms Phi(s f - s c), n2 x (a, b) two-sided terms Phi(a - f) Phi(f - b)
 template <int SK>
 struct FastHead<OCBNN_HEAD_NEG_EXP, SK> {
     static __device__ __forceinline__ void run(const float (&f)[SK], const float* __restrict__ prm, const FastConsts& c, float& val, float (&df)[SK]) {
@@ -181,71 +199,21 @@ struct FastHead<OCBNN_HEAD_NEG_EXP, SK> {
         const float* q = prm + 2;
         for (int k = 0; k < n1; ++k, q += 2) {
             float P, D;
-            phi_fast(q[1] * (f[0] - q[0]), c, P, D);
+            phi_fast(fmaf(q[1], f[0], -q[0]), c, P, D);
             val += P;
             d = fmaf(q[1], D, d);
         }
         for (int k = 0; k < n2; ++k, q += 2) {
-            float P1, D1, P2, D2;
-            phi_fast(q[0] - f[0], c, P1, D1);
-            phi_fast(f[0] - q[1], c, P2, D2);
-            val = fmaf(P1, P2, val);
-            d += P1 * D2 - D1 * P2;
+            float2 P, D;
+            phi_fast2(make_float2(q[0] - f[0], f[0] - q[1]), c, P, D);
+            val = fmaf(P.x, P.y, val);
+            d += P.x * D.y - D.x * P.y;
         }
 #pragma unroll
         for (int k = 0; k < SK; ++k) df[k] = 0.f;
         df[0] = d;
     }
-    // two points in lockstep: term k of both points is one packed Phi evaluation; a point with fewer terms is masked
-    static __device__ __forceinline__ void run_pair(float fa, float fb, const float* __restrict__ pa, const float* __restrict__ pb,
-                                                    const FastConsts& c, float2& val, float2& d) {
-        const int n1a = __float_as_int(pa[0]), n2a = __float_as_int(pa[1]);
-        const int n1b = __float_as_int(pb[0]), n2b = __float_as_int(pb[1]);
-        const int n1 = max(n1a, n1b), n2 = max(n2a, n2b);
-        const float2 ff = make_float2(fa, fb);
-        val = f2(0.f);
-        d = f2(0.f);
-        for (int k = 0; k < n1; ++k) {
-            const bool va = k < n1a, vb = k < n1b;
-            const float2 cc = make_float2(va ? pa[2 + 2 * k] : 0.f, vb ? pb[2 + 2 * k] : 0.f);
-            const float2 ss = make_float2(va ? pa[3 + 2 * k] : 0.f, vb ? pb[3 + 2 * k] : 0.f);
-            float2 P, D;
-            phi_fast2(__fmul2_rn(ss, __fadd2_rn(ff, make_float2(-cc.x, -cc.y))), c, P, D);
-            val = __ffma2_rn(P, make_float2(va ? 1.f : 0.f, vb ? 1.f : 0.f), val);
-            d = __ffma2_rn(ss, D, d);
-        }
-        const float* qa = pa + 2 + 2 * n1a;
-        const float* qb = pb + 2 + 2 * n1b;
-        for (int k = 0; k < n2; ++k) {
-            const bool va = k < n2a, vb = k < n2b;
-            const float2 lo = make_float2(va ? qa[2 * k] : 0.f, vb ? qb[2 * k] : 0.f);
-            const float2 hi = make_float2(va ? qa[2 * k + 1] : 0.f, vb ? qb[2 * k + 1] : 0.f);
-            const float2 msk = make_float2(va ? 1.f : 0.f, vb ? 1.f : 0.f);
-            float2 P1, D1, P2, D2;
-            phi_fast2(__fadd2_rn(lo, make_float2(-ff.x, -ff.y)), c, P1, D1);
-            phi_fast2(__fadd2_rn(ff, make_float2(-hi.x, -hi.y)), c, P2, D2);
-            val = __ffma2_rn(__fmul2_rn(P1, P2), msk, val);
-            const float2 dd = __ffma2_rn(P1, D2, make_float2(-D1.x * P2.x, -D1.y * P2.y));
-            d = __ffma2_rn(dd, msk, d);
-        }
-    }
 };
-template <int SK, int U>
-__device__ __forceinline__ void head_many_neg(const float (&f)[U][SK], const float* const (&prm)[U], const FastConsts& c, float (&val)[U],
-                                              float (&df)[U][SK]) {
-#pragma unroll
-    for (int u = 0; u + 1 < U; u += 2) {
-        float2 v, d;
-        FastHead<OCBNN_HEAD_NEG_EXP, SK>::run_pair(f[u][0], f[u + 1][0], prm[u], prm[u + 1], c, v, d);
-        val[u] = v.x;
-        val[u + 1] = v.y;
-#pragma unroll
-        for (int k = 0; k < SK; ++k) df[u][k] = df[u + 1][k] = 0.f;
-        df[u][0] = d.x;
-        df[u + 1][0] = d.y;
-    }
-    if (U & 1) FastHead<OCBNN_HEAD_NEG_EXP, SK>::run(f[U - 1], prm[U - 1], c, val[U - 1], df[U - 1]);
-}
 template <int SK>
 struct FastHead<OCBNN_HEAD_POS_GAUSS, SK> {
     static __device__ __forceinline__ void run(const float (&f)[SK], const float* __restrict__ prm, const FastConsts& c, float& val, float (&df)[SK]) {
@@ -277,23 +245,104 @@ struct FastHead<OCBNN_HEAD_LIK_BERNOULLI, SK> {
     }
 };
 
+// Head policies: run() evaluates the head of U points at once so that their serial MUFU chains interleave.
+template <int KIND>
+struct HeadEach {                                  // any head kind, one point after the other
+    template <int SK, int U>
+    static __device__ __forceinline__ void run(const float (&f)[U][SK], const float* const (&prm)[U], const FastConsts& c, float (&val)[U],
+                                               float (&df)[U][SK]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) FastHead<KIND, SK>::run(f[u], prm[u], c, val[u], df[u]);
+    }
+};
+// Negative COCP whose rows all have the same term structure (N1 one-sided, N2 two-sided terms; found by
+// ocbnn_problem_create): the N1 + 2 N2 Phi evaluations of the U points are packed pairwise into f32x2 lanes, no loop, no
+// per-row counts.  F1a/example.yaml (permitted [2.5,3]) is <2,0>; F3b (forbidden gap (1,2.5)) is <0,1>.
+template <int N1, int N2>
+struct HeadNegFixed {
+    template <int SK, int U>
+    static __device__ __forceinline__ void run(const float (&f)[U][SK], const float* const (&prm)[U], const FastConsts& c, float (&val)[U],
+                                               float (&df)[U][SK]) {
+        constexpr int NP = N1 + 2 * N2, T = U * NP;
+        float z[T], sg[U][N1 > 0 ? N1 : 1], P[T], D[T];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float* q = prm[u] + 2;
+#pragma unroll
+            for (int k = 0; k < N1; ++k) {
+                sg[u][k] = q[2 * k + 1];
+                z[u * NP + k] = fmaf(sg[u][k], f[u][0], -q[2 * k]);
+            }
+#pragma unroll
+            for (int k = 0; k < N2; ++k) {
+                z[u * NP + N1 + 2 * k] = q[2 * N1 + 2 * k] - f[u][0];
+                z[u * NP + N1 + 2 * k + 1] = f[u][0] - q[2 * N1 + 2 * k + 1];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i + 1 < T; i += 2) {
+            float2 Pp, Dp;
+            phi_fast2_1r(make_float2(z[i], z[i + 1]), c, Pp, Dp);
+            P[i] = Pp.x, P[i + 1] = Pp.y, D[i] = Dp.x, D[i + 1] = Dp.y;
+        }
+        if (T & 1) phi_fast(z[T - 1], c, P[T - 1], D[T - 1]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float v = 0.f, d = 0.f;
+#pragma unroll
+            for (int k = 0; k < N1; ++k) {
+                v = k == 0 ? P[u * NP] : v + P[u * NP + k];
+                d = k == 0 ? sg[u][0] * D[u * NP] : fmaf(sg[u][k], D[u * NP + k], d);
+            }
+#pragma unroll
+            for (int k = 0; k < N2; ++k) {
+                const int i = u * NP + N1 + 2 * k;
+                const float pd = P[i] * D[i + 1] - D[i] * P[i + 1];
+                if (N1 == 0 && k == 0) {
+                    v = P[i] * P[i + 1];
+                    d = pd;
+                } else {
+                    v = fmaf(P[i], P[i + 1], v);
+                    d += pd;
+                }
+            }
+            val[u] = v;
+#pragma unroll
+            for (int k = 0; k < SK; ++k) df[u][k] = 0.f;
+            df[u][0] = d;
+        }
+    }
+};
+
 #ifndef OCBNN_POINT_UNROLL
 #define OCBNN_POINT_UNROLL 2
 #endif
 
-// value + gradient contribution of U point records with a compile-time head.  The U points are independent until the
-// gradient accumulation, which gives the scheduler U forward/head dependency chains to interleave (the head is a long
-// serial chain of MUFU ops).  Records beyond the segment are passed with live[u] = 0 and contribute nothing.
-template <class N, int KIND, int U, class WV>
-__device__ __forceinline__ void point_eval(const WV& w, float2 (&g)[N::NS], double& lp, const float* const (&rec)[U],
-                                           const float (&live)[U], const FastConsts& fc) {
-    float2 xx[U][N::S0], a[U][N::HP], m[U][N::HP];
-    float f[U][N::SK], df[U][N::SK], val[U];
+// value + gradient contribution of U point records with a compile-time head.  `w` are the EVALUATION weights (W1, b1 in
+// scaled units, see act_in_scale); g accumulates the W1/b1 gradients in the same scaled units (evaluate() rescales once).
+// The U points are independent until the gradient accumulation, which gives the scheduler U forward/head dependency
+// chains to interleave.  Per hidden pair and point: S0 + 3 packed fma-pipe instructions + 2 MUFU forward, S0 + 2 backward
+// for single-output nets (dL/dz' = df w2 m: the factor w2 is constant over the points, so the W1/b1 accumulators hold
+// sum df m [x] and evaluate() multiplies by w2 once), S0 + 2 SK + 2 otherwise.
+// Single-input, single-output rbf nets ([1,H,1], every 1-D toy of the reference): dL/dz'_h = df w2_h z'_h a_h with
+// z'_h = w1'_h x + b1'_h, so the sums over points that the W1/b1 gradients need are moments of a in x,
+//   sum_p df_p z'_h a_h [x_p] = w1'_h A_{1[+1]} + b1'_h A_{0[+1]},   A_k = sum_p df_p x_p^k a_h(x_p),   A_0 = dL/dw2_h,
+// and the per-point work is three FFMA2 per hidden pair (A0, A1, A2) with neither z' nor z' a kept: one packed multiply and
+// two saved registers less per hidden pair and point.  evaluate() turns (A0, A1, A2) into the gradient once per evaluation.
+template <class N>
+__host__ __device__ constexpr bool use_moments() { return N::S0 == 1 && N::SK == 1 && N::ACT == OCBNN_ACT_RBF; }
+
+template <class N, class HEAD, int U>
+__device__ __forceinline__ void point_eval(const float2 (&w)[N::NS], float2 (&g)[N::NS], float& vacc, const float* const (&rec)[U],
+                                           const FastConsts& fc) {
+    constexpr bool MOM = use_moments<N>();
+    float2 a[U][N::HP], m[U][MOM ? 1 : N::HP];
+    float x[U][N::S0], f[U][N::SK], df[U][N::SK], val[U];
     const float* prm[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
 #pragma unroll
-        for (int d = 0; d < N::S0; ++d) xx[u][d] = f2(rec[u][d]);
+        for (int d = 0; d < N::S0; ++d) x[u][d] = rec[u][d];
         prm[u] = rec[u] + N::S0 + 2;
         float2 facc[N::SK];
 #pragma unroll
@@ -302,10 +351,16 @@ __device__ __forceinline__ void point_eval(const WV& w, float2 (&g)[N::NS], doub
         for (int hp = 0; hp < N::HP; ++hp) {
             float2 z = w[N::SB1 + hp];
 #pragma unroll
-            for (int d = 0; d < N::S0; ++d) z = __ffma2_rn(w[N::SW1 + d * N::HP + hp], xx[u][d], z);
-            act_pair<N::ACT>(z, a[u][hp], m[u][hp]);
+            for (int d = 0; d < N::S0; ++d) z = __ffma2_rn(w[N::SW1 + d * N::HP + hp], f2(x[u][d]), z);
+            if (MOM) {
+                const float2 t = __fmul2_rn(z, z);
+                a[u][hp] = make_float2(ex2_approx(-t.x), ex2_approx(-t.y));
+            } else {
+                act_pair<N::ACT>(z, a[u][hp], m[u][MOM ? 0 : hp]);
+            }
 #pragma unroll
-            for (int k = 0; k < N::SK; ++k) facc[k] = __ffma2_rn(w[N::SW2 + k * N::HP + hp], a[u][hp], facc[k]);
+            for (int k = 0; k < N::SK; ++k)
+                facc[k] = (hp == 0) ? __fmul2_rn(w[N::SW2 + k * N::HP], a[u][0]) : __ffma2_rn(w[N::SW2 + k * N::HP + hp], a[u][hp], facc[k]);
         }
 #pragma unroll
         for (int k = 0; k < N::SK; ++k) {
@@ -313,39 +368,65 @@ __device__ __forceinline__ void point_eval(const WV& w, float2 (&g)[N::NS], doub
             f[u][k] = (facc[k].x + facc[k].y) + b2;
         }
     }
-    if (KIND == OCBNN_HEAD_NEG_EXP) head_many_neg<N::SK, U>(f, prm, fc, val, df);
-    else head_many_generic<KIND, N::SK, U>(f, prm, fc, val, df);
-    float vsum = 0.f;                      // the U values are added in fp32, then once into the float64 accumulator
+    HEAD::template run<N::SK, U>(f, prm, fc, val, df);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const float wgt = rec[u][N::S0 + 1] * live[u];
-        vsum = fmaf(wgt, val[u], vsum);
+        const float wgt = rec[u][N::S0 + 1];
+        vacc = fmaf(wgt, val[u], vacc);
 #pragma unroll
         for (int k = 0; k < N::SK; ++k) df[u][k] *= wgt;
     }
-    lp += (double)vsum;
 #pragma unroll
     for (int k = 0; k < N::SK; ++k) {
-        float s = 0.f;
+        float s = df[0][k];
 #pragma unroll
-        for (int u = 0; u < U; ++u) s += df[u][k];
+        for (int u = 1; u < U; ++u) s += df[u][k];
         if (k & 1) g[N::SB2 + k / 2].y += s; else g[N::SB2 + k / 2].x += s;
+    }
+    if (MOM) {
+        float2 d0[U], d1[U], d2[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float dx = df[u][0] * x[u][0];
+            d0[u] = f2(df[u][0]);
+            d1[u] = f2(dx);
+            d2[u] = f2(dx * x[u][0]);
+        }
+#pragma unroll
+        for (int hp = 0; hp < N::HP; ++hp) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                g[N::SW2 + hp] = __ffma2_rn(d0[u], a[u][hp], g[N::SW2 + hp]);     // A0
+                g[N::SB1 + hp] = __ffma2_rn(d1[u], a[u][hp], g[N::SB1 + hp]);     // A1
+                g[N::SW1 + hp] = __ffma2_rn(d2[u], a[u][hp], g[N::SW1 + hp]);     // A2
+            }
+        }
+        return;
     }
 #pragma unroll
     for (int hp = 0; hp < N::HP; ++hp) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            float2 da = f2(0.f);
+            const float2 mm = m[u][MOM ? 0 : hp];
+            if (N::SK == 1) {
+                const float2 dk = f2(df[u][0]);
+                g[N::SW2 + hp] = __ffma2_rn(dk, a[u][hp], g[N::SW2 + hp]);
+                g[N::SB1 + hp] = __ffma2_rn(dk, mm, g[N::SB1 + hp]);
 #pragma unroll
-            for (int k = 0; k < N::SK; ++k) {
-                const float2 dk = f2(df[u][k]);
-                da = __ffma2_rn(dk, w[N::SW2 + k * N::HP + hp], da);
-                g[N::SW2 + k * N::HP + hp] = __ffma2_rn(dk, a[u][hp], g[N::SW2 + k * N::HP + hp]);
+                for (int d = 0; d < N::S0; ++d) g[N::SW1 + d * N::HP + hp] = __ffma2_rn(f2(df[u][0] * x[u][d]), mm, g[N::SW1 + d * N::HP + hp]);
+            } else {
+                float2 da = f2(0.f);
+#pragma unroll
+                for (int k = 0; k < N::SK; ++k) {
+                    const float2 dk = f2(df[u][k]);
+                    da = (k == 0) ? __fmul2_rn(dk, w[N::SW2 + hp]) : __ffma2_rn(dk, w[N::SW2 + k * N::HP + hp], da);
+                    g[N::SW2 + k * N::HP + hp] = __ffma2_rn(dk, a[u][hp], g[N::SW2 + k * N::HP + hp]);
+                }
+                const float2 dz = __fmul2_rn(da, mm);
+                g[N::SB1 + hp] = __fadd2_rn(g[N::SB1 + hp], dz);
+#pragma unroll
+                for (int d = 0; d < N::S0; ++d) g[N::SW1 + d * N::HP + hp] = __ffma2_rn(dz, f2(x[u][d]), g[N::SW1 + d * N::HP + hp]);
             }
-            const float2 dz = __fmul2_rn(__fmul2_rn(da, f2(act_scale<N::ACT>())), m[u][hp]);
-            g[N::SB1 + hp] = __fadd2_rn(g[N::SB1 + hp], dz);
-#pragma unroll
-            for (int d = 0; d < N::S0; ++d) g[N::SW1 + d * N::HP + hp] = __ffma2_rn(dz, xx[u][d], g[N::SW1 + d * N::HP + hp]);
         }
     }
 }
@@ -421,6 +502,7 @@ __device__ __forceinline__ EvalCtx make_ctx(const EvalArgs& a, float* tab, const
     c.hc.pos_inv_var = a.pos_inv_var;
     c.fc.tau2 = make_float2(2.f * a.tau0, 2.f * a.tau1);
     c.fc.tau_l2e = make_float2(2.f * a.tau0 * 1.4426950408889634f, 2.f * a.tau1 * 1.4426950408889634f);
+    c.fc.zmax = 40.f / fmaxf(2.f * fmaxf(a.tau0, a.tau1), 1e-30f);
     c.fc.lik_scale = a.lik_scale;
     c.fc.pos_inv_var = a.pos_inv_var;
     return c;
@@ -437,30 +519,48 @@ __device__ __forceinline__ void load_pri_slots(float4* pri_s, const EvalArgs& a)
     }
 }
 
-template <class N, int G, int KIND, class WV>
-__device__ __forceinline__ void eval_segment(const EvalCtx& c, int rs, int lo, int hi, const WV& w, float2 (&g)[N::NS],
+// points [lo, hi) of the staged tile with one compile-time head: lane r of the chain's G lanes takes points lo + r + k G,
+// U at a time; the (at most one per lane) leftover point goes through the U = 1 instantiation.
+// The point values are added in fp32 over up to 4 trips (4 U points) and then into the float64 sum: one F2F + DADD per 4
+// trips instead of per trip (F2F issues on the XU pipe, which the MUFU ops of these kernels already load the most).
+template <class N, int G, int U, class HEAD>
+__device__ __forceinline__ void eval_segment(const EvalCtx& c, int rs, int lo, int hi, const float2 (&w)[N::NS], float2 (&g)[N::NS],
                                              double& lp, int lane) {
-    constexpr int U = OCBNN_POINT_UNROLL;
-    for (int j = lo + lane; j < hi; j += U * G) {
-        const float* rec[U];
-        float live[U];
+    int j = lo + lane;
+    float vacc = 0.f;
+    while (j + (U - 1) * G < hi) {
+#pragma unroll 1
+        for (int trip = 0; trip < 4 && j + (U - 1) * G < hi; ++trip, j += U * G) {
+            const float* rec[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const bool ok = j + u * G < hi;
-            rec[u] = c.tab + (ok ? j + u * G : j) * rs;
-            live[u] = ok ? 1.f : 0.f;
+            for (int u = 0; u < U; ++u) rec[u] = c.tab + (j + u * G) * rs;
+            point_eval<N, HEAD, U>(w, g, vacc, rec, c.fc);
         }
-        point_eval<N, KIND, U, WV>(w, g, lp, rec, live, c.fc);
+        lp += (double)vacc;
+        vacc = 0.f;
     }
+    if (U > 1) {
+        for (; j < hi; j += G) {
+            const float* rec[1] = {c.tab + j * rs};
+            point_eval<N, HEAD, 1>(w, g, vacc, rec, c.fc);
+        }
+    }
+    lp += (double)vacc;
 }
 
-// log posterior value and gradient at w.  Block-uniform control flow (contains __syncthreads when the point set
-// does not fit one tile or `restage` is set).  On return every lane of the group holds the full g and lp.
-template <class N, int G, class WV>
-__device__ __forceinline__ void evaluate(const EvalArgs& a, const EvalCtx& c, bool restage, const WV& w, float2 (&g)[N::NS],
+// log posterior value and gradient at the weights behind the view `q`.  Block-uniform control flow (contains
+// __syncthreads when the point set does not fit one tile or `restage` is set).  On return every lane of the group holds
+// the full g and lp.
+template <class N, int G, int U, class QV>
+__device__ __forceinline__ void evaluate(const EvalArgs& a, const EvalCtx& c, bool restage, const QV& q, float2 (&g)[N::NS],
                                          float& lp_out, int lane) {
+    float2 w[N::NS];                                  // evaluation copy: W1 and b1 in scaled units (act_in_scale)
 #pragma unroll
-    for (int s = 0; s < N::NS; ++s) g[s] = f2(0.f);
+    for (int s = 0; s < N::NS; ++s) {
+        const float2 v = q[s];
+        w[s] = (s < N::SW2 && act_in_scale<N::ACT>() != 1.f) ? __fmul2_rn(v, f2(act_in_scale<N::ACT>())) : v;
+        g[s] = f2(0.f);
+    }
     double lp = 0.0;
     const bool multi = c.npts > c.tile_cap;
     for (int begin = 0; begin < c.npts; begin += c.tile_cap) {
@@ -477,15 +577,18 @@ __device__ __forceinline__ void evaluate(const EvalArgs& a, const EvalCtx& c, bo
             seg_lo = c.seg_end[sg];
             if (lo >= hi) continue;
             if (sg == 0) {
-                if (a.lik_head == OCBNN_HEAD_LIK_GAUSS) eval_segment<N, G, OCBNN_HEAD_LIK_GAUSS, WV>(c, a.rs, lo, hi, w, g, lp, lane);
-                else if (a.lik_head == OCBNN_HEAD_LIK_SOFTMAX) eval_segment<N, G, OCBNN_HEAD_LIK_SOFTMAX, WV>(c, a.rs, lo, hi, w, g, lp, lane);
-                else eval_segment<N, G, OCBNN_HEAD_LIK_BERNOULLI, WV>(c, a.rs, lo, hi, w, g, lp, lane);
+                if (a.lik_head == OCBNN_HEAD_LIK_GAUSS) eval_segment<N, G, U, HeadEach<OCBNN_HEAD_LIK_GAUSS>>(c, a.rs, lo, hi, w, g, lp, lane);
+                else if (a.lik_head == OCBNN_HEAD_LIK_SOFTMAX) eval_segment<N, G, U, HeadEach<OCBNN_HEAD_LIK_SOFTMAX>>(c, a.rs, lo, hi, w, g, lp, lane);
+                else eval_segment<N, G, U, HeadEach<OCBNN_HEAD_LIK_BERNOULLI>>(c, a.rs, lo, hi, w, g, lp, lane);
             } else if (sg == 1) {
-                eval_segment<N, G, OCBNN_HEAD_POS_GAUSS, WV>(c, a.rs, lo, hi, w, g, lp, lane);
+                eval_segment<N, G, U, HeadEach<OCBNN_HEAD_POS_GAUSS>>(c, a.rs, lo, hi, w, g, lp, lane);
             } else if (sg == 2) {
-                eval_segment<N, G, OCBNN_HEAD_NEG_EXP, WV>(c, a.rs, lo, hi, w, g, lp, lane);
+                if (a.neg_n1 == 2 && a.neg_n2 == 0) eval_segment<N, G, U, HeadNegFixed<2, 0>>(c, a.rs, lo, hi, w, g, lp, lane);
+                else if (a.neg_n1 == 0 && a.neg_n2 == 1) eval_segment<N, G, U, HeadNegFixed<0, 1>>(c, a.rs, lo, hi, w, g, lp, lane);
+                else if (a.neg_n1 == 1 && a.neg_n2 == 0) eval_segment<N, G, U, HeadNegFixed<1, 0>>(c, a.rs, lo, hi, w, g, lp, lane);
+                else eval_segment<N, G, U, HeadEach<OCBNN_HEAD_NEG_EXP>>(c, a.rs, lo, hi, w, g, lp, lane);
             } else {
-                eval_segment<N, G, OCBNN_HEAD_DIRICHLET, WV>(c, a.rs, lo, hi, w, g, lp, lane);
+                eval_segment<N, G, U, HeadEach<OCBNN_HEAD_DIRICHLET>>(c, a.rs, lo, hi, w, g, lp, lane);
             }
         }
     }
@@ -500,21 +603,36 @@ __device__ __forceinline__ void evaluate(const EvalArgs& a, const EvalCtx& c, bo
             lp += __shfl_xor_sync(0xffffffffu, lp, off);
         }
     }
-    // Gaussian prior over the weights (isotropic, or the AOCP diagonal Gaussian): base.py:106-133.
-    // Padding slots have 1/var = 0 and are masked so that they never move.
-    double pr = 0.0;
+    if (use_moments<N>()) {      // (A0, A1, A2) in the (W2, b1, W1) slots -> sum_p df z' a [x] (see point_eval); W2 slot already final
+#pragma unroll
+        for (int hp = 0; hp < N::HP; ++hp) {
+            const float2 A0 = g[N::SW2 + hp], A1 = g[N::SB1 + hp], A2 = g[N::SW1 + hp];
+            g[N::SB1 + hp] = __ffma2_rn(w[N::SW1 + hp], A1, __fmul2_rn(w[N::SB1 + hp], A0));
+            g[N::SW1 + hp] = __ffma2_rn(w[N::SW1 + hp], A2, __fmul2_rn(w[N::SB1 + hp], A1));
+        }
+    }
+    // Gaussian prior over the weights (isotropic, or the AOCP diagonal Gaussian): base.py:106-133, added to the rescaled
+    // data gradient.  Padding slots have 1/var = 0 and are masked so that they never move.
+    float pr = 0.f;              // fp32 like the reference's Normal.log_prob(...).sum(); added once to the float64 value
 #pragma unroll
     for (int s = 0; s < N::NS; ++s) {
         const float4 mv = c.pri[s];
-        const float2 diff = __fadd2_rn(w[s], make_float2(-mv.x, -mv.y));
+        const float2 diff = __fadd2_rn(q[s], make_float2(-mv.x, -mv.y));
         const float2 t = __fmul2_rn(diff, make_float2(mv.z, mv.w));
-        g[s] = __fadd2_rn(g[s], make_float2(-t.x, -t.y));
+        if (s < N::SW2 && N::SK == 1) {               // accumulated without the w2 factor (point_eval)
+            const float2 sc = __fmul2_rn(q[N::SW2 + (s % N::HP)], f2(act_grad_scale<N::ACT>()));
+            g[s] = __ffma2_rn(g[s], sc, make_float2(-t.x, -t.y));
+        } else if (s < N::SW2 && act_grad_scale<N::ACT>() != 1.f) {
+            g[s] = __ffma2_rn(g[s], f2(act_grad_scale<N::ACT>()), make_float2(-t.x, -t.y));
+        } else {
+            g[s] = __fadd2_rn(g[s], make_float2(-t.x, -t.y));
+        }
         const float2 e = __fmul2_rn(diff, t);
-        pr += (double)e.x + (double)e.y;
+        pr += e.x + e.y;
         if (N::cidx(s, 0) < 0) g[s].x = 0.f;
         if (N::cidx(s, 1) < 0) g[s].y = 0.f;
     }
-    lp += c.lp_const - 0.5 * pr;
+    lp += c.lp_const - 0.5 * (double)pr;
     lp_out = (float)lp;
 }
 

@@ -32,7 +32,10 @@ def t2d(a, dtype=torch.float32):
 
 def check(x, ref, x32, x64, what, floor=TOL):
     cond = rel_err(x32, x64)
-    tol = np.maximum(floor, 4 * cond)
+    # against the reference: 1e-5 wherever fp32 is well conditioned (cond = fp32-vs-float64 oracle gap below 2.5e-6) and the
+    # reference's own fp32 result is within that of the float64 truth; on ill-conditioned rows the bound is the triangle
+    # inequality |engine - ref| <= |engine - f64| + |ref - f64| with the engine's side held to 1e-5 + 2 cond on the next line
+    tol = np.maximum(np.maximum(floor, 4 * cond), rel_err(ref, x64) + floor + 2 * cond)
     e_ref, e_64 = rel_err(x, ref), rel_err(x, x64)
     assert (e_64 <= floor + 2 * cond).all(), (what, "engine vs float64 oracle", e_64, cond)
     assert (e_ref <= tol).all(), (what, "engine vs reference", e_ref, tol)
