@@ -296,8 +296,7 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        acc_cnt, smp = m.hmc_run(qd, K, True, collect_every=1, chunk=1)
-        samples_h.copy_(smp, non_blocking=True)
+        acc_cnt, smp = m.hmc_run(qd, K, True, collect_every=1, chunk=1, samples_host=samples_h)
         acc_host = acc_cnt.cpu()
         e1.record()
         barrier()
@@ -307,7 +306,7 @@ def main():
             torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
         e2e = {"value": world * M * L * K / (float(ms2.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(M * D * 4 + M * 8), "d2h_bytes_per_step": int(M * D * 4 + M * 8 // K),
-               "path": "HMCMixin.hmc_run(collect_every=1, chunk=1): pinned-host momenta+uniforms H2D per step on a side stream, samples D2H"}
+               "path": "HMCMixin.hmc_run(collect_every=1, chunk=1, samples_host=pinned): momenta+uniforms H2D per step on a side stream, that step's samples D2H on a copy stream, accept counts D2H at the end"}
 
     if rank != 0:
         if world > 1:
@@ -333,7 +332,7 @@ def main():
     # The binding pipe is the one with the larger fraction of its measured peak: MUFU (exp2/rcp, 16 op/clk/SM) vs fp32 FMA.
     mufu_frac, fp32_frac = ach_mufu / peak_mufu, ach_flops / peak_ffma2
     mufu_bound = mufu_frac >= fp32_frac
-    roofline = {"bound": "mufu" if mufu_bound else "fp32-simt", "kernel": "k_hmc_small_sm" if True else "k_hmc_small",
+    roofline = {"bound": "mufu" if mufu_bound else "fp32-simt", "kernel": "k_hmc_small",
                 "achieved": (ach_mufu if mufu_bound else ach_flops) / 1e12, "peak": (peak_mufu if mufu_bound else peak_ffma2) / 1e12,
                 "unit": "Top/s" if mufu_bound else "TFLOP/s", "frac": mufu_frac if mufu_bound else fp32_frac, "traffic": traffic,
                 "peak_source": "instruction-pipe probes measured in this run (ocbnn_probe_peak: MUFU.EX2, packed FFMA2); MEASURED_PEAKS.json has HBM and bf16 tensor peaks only",

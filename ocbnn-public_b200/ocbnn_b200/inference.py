@@ -78,11 +78,13 @@ class HMCMixin:
             q[c] = prev[c] if prev is not None and prev.shape[0] > c else Normal(0, self.sigma_w).sample(torch.Size([self.nweights]))
         return q.to(dev).contiguous()
 
-    def hmc_run(self, q, n_it, with_data, collect_every=0, chunk=None):
+    def hmc_run(self, q, n_it, with_data, collect_every=0, chunk=None, samples_host=None):
         """n_it iterations from state q (M,D, device; updated in place).  Returns (accepts (M,), samples or None).
 
         The iterations run in chunks (one kernel launch each).  The momenta / uniforms of chunk k+1 are drawn and uploaded
-        on a side stream while the kernel of chunk k runs, so host RNG and H2D copies overlap the compute."""
+        on a side stream while the kernel of chunk k runs, so host RNG and H2D copies overlap the compute.  With
+        `samples_host` (pinned CPU tensor (n_it // collect_every, M, D)) the samples of every chunk are copied to the host on
+        a third stream while the next chunk runs; the copies are complete when this method returns."""
         prob = self.engine_problem()
         M = q.shape[0]
         acc_total = torch.zeros(M, dtype=torch.int64, device=q.device)
@@ -97,6 +99,11 @@ class HMCMixin:
             side = self._hmc_side_stream = torch.cuda.Stream(device=q.device)
 
         side.wait_stream(main)                           # everything queued so far (q, the problem upload) is visible to the side stream
+        d2h = None
+        if samples_host is not None and nsamp:
+            d2h = getattr(self, "_hmc_d2h_stream", None)
+            if d2h is None or d2h.device != q.device:
+                d2h = self._hmc_d2h_stream = torch.cuda.Stream(device=q.device)
 
         def draw(n):
             with torch.cuda.stream(side):
@@ -118,13 +125,21 @@ class HMCMixin:
             acc, _, flags = prob.hmc_iterate(q, p0, u, self.hmc_epsilon, self.hmc_l, with_data,
                                              bool(getattr(self, "restore_on_reject", False)), samples=sl, thin=collect_every,
                                              lanes=int(getattr(self, "lanes", 0) or 0))
+            if d2h is not None and sl is not None and sl.shape[0]:
+                d2h.wait_stream(main)
+                with torch.cuda.stream(d2h):             # overlaps the next chunk's kernel
+                    samples_host[done // collect_every:(done + n) // collect_every].copy_(sl, non_blocking=True)
             done += n
             if done < n_it:
                 nxt = draw(min(chunk, n_it - done))      # overlaps the kernel just launched
             acc_total += acc.sum(dim=0)
             nan_seen = torch.maximum(nan_seen, flags.max())
+        if d2h is not None:
+            main.wait_stream(d2h)
         if int(nan_seen) != 0:                           # one host sync per run (the reference checks every iteration)
             _raise_nan(self)
+        if d2h is not None:
+            d2h.synchronize()
         return acc_total, samples
 
     def infer(self, verbose=True, with_data=True):

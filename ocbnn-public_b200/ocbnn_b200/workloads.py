@@ -150,6 +150,6 @@ def hmc_step_work(model, with_data=True):
     mufu = npts * hidden if model.activation == "rbf" else 0
     if cp is not None and cp.cx.shape[0]:
         neg = int((cp.ckind == 1).sum())
-        mufu += neg * 6                                   # 2 gaps x (2 exp + 1 rcp)
+        mufu += neg * 5                                   # 2 Phi terms x 2 exp + one reciprocal for the pair (phi_fast2_1r)
         mufu += int((cp.ckind == 3).sum()) * (sizes[-1] + 2)
     return npts * flops_per_point(sizes) + 8 * D, mufu, 12.0 * D / float(model.hmc_l)
