@@ -166,9 +166,15 @@ OCBNN_API int ocbnn_svgd_hist_pass(const float *x, int64_t n, int64_t d, int64_t
 OCBNN_API int ocbnn_svgd_hist_pass_prepared(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t pass, uint32_t *hist,
                                             uint64_t *select_state, void *workspace, void *stream);
 OCBNN_API int ocbnn_svgd_select_update(int32_t pass, uint32_t *hist, uint64_t *select_state, int64_t n, float *out_h, void *stream);
-/* single-GPU convenience: prepare (tensor path) + all three passes */
+/* single-GPU convenience: prepare (tensor path) + the select.  With all rows on one GPU the tensor path finds the same exact
+ * median in three launches (sampled bracket, one counting/compaction pass over the distances, one-CTA select among the ~2.5 %
+ * candidates; in-kernel fallback to the radix select if the bracket misses).  On return the first 4 x u64 of the select state
+ * hold (bracket hit, candidates, values below the bracket, exact zeros). */
 OCBNN_API int ocbnn_svgd_bandwidth(const float *x, int64_t n, int64_t d, float *out_h, int32_t use_tensor, void *workspace,
                                    int64_t workspace_bytes, void *stream);
+/* median-select algorithm of ocbnn_svgd_bandwidth's tensor path: 1 bracket select (default), 0 the 3-pass radix select,
+ * 2 bracket select with a sabotaged bracket (exercises the fallback; tests).  mode < 0 queries.  Returns the previous mode. */
+OCBNN_API int ocbnn_svgd_select_mode(int32_t mode);
 
 /* K3b — SVGD update direction phi_i = (1/n) sum_j [K_ji g_j + grad_{x_j} K_ji] (inference.py:219-259) for rows
  * [row_begin, row_begin + n_rows) of the (gathered) particle matrix x (n x D) with gradients g (n x D).

@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     objs = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in srcs]
-    if jobs or not os.path.exists(LIB):
+    if jobs or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lcuda"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:

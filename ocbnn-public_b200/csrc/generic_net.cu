@@ -8,6 +8,7 @@
 // tile are one LDS.128 and consecutive feature rows fall in distinct banks.
 // Replaces forward (bnn/base.py:89-104) + autograd for the application-sized nets; fp32 SIMT on purpose:
 // the parity bar is 1e-5 and tcgen05 has no fp32 MMA.
+#include <cstdlib>
 #include "heads.cuh"
 #include "small_net.cuh"
 
@@ -392,19 +393,30 @@ k_forward_generic(GenLayout L, const float* __restrict__ w, long long m, const f
     }
 }
 
-// Points per tile: resident CTAs per SM matter more than tile size (measured on W6: 32-point tiles with 3 CTAs/SM beat 64-point
-// tiles with 1-2 CTAs/SM by 20 %), so prefer the largest tile that still leaves >= 3 CTAs per SM, then >= 2, then whatever fits.
+// Points per tile vs resident CTAs per SM.  Measured on B200: on W6 (credit, D = 3202) 32-point tiles with 3 CTAs/SM beat
+// 64-point tiles with 1-2 CTAs/SM by 20 %; on W7 (recid, D = 11201, weights + gradient = 95 KB) trading the tile down to 4-8
+// points to squeeze a second CTA in halves the throughput (the 4x4 register tiles lose their reuse).  So: tiles of >= 16 points
+// first (most resident CTAs wins), smaller tiles only when nothing else fits.
 static int pick_tp(const Problem& p, GenLayout& L, bool with_grad) {
     auto need_for = [&](int tp) {
         L = make_layout(p, tp);
         return with_grad ? gen_smem_bytes(L, p.rs) : sizeof(float) * ((size_t)L.wtot + (size_t)L.rows_tot * L.ts);
     };
     const long long cap = p.max_smem_optin;
+    const int force = [] { const char* e = getenv("OCBNN_GEN_TP"); return e ? atoi(e) : 0; }();
+    if (force > 0) {
+        const size_t need = need_for(force);
+        return (long long)need <= cap ? (int)need : -1;
+    }
     for (int want : {3, 2, 1})
-        for (int tp : {32, 16, 8, 4}) {
+        for (int tp : {32, 16}) {
             const size_t need = need_for(tp);
             if ((long long)need <= cap && cap / (long long)(need + 1024) >= want) return (int)need;
         }
+    for (int tp : {8, 4}) {
+        const size_t need = need_for(tp);
+        if ((long long)need <= cap) return (int)need;
+    }
     return -1;
 }
 

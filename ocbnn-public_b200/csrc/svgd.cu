@@ -1,3 +1,5 @@
+#include <atomic>
+#include <cstdlib>
 // svgd.cu — SVGD kernels, exact fp32 SIMT path.
 //   K3a  median-heuristic bandwidth: exact LOWER median of ||x_i - x_j + 1e-6||, i<j, zeros dropped, by a
 //        3-pass radix select on the fp32 bit patterns (11+11+10 bits); h = med^2 / ln n   (inference.py:208-217)
@@ -364,6 +366,7 @@ int tc_svgd_prepare(const float* x, long long n, long long d, long long row_begi
 int tc_svgd_hist(long long n, long long d, long long row_begin, long long n_rows, int pass, unsigned* hist, const unsigned long long* state, void* ws,
                  cudaStream_t st);
 int tc_svgd_phi(const float* g, const float* h, long long n, long long d, long long row_begin, long long n_rows, float* phi, void* ws, cudaStream_t st);
+int tc_svgd_select_fast(long long n, long long d, void* ws, float* out_h, int mode, unsigned long long* dbg, cudaStream_t st);
 } }
 
 // use_tensor: 0 exact fp32 SIMT kernels ; 1 tcgen05 path ; -1 choose (tensor path from 1024 particles up)
@@ -395,6 +398,15 @@ extern "C" OCBNN_API int ocbnn_svgd_hist_pass_prepared(int64_t n, int64_t d, int
     return tc::tc_svgd_hist(n, d, row_begin, n_rows, pass, hist, reinterpret_cast<const unsigned long long*>(select_state), workspace, st);
 }
 
+// 1 fast (default), 0 legacy, 2 fast with a sabotaged bracket; initial value from OCBNN_SVGD_SELECT = fast | legacy | fallback
+static std::atomic<int> g_select_mode{[] { const char* e = getenv("OCBNN_SVGD_SELECT"); return !e ? 1 : e[0] == 'l' ? 0 : (e[0] == 'f' && e[1] == 'a' && e[2] == 'l') ? 2 : 1; }()};
+// sets the median-select algorithm of ocbnn_svgd_bandwidth's single-rank tensor path (mode < 0: query only); returns the previous mode
+extern "C" OCBNN_API int ocbnn_svgd_select_mode(int32_t mode) {
+    const int prev = g_select_mode.load();
+    if (mode >= 0 && mode <= 2) g_select_mode.store(mode);
+    return prev;
+}
+
 extern "C" OCBNN_API int ocbnn_svgd_bandwidth(const float* x, int64_t n, int64_t d, float* out_h, int32_t use_tensor, void* workspace,
                                               int64_t workspace_bytes, void* stream) {
     OCBNN_REQUIRE(workspace && workspace_bytes >= ocbnn_svgd_workspace_bytes(n, d, n, use_tensor), OCBNN_EINVAL,
@@ -405,6 +417,14 @@ extern "C" OCBNN_API int ocbnn_svgd_bandwidth(const float* x, int64_t n, int64_t
     const bool tensor = want_tensor(use_tensor, n);
     int rc;
     bool hist0_done = false;
+    // OCBNN_SVGD_SELECT: fast (default; bracket + count + compact, all rows are on this rank) | legacy (3 radix-select histogram
+    // passes, the algorithm the multi-GPU path all-reduces) | fallback (fast path with a sabotaged bracket: tests the in-kernel fallback)
+    const int sel_mode = g_select_mode.load();
+    if (tensor && sel_mode != 0 && n <= 2000000000ll) {
+        if ((rc = tc::tc_svgd_prepare(x, n, d, 0, n, tcws, workspace_bytes - (3 * kBins * sizeof(uint32_t) + 256), nullptr, nullptr, (cudaStream_t)stream)))
+            return rc;
+        return tc::tc_svgd_select_fast(n, d, tcws, out_h, sel_mode, reinterpret_cast<unsigned long long*>(state), (cudaStream_t)stream);
+    }
     if (tensor) {                       // the pass-0 histogram rides on the distance pass when the direct kernel forms the distances
         k_zero_u32<<<(3 * kBins + 255) / 256, 256, 0, (cudaStream_t)stream>>>(hist, 3 * kBins);
         OCBNN_LAUNCH_CHECK();

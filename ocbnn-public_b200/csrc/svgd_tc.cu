@@ -4,6 +4,7 @@
 // run on tcgen05 with TMA-staged operands in 3xTF32 precision (tc_gemm.cuh); Xc = X - mean(X) (phi is translation
 // invariant; centring removes the cancellation in the Gram form of the distance).  The exact fp32 SIMT arm in svgd.cu is
 // the parity reference of this path.  Also exports the GEMM building block itself for testing.
+#include <cstdlib>
 #include <cudaTypedefs.h>
 #include "tc_gemm.cuh"
 
@@ -112,12 +113,16 @@ k_split_tf32(const float* __restrict__ x, long long rows, long long cols, long l
 // =========================================================================================================================
 // SVGD tensor pipeline.  Workspace layout (floats unless noted), n4 = n rounded up to 4, dp = D rounded up to 32:
 //   hdr (256 B) | mean[dp] | r[n] | s[n] | xc_hi[n x dp] | xc_lo[n x dp] | d2[n_rows x n4] | k_hi, k_lo[n_rows x n4] |
-//   vt_hi, vt_lo[2dp x n4] | rowsum[n_rows] | o[splits x n_rows x 2dp]
+//   vt_hi, vt_lo[2dp x n4] | rowsum[n_rows] | o[splits x n_rows x 2dp] | select header | select candidates[n^2/32]
 // =========================================================================================================================
 struct TcWs {
     long long n, d, n4, dp, n_rows, row_begin;
     int splits, bn;
     float *mean, *r, *s, *xc_hi, *xc_lo, *d2, *k_hi, *k_lo, *vt_hi, *vt_lo, *rowsum, *o;
+    float *cand, *list2, *samples;   // bracket select: candidates, short list (cand_cap floats each), pair sample
+    unsigned* ghist;                  // bracket select: linear histogram over the bracket
+    unsigned long long* sel; // bracket-select header: see SelHdr
+    long long cand_cap;
     unsigned* hist;
     unsigned long long* state;
     long long bytes;
@@ -153,6 +158,12 @@ static TcWs carve(void* workspace, long long n, long long d, long long row_begin
     w.vt_lo = take(2 * w.dp * w.n4);
     w.rowsum = take(n_rows);
     w.o = take((long long)w.splits * n_rows * 2 * w.dp);
+    w.sel = reinterpret_cast<unsigned long long*>(take(64));
+    w.cand_cap = n_rows == n ? (n * n / 32 > (1 << 16) ? n * n / 32 : (1 << 16)) : 0;
+    w.cand = take(w.cand_cap);
+    w.list2 = take(w.cand_cap);
+    w.samples = take(n_rows == n ? 65536 : 0);
+    w.ghist = reinterpret_cast<unsigned*>(take(n_rows == n ? 4096 : 0));
     w.bytes = p - reinterpret_cast<char*>(workspace);
     return w;
 }
@@ -303,6 +314,274 @@ k_hist_d2(const float* __restrict__ d2, const float* __restrict__ ssum, long lon
         if (sh[b]) atomicAdd(&hist[pass * 2048 + b], sh[b]);
 }
 
+// ---- K3a, single-rank fast path: exact lower median by bracket + count + compact ---------------------------------------
+// The radix-select histograms above pay for contention: the n(n-1)/2 distances of a particle cloud cluster in a handful of
+// top-bit bins.  With all rows on one GPU the median is found without a contended histogram:
+//   k_sel_sample   65536 pseudo-random pairs (i < j), their distances read from d2;
+//   k_sel_bracket  one CTA histograms the sample linearly between its min and max and takes the bin edges of the sample
+//                  quantiles 0.5 -/+ 0.011 (5.6 sigma of the sample-rank error) as a bracket [lo, hi] that holds the true
+//                  median and ~2.5 % of all distances;
+//   k_sel_count    one pass over the upper triangle of d2: counts exact zeros and values below lo in registers, appends the
+//                  values inside the bracket to a candidate list (warp-private shared-memory staging, one global atomic per
+//                  ~200 candidates) and counts them in a 4096-bin LINEAR histogram over the bracket (uniform occupancy, so
+//                  the global atomics do not collide);
+//   k_sel_gather   every CTA locates the histogram bin that holds the wanted rank and the candidates of that bin are
+//                  appended to a second, short list;
+//   k_sel_final    one CTA radix-selects (11 + 11 + 10 bits) inside the short list and emits h = med^2 / ln n.  If the
+//                  bracket missed (never observed; probability ~1e-8 per call) or a list overflowed, the same CTA falls
+//                  back to the 3-pass radix select over d2.  Exact either way.
+struct SelHdr {                 // 64 bytes in the workspace
+    float lo, hi;
+    unsigned ncand, overflow;
+    unsigned long long zeros, below;
+    unsigned n2, bin;           // short list length, hit bin
+    unsigned long long resid;   // rank inside the hit bin
+    unsigned long long pad[2];
+};
+
+__device__ __forceinline__ float pair_dist(const float* __restrict__ d2, const float* __restrict__ ssum, long long n4, int d, long long i, long long j) {
+    const float eps = 1e-6f, deps2 = (float)d * 1e-12f;
+    return sqrtf(fmaxf(d2[i * n4 + j] + 2.f * eps * (ssum[i] - ssum[j]) + deps2, 0.f));
+}
+__device__ __forceinline__ unsigned mix32(unsigned x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+constexpr int kSelSamples = 65536, kSelBins = 4096;
+
+__global__ void __launch_bounds__(256)
+k_sel_sample(const float* __restrict__ d2, const float* __restrict__ ssum, long long n, long long n4, int d, float* __restrict__ samples) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kSelSamples) return;
+    const unsigned a = mix32((unsigned)idx * 2u + 0x9e3779b9u), b = mix32(a ^ 0x85ebca6bu);
+    long long i = (long long)(a % (unsigned)n), j = (long long)(b % (unsigned)n);
+    if (i == j) j = (j + 1) % n;
+    if (i > j) { const long long tmp = i; i = j; j = tmp; }
+    samples[idx] = pair_dist(d2, ssum, n4, d, i, j);
+}
+
+// block-wide: index of the bin holding 0-based rank `rank` in bins[0..NT*BPT) (shared or global), residual rank out.
+// NT threads, BPT consecutive bins per thread.  Contains __syncthreads.
+template <int NT, int BPT>
+__device__ __forceinline__ int block_find_bin(const unsigned* bins, unsigned long long rank, unsigned long long* resid, unsigned* wsum, int* s_bin,
+                                              unsigned long long* s_res) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    unsigned loc[BPT], mine = 0;
+#pragma unroll
+    for (int k = 0; k < BPT; ++k) { loc[k] = bins[t * BPT + k]; mine += loc[k]; }
+    unsigned incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += y;
+    }
+    __syncthreads();
+    if (lane == 31) wsum[warp] = incl;
+    if (t == 0) { *s_bin = NT * BPT - 1; *s_res = 0; }
+    __syncthreads();
+    unsigned long long cum = 0;
+    for (int w = 0; w < warp; ++w) cum += wsum[w];
+    cum += incl - mine;
+#pragma unroll
+    for (int k = 0; k < BPT; ++k) {
+        if (loc[k] && rank >= cum && rank < cum + loc[k]) { *s_bin = t * BPT + k; *s_res = rank - cum; }
+        cum += loc[k];
+    }
+    __syncthreads();
+    *resid = *s_res;
+    return *s_bin;
+}
+
+__global__ void __launch_bounds__(1024)
+k_sel_bracket(const float* __restrict__ samples, SelHdr* __restrict__ hdr, unsigned* __restrict__ ghist, int sabotage) {
+    __shared__ unsigned sh[kSelBins];
+    __shared__ float red_min[32], red_max[32];
+    __shared__ unsigned red_cnt[32];
+    __shared__ unsigned wsum[32];
+    __shared__ int s_bin;
+    __shared__ unsigned long long s_res;
+    constexpr int PT = kSelSamples / 1024;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < kSelBins; i += 1024) { sh[i] = 0u; ghist[i] = 0u; }
+    float v[PT];
+    float mn = INFINITY, mx = 0.f;
+    unsigned cnt = 0;
+#pragma unroll
+    for (int k = 0; k < PT; ++k) {
+        const float x = samples[k * 1024 + t];
+        v[k] = x;
+        if (x != 0.f) { mn = fminf(mn, x); mx = fmaxf(mx, x); ++cnt; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    }
+    if (lane == 0) { red_min[warp] = mn; red_max[warp] = mx; red_cnt[warp] = cnt; }
+    __syncthreads();
+    mn = INFINITY; mx = 0.f; cnt = 0;
+    for (int w = 0; w < 32; ++w) { mn = fminf(mn, red_min[w]); mx = fmaxf(mx, red_max[w]); cnt += red_cnt[w]; }
+    const float scale = mx > mn ? (float)kSelBins / (mx - mn) : 0.f;
+#pragma unroll
+    for (int k = 0; k < PT; ++k)
+        if (v[k] != 0.f) atomicAdd(&sh[min(kSelBins - 1, (int)((v[k] - mn) * scale))], 1u);
+    __syncthreads();
+    const float delta = 0.011f, width = scale > 0.f ? 1.f / scale : 0.f;
+    const unsigned r_lo = (unsigned)fmaxf(0.f, floorf((0.5f - delta) * (float)cnt)), r_hi = min(cnt ? cnt - 1 : 0u, (unsigned)ceilf((0.5f + delta) * (float)cnt));
+    unsigned long long dummy;
+    const int b_lo = block_find_bin<1024, 4>(sh, r_lo, &dummy, wsum, &s_bin, &s_res);
+    const int b_hi = block_find_bin<1024, 4>(sh, r_hi, &dummy, wsum, &s_bin, &s_res);
+    if (t == 0) {
+        float lo = fmaxf(mn + ((float)b_lo - 1.f) * width, 0.f), hi = mn + ((float)b_hi + 2.f) * width;      // one bin of margin each side
+        if (cnt == 0) { lo = 0.f; hi = 0.f; }
+        if (sabotage) { lo = mx * 4.f + 1.f; hi = mx * 8.f + 2.f; }
+        hdr->lo = lo; hdr->hi = hi;
+        hdr->ncand = 0u; hdr->overflow = 0u; hdr->zeros = 0ull; hdr->below = 0ull; hdr->n2 = 0u; hdr->bin = 0u; hdr->resid = 0ull;
+    }
+}
+
+__device__ __forceinline__ int sel_lbin(float v, float lo, float scale) { return min(kSelBins - 1, max(0, (int)((v - lo) * scale))); }
+
+__global__ void __launch_bounds__(256)
+k_sel_count(const float* __restrict__ d2, const float* __restrict__ ssum, long long n, long long n4, int d, SelHdr* __restrict__ hdr,
+            float* __restrict__ cand, long long cand_cap, unsigned* __restrict__ ghist) {
+    __shared__ float stage[8][256];
+    __shared__ unsigned long long red[2][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float lo = hdr->lo, hi = hdr->hi;
+    const float scale = hi > lo ? (float)kSelBins / (hi - lo) : 0.f;
+    const float eps = 1e-6f, deps2 = (float)d * 1e-12f;
+    unsigned zeros = 0, below = 0, staged = 0;      // staged: warp-uniform
+    auto flush = [&]() {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&hdr->ncand, staged);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((long long)base + staged > cand_cap) { if (lane == 0) hdr->overflow = 1u; }
+        else for (unsigned k = lane; k < staged; k += 32) cand[base + k] = stage[warp][k];
+        __syncwarp();
+        staged = 0;
+    };
+    for (long long i = blockIdx.x; i < n; i += gridDim.x) {
+        const float si = ssum[i];
+        for (long long j0 = (i + 1) / 256 * 256; j0 < n; j0 += 256) {
+            const long long j = j0 + threadIdx.x;
+            bool is_c = false;
+            float v = 0.f;
+            if (j > i && j < n) {
+                v = sqrtf(fmaxf(d2[i * n4 + j] + 2.f * eps * (si - ssum[j]) + deps2, 0.f));
+                if (v == 0.f) ++zeros;
+                else if (v < lo) ++below;
+                else is_c = v <= hi;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, is_c);
+            if (m) {
+                if (is_c) {
+                    stage[warp][staged + __popc(m & ((1u << lane) - 1u))] = v;
+                    atomicAdd(&ghist[sel_lbin(v, lo, scale)], 1u);
+                }
+                staged += __popc(m);
+                __syncwarp();
+                if (staged > 256 - 32) flush();
+            }
+        }
+    }
+    if (staged) flush();
+    unsigned long long z = zeros, b = below;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        z += __shfl_xor_sync(0xffffffffu, z, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+    }
+    if (lane == 0) { red[0][warp] = z; red[1][warp] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        z = 0; b = 0;
+        for (int w = 0; w < 8; ++w) { z += red[0][w]; b += red[1][w]; }
+        if (z) atomicAdd(&hdr->zeros, z);
+        if (b) atomicAdd(&hdr->below, b);
+    }
+}
+
+__device__ __forceinline__ bool sel_ok(const SelHdr* hdr, long long n, unsigned long long* rank_out) {
+    const unsigned long long pairs = (unsigned long long)n * (unsigned long long)(n - 1) / 2ull;
+    const unsigned long long nz = pairs - hdr->zeros;
+    const unsigned long long rank = nz ? (nz - 1) / 2 : 0;                      // LOWER median (torch.median)
+    *rank_out = rank;
+    return !hdr->overflow && nz > 0 && rank >= hdr->below && rank < hdr->below + hdr->ncand;
+}
+
+__global__ void __launch_bounds__(256)
+k_sel_gather(long long n, SelHdr* __restrict__ hdr, const unsigned* __restrict__ ghist, const float* __restrict__ cand, float* __restrict__ list2,
+             long long cap2) {
+    __shared__ unsigned wsum[8];
+    __shared__ int s_bin;
+    __shared__ unsigned long long s_res;
+    unsigned long long rank, resid;
+    if (!sel_ok(hdr, n, &rank)) return;                 // uniform over the grid: k_sel_final takes the fallback
+    const int b1 = block_find_bin<256, 16>(ghist, rank - hdr->below, &resid, wsum, &s_bin, &s_res);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { hdr->bin = (unsigned)b1; hdr->resid = resid; }
+    const float lo = hdr->lo, hi = hdr->hi;
+    const float scale = hi > lo ? (float)kSelBins / (hi - lo) : 0.f;
+    const unsigned ncand = hdr->ncand;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += gridDim.x * blockDim.x) {
+        const float v = cand[i];
+        if (sel_lbin(v, lo, scale) == b1) {
+            const unsigned pos = atomicAdd(&hdr->n2, 1u);
+            if ((long long)pos < cap2) list2[pos] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_sel_final(const float* __restrict__ d2, const float* __restrict__ ssum, long long n, long long n4, int d, const SelHdr* __restrict__ hdr,
+            const float* __restrict__ list2, long long cap2, float* __restrict__ out_h, unsigned long long* __restrict__ dbg) {
+    __shared__ unsigned sh[2048];
+    __shared__ unsigned wsum[32];
+    __shared__ int s_bin;
+    __shared__ unsigned long long s_res;
+    const int t = threadIdx.x;
+    unsigned long long rank;
+    const bool ok = sel_ok(hdr, n, &rank) && (long long)hdr->n2 <= cap2;
+    const unsigned long long pairs = (unsigned long long)n * (unsigned long long)(n - 1) / 2ull;
+    float med = nanf("");                               // torch: median of an empty tensor
+    if (pairs != hdr->zeros) {
+        unsigned prefix = 0;
+        unsigned long long r = ok ? hdr->resid : rank;
+        const unsigned n2 = hdr->n2;
+        for (int pass = 0; pass < 3; ++pass) {
+            __syncthreads();
+            for (int i = t; i < 2048; i += 1024) sh[i] = 0u;
+            __syncthreads();
+            auto add = [&](unsigned bits) {
+                if (pass == 0) atomicAdd(&sh[bits >> 21], 1u);
+                else if (pass == 1) { if ((bits >> 21) == (prefix >> 21)) atomicAdd(&sh[(bits >> 10) & 2047u], 1u); }
+                else if ((bits >> 10) == (prefix >> 10)) atomicAdd(&sh[bits & 1023u], 1u);
+            };
+            if (ok) {
+                for (unsigned i = t; i < n2; i += 1024) add(__float_as_uint(list2[i]));
+            } else {
+                // fallback: radix select over the upper triangle of d2 (one CTA; never taken with a sane bracket; 32-bit bin
+                // counts, i.e. n <= 92681)
+                for (long long i = 0; i < n; ++i)
+                    for (long long j = i + 1 + t; j < n; j += 1024) {
+                        const unsigned bits = __float_as_uint(pair_dist(d2, ssum, n4, d, i, j));
+                        if (bits != 0u) add(bits);
+                    }
+            }
+            __syncthreads();
+            const int b = block_find_bin<1024, 2>(sh, r, &r, wsum, &s_bin, &s_res);
+            prefix |= pass == 0 ? ((unsigned)b << 21) : pass == 1 ? ((unsigned)b << 10) : (unsigned)b;
+        }
+        med = __uint_as_float(prefix);
+    }
+    if (t == 0) {
+        if (out_h) *out_h = __fdiv_rn(__fmul_rn(med, med), (float)log((double)n));
+        if (dbg) { dbg[0] = ok ? 1ull : 0ull; dbg[1] = hdr->ncand; dbg[2] = hdr->below; dbg[3] = hdr->zeros; }
+    }
+}
+
 // K = exp(-d2/h) split into tf32 hi/lo, row sums; one block per row
 __global__ void __launch_bounds__(256)
 k_kmat_split(const float* __restrict__ d2, const float* __restrict__ hptr, long long n, long long n4, long long n_rows, float* __restrict__ k_hi,
@@ -400,7 +679,8 @@ static int tc_prepare(const TcWs& w, const float* x, unsigned* hist0, bool* hist
     OCBNN_LAUNCH_CHECK();
     k_center_split<<<(unsigned)((w.n * 32 + 255) / 256), 256, 0, st>>>(x, w.mean, w.n, (int)w.d, (int)w.dp, w.xc_hi, w.xc_lo, w.r, w.s);
     OCBNN_LAUNCH_CHECK();
-    if (w.dp <= 64) {
+    static const bool gram_small = [] { const char* e = getenv("OCBNN_SVGD_GRAM"); return e && e[0] == 't'; }();   // experiment: tensor Gram for small D too
+    if (w.dp <= 64 && !gram_small) {
         dim3 grid((unsigned)((w.n4 + 63) / 64), (unsigned)((w.n_rows + 63) / 64));
         if (w.dp == 32) k_d2_direct<32><<<grid, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.s, w.n, w.n4, (int)w.d, w.row_begin, w.n_rows, w.d2, hist0);
         else k_d2_direct<64><<<grid, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.s, w.n, w.n4, (int)w.d, w.row_begin, w.n_rows, w.d2, hist0);
@@ -452,6 +732,24 @@ int tc_svgd_hist(long long n, long long d, long long row_begin, long long n_rows
                  cudaStream_t st) {
     TcWs w = carve(ws, n, d, row_begin, n_rows);
     k_hist_d2<<<(unsigned)(n_rows < 148 * 8 ? n_rows : 148 * 8), 256, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, row_begin, n_rows, pass, hist, state);
+    OCBNN_LAUNCH_CHECK();
+    return OCBNN_OK;
+}
+// exact lower median of the perturbed pair distances of the prepared workspace (all rows on this rank) -> h = med^2 / ln n.
+// mode 1: normal ; mode 2: sabotage the bracket (exercises the in-kernel fallback; tests only).  dbg: optional 4 x u64
+// (bracket hit, candidates, below, zeros).
+int tc_svgd_select_fast(long long n, long long d, void* ws, float* out_h, int mode, unsigned long long* dbg, cudaStream_t st) {
+    TcWs w = carve(ws, n, d, 0, n);
+    SelHdr* hdr = reinterpret_cast<SelHdr*>(w.sel);
+    k_sel_sample<<<kSelSamples / 256, 256, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, w.samples);
+    OCBNN_LAUNCH_CHECK();
+    k_sel_bracket<<<1, 1024, 0, st>>>(w.samples, hdr, w.ghist, mode == 2 ? 1 : 0);
+    OCBNN_LAUNCH_CHECK();
+    k_sel_count<<<(unsigned)(n < 148 * 8 ? n : 148 * 8), 256, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, hdr, w.cand, w.cand_cap, w.ghist);
+    OCBNN_LAUNCH_CHECK();
+    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap);
+    OCBNN_LAUNCH_CHECK();
+    k_sel_final<<<1, 1024, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, hdr, w.list2, w.cand_cap, out_h, dbg);
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }

@@ -80,6 +80,7 @@ _SIGS = {
                                        C.c_void_p, C.c_void_p]),
     "ocbnn_svgd_select_update": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ocbnn_svgd_bandwidth": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ocbnn_svgd_select_mode": (C.c_int, [C.c_int32]),
     "ocbnn_svgd_prepare": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "ocbnn_svgd_hist_pass_prepared": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p]),
@@ -289,6 +290,12 @@ def svgd_bandwidth(X, workspace, out_h=None, use_tensor=0):
     h = out_h if out_h is not None else torch.empty(1, device=X.device)
     check(lib().ocbnn_svgd_bandwidth(_ptr(X), X.shape[0], X.shape[1], _ptr(h), int(use_tensor), _ptr(workspace), workspace.numel() * 8, _stream()))
     return h
+
+
+def svgd_select_mode(mode=-1):
+    """Median-select algorithm of svgd_bandwidth's tensor path: 1 bracket select (default), 0 radix select, 2 sabotaged bracket
+    (tests the in-kernel fallback); returns the previous mode."""
+    return int(lib().ocbnn_svgd_select_mode(int(mode)))
 
 
 def svgd_prepare(X, row_begin, n_rows, workspace, use_tensor=1):

@@ -62,3 +62,35 @@ def test_svgd_epoch_tensor_vs_simt():
         assert abs(float(st_t["h"]) - float(st_s["h"])) <= 1e-5 * float(st_s["h"])
         rel = (st_t["phi"] - st_s["phi"]).norm(dim=1) / st_s["phi"].norm(dim=1)
         assert float(rel.max()) < 2e-5, float(rel.max())
+
+
+@pytest.mark.parametrize("n,D,dup", [(1500, 31, 0), (2050, 41, 0), (1100, 200, 0), (1200, 31, 300), (64, 10, 0)])
+def test_svgd_bandwidth_select_modes_agree(n, D, dup):
+    """The bracket select (default), its in-kernel fallback (sabotaged bracket) and the 3-pass radix select return the same
+    exact lower median, bit for bit; `dup` duplicated particles give exact-zero distances (dropped) and heavy ties."""
+    gen = torch.Generator().manual_seed(n * 3 + D)
+    X = torch.randn(n, D, generator=gen) * 0.8 + 0.3
+    if dup:
+        X[-dup:] = X[:dup]
+    Xd = X.cuda()
+    ws = E.svgd_workspace(n, D, Xd.device, use_tensor=1)
+    _, state = E.svgd_ws_views(ws)
+    prev = E.svgd_select_mode(-1)
+    try:
+        out = {}
+        for mode in (1, 0, 2):
+            E.svgd_select_mode(mode)
+            out[mode] = float(E.svgd_bandwidth(Xd, ws, use_tensor=1))
+            if mode == 1:
+                hit, ncand, below, zeros = [int(v) for v in state[:4].cpu()]
+                pairs = n * (n - 1) // 2
+                assert hit == 1, "the sampled bracket must contain the median"
+                assert zeros == 0          # the +1e-6 inside the norm keeps duplicated particles at distance sqrt(D) 1e-6 (reference too)
+                assert 0 < ncand <= max(4096, 0.08 * pairs), (ncand, pairs)
+            if mode == 2:
+                assert int(state[0]) == 0, "sabotaged bracket must take the fallback"
+        assert out[1] == out[0] == out[2], out
+        h_ref = float(orc.svgd_rbf_h(X.numpy()))
+        assert abs(out[1] - h_ref) <= (3e-6 if D <= 64 else 1e-5) * h_ref
+    finally:
+        E.svgd_select_mode(prev)
