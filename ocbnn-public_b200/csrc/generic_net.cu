@@ -15,6 +15,10 @@
 namespace ocbnn {
 
 constexpr int kGenThreads = 256;
+#ifndef OCBNN_GEN_SMALLTILES
+#define OCBNN_GEN_SMALLTILES 0
+#endif
+constexpr bool kSmallTiles = OCBNN_GEN_SMALLTILES != 0;   // 4 x 2 register tiles for layers with few 4 x 4 tiles (measured slower: see DESIGN.md)
 constexpr int kMaxRt = 10;  // largest output width the runtime head dispatch handles
 
 struct GenLayout {
@@ -85,64 +89,133 @@ __device__ __forceinline__ float dact_rt(int act, float z, float a) {
     return 1.f;
 }
 
-// Z[o][p] = b[o] + sum_d W[d][o] A[d][p] ; Aout = act(Z) unless last
-__device__ __forceinline__ void gen_forward_layer(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ Ain,
+// Work hand-out.  Every phase of a point tile is a list of equal-cost register tiles; thread t takes items t, t + T, ... of
+// the phase's list (`first` rotates the start so that two lists of one phase - the weight-gradient tiles and the
+// input-gradient tiles of a layer - continue one another instead of both starting at thread 0).  The tile shape is picked
+// per layer so that the list is at least ~0.8 T long when the layer allows it: 4 x 4 outputs per thread (2 LDS.128 per 16
+// FMA) for wide layers, 4 x 2 otherwise, and one dot product per thread for output layers of <= 8 units (a [50 -> 2] layer
+// handled as 4 x 4 tiles keeps 8 threads busy for as long as the [50 -> 50] layer before it keeps 104).
+// Item -> tile coordinates use a multiply-high division (exact for items < 2^16, divisors < 2^16): the layer widths are
+// run-time values and a hardware-less integer division costs more than the k-loop of a small tile.
+__device__ __forceinline__ int item_begin(int first) {
+    int t = (int)threadIdx.x - first;
+    return t < 0 ? t + (int)blockDim.x : t;
+}
+struct FastDiv {
+    unsigned m;
+    int d;
+    __device__ __forceinline__ explicit FastDiv(int dd) : m(0xFFFFFFFFu / (unsigned)dd + 1u), d(dd) {}
+    __device__ __forceinline__ void divmod(int n, int& q, int& r) const {
+        q = d == 1 ? n : (int)__umulhi((unsigned)n, m);
+        r = n - q * d;
+    }
+};
+
+// Z[o][p] = b[o] + sum_d W[d][o] A[d][p] ; Aout = act(Z) unless last.   PT points x 4 outputs per thread.
+template <int PT>
+__device__ __forceinline__ void gen_forward_tiles(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ Ain,
                                                   float* __restrict__ Z, float* __restrict__ Aout, int s_in, int ws, int tp, int ts, int act,
                                                   bool last) {
-    const int npt = tp >> 2, ntile = (ws >> 2) * npt;
+    const int npt = tp / PT, ntile = (ws >> 2) * npt;
+    const FastDiv dv(npt);
     for (int tile = threadIdx.x; tile < ntile; tile += blockDim.x) {
-        const int pt = tile % npt, ot = tile / npt;
-        float4 bb = *reinterpret_cast<const float4*>(b + 4 * ot);
-        float acc[4][4];
+        int ot, pt;
+        dv.divmod(tile, ot, pt);
+        const float4 bb = *reinterpret_cast<const float4*>(b + 4 * ot);
+        float acc[4][PT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[0][j] = bb.x; acc[1][j] = bb.y; acc[2][j] = bb.z; acc[3][j] = bb.w; }
+        for (int j = 0; j < PT; ++j) { acc[0][j] = bb.x; acc[1][j] = bb.y; acc[2][j] = bb.z; acc[3][j] = bb.w; }
         const float* wp = W + 4 * ot;
-        const float* ap = Ain + 4 * pt;
-#pragma unroll 4
-        for (int d = 0; d < s_in; ++d) {
-            float4 w4 = *reinterpret_cast<const float4*>(wp + d * ws);
-            float4 a4 = *reinterpret_cast<const float4*>(ap + d * ts);
-            const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float* ap = Ain + PT * pt;
+#pragma unroll 5
+        for (int d = 0; d < s_in; ++d, wp += ws, ap += ts) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wp);
+            float av[PT];
+            if (PT == 4) { const float4 a4 = *reinterpret_cast<const float4*>(ap); av[0] = a4.x; av[1] = a4.y; av[2 % PT] = a4.z; av[3 % PT] = a4.w; }
+            else { const float2 a2 = *reinterpret_cast<const float2*>(ap); av[0] = a2.x; av[1] = a2.y; }
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[i], av[j], acc[i][j]);
+                for (int j = 0; j < PT; ++j) acc[i][j] = fmaf(wv[i], av[j], acc[i][j]);
         }
+        float* zr = Z + 4 * ot * ts + PT * pt;
+        float* ar = Aout + 4 * ot * ts + PT * pt;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float* zr = Z + (4 * ot + i) * ts + 4 * pt;
-            *reinterpret_cast<float4*>(zr) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-            if (!last) {
-                float* ar = Aout + (4 * ot + i) * ts + 4 * pt;
-                *reinterpret_cast<float4*>(ar) = make_float4(act_rt(act, acc[i][0]), act_rt(act, acc[i][1]), act_rt(act, acc[i][2]),
-                                                             act_rt(act, acc[i][3]));
+        for (int i = 0; i < 4; ++i, zr += ts, ar += ts) {
+            if (PT == 4) {
+                *reinterpret_cast<float4*>(zr) = make_float4(acc[i][0], acc[i][1], acc[i][2 % PT], acc[i][3 % PT]);
+                if (!last) *reinterpret_cast<float4*>(ar) = make_float4(act_rt(act, acc[i][0]), act_rt(act, acc[i][1]), act_rt(act, acc[i][2 % PT]), act_rt(act, acc[i][3 % PT]));
+            } else {
+                *reinterpret_cast<float2*>(zr) = make_float2(acc[i][0], acc[i][1]);
+                if (!last) *reinterpret_cast<float2*>(ar) = make_float2(act_rt(act, acc[i][0]), act_rt(act, acc[i][1]));
             }
         }
     }
 }
+// narrow layers (ws <= 8): one (output, point) dot product per thread
+__device__ __forceinline__ void gen_forward_narrow(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ Ain,
+                                                   float* __restrict__ Z, float* __restrict__ Aout, int s_in, int ws, int tp, int ts, int act,
+                                                   bool last) {
+    const FastDiv dv(tp);
+    for (int item = threadIdx.x; item < ws * tp; item += blockDim.x) {
+        int o, p;
+        dv.divmod(item, o, p);
+        float acc0 = b[o], acc1 = 0.f;
+        const float* wp = W + o;
+        const float* ap = Ain + p;
+        int d = 0;
+        for (; d + 1 < s_in; d += 2, wp += 2 * ws, ap += 2 * ts) {
+            acc0 = fmaf(wp[0], ap[0], acc0);
+            acc1 = fmaf(wp[ws], ap[ts], acc1);
+        }
+        if (d < s_in) acc0 = fmaf(wp[0], ap[0], acc0);
+        const float z = acc0 + acc1;
+        Z[o * ts + p] = z;
+        if (!last) Aout[o * ts + p] = act_rt(act, z);
+    }
+}
+__device__ __forceinline__ void gen_forward_layer(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ Ain,
+                                                  float* __restrict__ Z, float* __restrict__ Aout, int s_in, int ws, int tp, int ts, int act,
+                                                  bool last) {
+    if (ws <= 8) gen_forward_narrow(W, b, Ain, Z, Aout, s_in, ws, tp, ts, act, last);
+    else if (!kSmallTiles || (ws >> 2) * (tp >> 2) * 5 >= (int)blockDim.x * 4) gen_forward_tiles<4>(W, b, Ain, Z, Aout, s_in, ws, tp, ts, act, last);
+    else gen_forward_tiles<2>(W, b, Ain, Z, Aout, s_in, ws, tp, ts, act, last);
+}
 
-// gW[d][o] += sum_p A[d][p] dZ[o][p] ; gb[o] += sum_p dZ[o][p].   Thread tile: rows d = dt + i*ND, o = ot + j*NO (interleaved,
-// so that the rows a warp touches at one step are consecutive -> distinct banks).
-__device__ __forceinline__ void gen_backward_weights(float* __restrict__ gW, float* __restrict__ gb, const float* __restrict__ Ain,
-                                                     const float* __restrict__ dZ, int s_in, int s_out, int ws, int tp, int ts) {
-    const int ND = (s_in + 3) >> 2, NO = ws >> 2, ntile = ND * NO;
+// gW[d][o] += sum_p A[d][p] dZ[o][p].   Thread tile: rows d = dt + i*ND (i < 4), o = ot + j*NO (j < OJ), interleaved so that
+// the rows a warp touches at one step are consecutive -> distinct banks.  Rows past the layer are clamped to its last row
+// (the duplicate result is not stored), so the point loop has no guards.
+template <int OJ>
+__device__ __forceinline__ void gen_backward_weights_tiles(float* __restrict__ gW, const float* __restrict__ Ain, const float* __restrict__ dZ,
+                                                           int s_in, int s_out, int ws, int tp, int ts) {
+    const int ND = (s_in + 3) >> 2, NO = (ws + OJ - 1) / OJ, ntile = ND * NO;
+    const FastDiv dv(ND);
     for (int tile = threadIdx.x; tile < ntile; tile += blockDim.x) {
-        const int dt = tile % ND, ot = tile / ND;
-        float acc[4][4];
+        int ot, dt;
+        dv.divmod(tile, ot, dt);
+        float acc[4][OJ];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+            for (int j = 0; j < OJ; ++j) acc[i][j] = 0.f;
+        const float* ar[4];
+        const float* zr[OJ];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ar[i] = Ain + (dt + i * ND) * ts;                 // pad rows are zero
+#pragma unroll
+        for (int j = 0; j < OJ; ++j) zr[j] = dZ + min(ot + j * NO, ws - 1) * ts;
+#pragma unroll 2
         for (int p = 0; p < tp; p += 4) {
-            float4 a4[4], z4[4];
+            float4 a4[4], z4[OJ];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a4[i] = *reinterpret_cast<const float4*>(Ain + (dt + i * ND) * ts + p);   // pad rows are zero
+            for (int i = 0; i < 4; ++i) a4[i] = *reinterpret_cast<const float4*>(ar[i] + p);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) z4[j] = *reinterpret_cast<const float4*>(dZ + (ot + j * NO) * ts + p);
+            for (int j = 0; j < OJ; ++j) z4[j] = *reinterpret_cast<const float4*>(zr[j] + p);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < OJ; ++j) {
                     acc[i][j] = fmaf(a4[i].x, z4[j].x, acc[i][j]);
                     acc[i][j] = fmaf(a4[i].y, z4[j].y, acc[i][j]);
                     acc[i][j] = fmaf(a4[i].z, z4[j].z, acc[i][j]);
@@ -154,69 +227,99 @@ __device__ __forceinline__ void gen_backward_weights(float* __restrict__ gW, flo
             const int d = dt + i * ND;
             if (d < s_in) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < OJ; ++j) {
                     const int o = ot + j * NO;
                     if (o < s_out) gW[d * ws + o] += acc[i][j];
                 }
             }
         }
     }
-    for (int o = threadIdx.x; o < s_out; o += blockDim.x) {
-        float s = 0.f;
-        for (int p = 0; p < tp; ++p) s += dZ[o * ts + p];
-        gb[o] += s;
+}
+// returns the number of list items (so that the caller can continue the hand-out with the next list)
+__device__ __forceinline__ int gen_backward_weights(float* __restrict__ gW, float* __restrict__ gb, const float* __restrict__ Ain,
+                                                    const float* __restrict__ dZ, int s_in, int s_out, int ws, int tp, int ts) {
+    const int T = (int)blockDim.x, ND = (s_in + 3) >> 2;
+    int items;
+    if (!kSmallTiles || ND * (ws >> 2) * 5 >= T * 4) {
+        items = ND * ((ws + 3) / 4);
+        gen_backward_weights_tiles<4>(gW, Ain, dZ, s_in, s_out, ws, tp, ts);
+    } else {
+        items = ND * ((ws + 1) / 2);
+        gen_backward_weights_tiles<2>(gW, Ain, dZ, s_in, s_out, ws, tp, ts);
     }
+    // bias gradient: one thread per output, handed out from the top so that it lands on threads the tile list left idle
+    for (int o = (int)blockDim.x - 1 - (int)threadIdx.x; o < s_out; o += blockDim.x) {
+        float s0 = 0.f, s1 = 0.f;
+        const float* zr = dZ + o * ts;
+        for (int p = 0; p < tp; p += 4) {
+            const float4 z = *reinterpret_cast<const float4*>(zr + p);
+            s0 += z.x + z.y;
+            s1 += z.z + z.w;
+        }
+        gb[o] += s0 + s1;
+    }
+    return items;
 }
 
-// dZprev[d][p] = (sum_o W[d][o] dZ[o][p]) * act'(Zprev[d][p])
-__device__ __forceinline__ void gen_backward_input(const float* __restrict__ W, const float* __restrict__ dZ, const float* __restrict__ Zprev,
-                                                   const float* __restrict__ Aprev, float* __restrict__ dZprev, int s_in, int ws, int wsp, int tp,
-                                                   int ts, int act) {
-    // wsp: padded width of the previous layer (rows of dZprev to produce, rows >= s_in are written as zero)
-    const int ND = wsp >> 2, npt = tp >> 2, ntile = ND * npt;
-    // handed out from the last thread downwards: the weight-gradient tiles of the same phase start at thread 0
-    for (int tile = (int)blockDim.x - 1 - (int)threadIdx.x; tile < ntile; tile += blockDim.x) {
-        const int dt = tile % ND, pt = tile / ND;
-        float acc[4][4];
+// dZprev[d][p] = (sum_o W[d][o] dZ[o][p]) * act'(Zprev[d][p]).  4 rows d x PT points per thread.  Rows d >= s_in read the
+// (finite) shared memory that follows W_l and are written as zero.
+template <int PT>
+__device__ __forceinline__ void gen_backward_input_tiles(const float* __restrict__ W, const float* __restrict__ dZ, const float* __restrict__ Zprev,
+                                                         const float* __restrict__ Aprev, float* __restrict__ dZprev, int s_in, int ws, int wsp,
+                                                         int tp, int ts, int act, int first) {
+    // wsp: padded width of the previous layer (rows of dZprev to produce)
+    const int ND = wsp >> 2, npt = tp / PT, ntile = ND * npt;
+    const FastDiv dv(ND);
+    for (int tile = item_begin(first); tile < ntile; tile += blockDim.x) {
+        int pt, dt;
+        dv.divmod(tile, pt, dt);
+        float acc[4][PT];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-        for (int o = 0; o < ws; o += 4) {
-            float4 w4[4], z4[4];
+            for (int j = 0; j < PT; ++j) acc[i][j] = 0.f;
+        const float* wr[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int d = dt + i * ND;
-                w4[i] = d < s_in ? *reinterpret_cast<const float4*>(W + d * ws + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i) wr[i] = W + min(dt + i * ND, s_in - 1) * ws;
+        const float* zp = dZ + PT * pt;
+#pragma unroll 2
+        for (int o = 0; o < ws; o += 4, zp += 4 * ts) {
+            float4 w4[4];
+            float zv[4][PT];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w4[i] = *reinterpret_cast<const float4*>(wr[i] + o);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                if (PT == 4) { const float4 z = *reinterpret_cast<const float4*>(zp + jj * ts); zv[jj][0] = z.x; zv[jj][1] = z.y; zv[jj][2 % PT] = z.z; zv[jj][3 % PT] = z.w; }
+                else { const float2 z = *reinterpret_cast<const float2*>(zp + jj * ts); zv[jj][0] = z.x; zv[jj][1] = z.y; }
             }
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) z4[jj] = *reinterpret_cast<const float4*>(dZ + (o + jj) * ts + 4 * pt);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float wv[4] = {w4[i].x, w4[i].y, w4[i].z, w4[i].w};
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    acc[i][0] = fmaf(wv[jj], z4[jj].x, acc[i][0]);
-                    acc[i][1] = fmaf(wv[jj], z4[jj].y, acc[i][1]);
-                    acc[i][2] = fmaf(wv[jj], z4[jj].z, acc[i][2]);
-                    acc[i][3] = fmaf(wv[jj], z4[jj].w, acc[i][3]);
-                }
+                for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                    for (int j = 0; j < PT; ++j) acc[i][j] = fmaf(wv[jj], zv[jj][j], acc[i][j]);
             }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int d = dt + i * ND;
-            float4 zz = *reinterpret_cast<const float4*>(Zprev + d * ts + 4 * pt);
-            float4 aa = *reinterpret_cast<const float4*>(Aprev + d * ts + 4 * pt);
-            float4 r;
-            r.x = acc[i][0] * dact_rt(act, zz.x, aa.x);
-            r.y = acc[i][1] * dact_rt(act, zz.y, aa.y);
-            r.z = acc[i][2] * dact_rt(act, zz.z, aa.z);
-            r.w = acc[i][3] * dact_rt(act, zz.w, aa.w);
-            if (d >= s_in) r = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(dZprev + d * ts + 4 * pt) = r;
+            const int off = d * ts + PT * pt;
+            float r[PT];
+#pragma unroll
+            for (int j = 0; j < PT; ++j) r[j] = d < s_in ? acc[i][j] * dact_rt(act, Zprev[off + j], Aprev[off + j]) : 0.f;
+            if (PT == 4) *reinterpret_cast<float4*>(dZprev + off) = make_float4(r[0], r[1], r[2 % PT], r[3 % PT]);
+            else *reinterpret_cast<float2*>(dZprev + off) = make_float2(r[0], r[1]);
         }
     }
+}
+__device__ __forceinline__ void gen_backward_input(const float* __restrict__ W, const float* __restrict__ dZ, const float* __restrict__ Zprev,
+                                                   const float* __restrict__ Aprev, float* __restrict__ dZprev, int s_in, int ws, int wsp, int tp,
+                                                   int ts, int act, int first) {
+    first %= (int)blockDim.x;
+    if (!kSmallTiles || (wsp >> 2) * (tp >> 2) * 5 >= (int)blockDim.x * 4) gen_backward_input_tiles<4>(W, dZ, Zprev, Aprev, dZprev, s_in, ws, wsp, tp, ts, act, first);
+    else gen_backward_input_tiles<2>(W, dZ, Zprev, Aprev, dZprev, s_in, ws, wsp, tp, ts, act, first);
 }
 
 template <int SK>
@@ -247,7 +350,7 @@ __device__ __forceinline__ float head_dispatch(int sk, int kind, const float* Zl
     }
 }
 
-__global__ void __launch_bounds__(kGenThreads)
+__global__ void __launch_bounds__(kGenThreads, 4)
 k_logpost_generic(EvalArgs a, GenLayout L, const float* __restrict__ w, long long m, float* __restrict__ out_lp, float* __restrict__ out_grad) {
     extern __shared__ __align__(16) float smem[];
     float* Ws = smem;
@@ -312,10 +415,10 @@ k_logpost_generic(EvalArgs a, GenLayout L, const float* __restrict__ w, long lon
             }
             for (int l = nl; l >= 1; --l) {
                 const float* Aprev = (l == 1) ? Act : Act + ((size_t)L.arow[l - 1] + L.ws[l - 1]) * ts;
-                gen_backward_weights(Gs + L.woff[l], Gs + L.boff[l], Aprev, dZ, L.s[l - 1], L.s[l], L.ws[l], tp, ts);
+                const int used = gen_backward_weights(Gs + L.woff[l], Gs + L.boff[l], Aprev, dZ, L.s[l - 1], L.s[l], L.ws[l], tp, ts);
                 if (l > 1) {
                     const float* Zprev = Act + (size_t)L.arow[l - 1] * ts;
-                    gen_backward_input(Ws + L.woff[l], dZ, Zprev, Aprev, dZo, L.s[l - 1], L.ws[l], L.ws[l - 1], tp, ts, L.act);
+                    gen_backward_input(Ws + L.woff[l], dZ, Zprev, Aprev, dZo, L.s[l - 1], L.ws[l], L.ws[l - 1], tp, ts, L.act, used);
                 }
                 __syncthreads();
                 float* t = dZ; dZ = dZo; dZo = t;
