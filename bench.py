@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--leapfrog", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-svgd", action="store_true", help="skip the secondary SVGD particle-iters/s measurement")
     ap.add_argument("--extras", action="store_true", help="also time SVGD/SGLD/BBB and the chain-count sweep (extra JSON keys)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
@@ -308,6 +309,15 @@ def main():
                "h2d_bytes_per_step": int(M * D * 4 + M * 8), "d2h_bytes_per_step": int(M * D * 4 + M * 8 // K),
                "path": "HMCMixin.hmc_run(collect_every=1, chunk=1, samples_host=pinned): momenta+uniforms H2D per step on a side stream, that step's samples D2H on a copy stream, accept counts D2H at the end"}
 
+    # ---- second headline metric of BASELINE.json: SVGD particle-iters/s (W4 = repro/F3b.yaml, 4096 particles per GPU) --------
+    svgd = None
+    if not args.no_svgd:
+        os.chdir(scratch)
+        try:
+            svgd = svgd_secondary(dev, world, barrier)
+        finally:
+            os.chdir(cwd)
+
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -357,12 +367,41 @@ def main():
                        "chains_per_gpu": M, "chains_total": world * M, "leapfrog_l": L, "hmc_epsilon": m.hmc_epsilon, "lanes_per_chain": args.lanes or "auto",
                        "l2": "flushed between timed steps (256 MiB write)", "accept_rate": accept_rate},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "wall_s_timed_region": wall}
+            "wall_s_timed_region": wall, "svgd": svgd}
     if args.extras:
         line["extras"] = extras(m, prob, dev, args)
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def svgd_secondary(dev, world, barrier, per_gpu=4096, epochs=20, warm=3):
+    """SVGD particle-iters/s through the host driver (SVGDMixin.svgd_setup / svgd_epoch, the body of infer()): W4 = repro/F3b.yaml
+    ([1,10,1] rbf regressor on toy4 + negative COCP), `per_gpu` particles per GPU.  Every epoch = K1 gradients of this rank's
+    particles, all-gather of particles and gradients (NCCL, N > 1), exact median bandwidth, phi on tcgen05 (3xTF32), Adagrad.
+    Weak scaling in the particle count; note that the pair work grows with n^2."""
+    from ocbnn_b200 import workloads
+    n = per_gpu * world
+    ms = workloads.build("W4", seed=0, infer_nsamples=n)
+    X0 = torch.randn(n, ms.nweights, generator=torch.Generator().manual_seed(5))
+    st = ms.svgd_setup(X0)
+    for ep in range(1, warm + 1):
+        ms.svgd_epoch(st, ep, True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for ep in range(warm + 1, warm + epochs + 1):
+        ms.svgd_epoch(st, ep, True)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_total = float(t.item())
+    return {"metric": "svgd_particle_iters_per_s", "value": n * epochs / (ms_total * 1e-3), "unit": "particle-iters/s", "particles_total": n,
+            "particles_per_gpu": per_gpu, "epochs": epochs, "ms_per_epoch": ms_total / epochs, "tensor_path": bool(st["tensor"]),
+            "workload": "W4 repro/F3b.yaml SVGD + negative COCP, toy4, [1,10,1] rbf; particles ~ N(0,1)",
+            "finite": bool(torch.isfinite(st["X"]).all())}
 
 
 def _time_cuda(fn, reps=3, warm=1):

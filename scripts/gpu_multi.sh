@@ -10,5 +10,5 @@ for n in 1 $N; do
   tail -1 gpurun_out/bench_n$n.log | python -c "
 import sys, json
 d = json.loads(sys.stdin.readline())
-print('n_gpus', d['n_gpus'], 'value %.3e' % d['value'], 'e2e %.3e' % d['e2e']['value'], 'ms/step %.3f' % d['ms_per_step'])"
+print('n_gpus', d['n_gpus'], 'value %.3e' % d['value'], 'e2e %.3e' % d['e2e']['value'], 'ms/step %.3f' % d['ms_per_step'], 'svgd', d.get('svgd'))"
 done

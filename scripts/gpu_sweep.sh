@@ -8,7 +8,7 @@ tail -5 gpurun_out/pytest_gpu.log
 for cfg in ${SWEEP:-"3 2" "4 2" "5 2" "5 1" "3 3" "3 4"}; do
   set -- $cfg
   echo "MB=$1 U=$2" >> gpurun_out/sweep.log
-  OCBNN_HMC_MB=$1 OCBNN_HMC_U=$2 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e 2>>gpurun_out/sweep.err | python -c "
+  OCBNN_HMC_MB=$1 OCBNN_HMC_U=$2 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-svgd 2>>gpurun_out/sweep.err | python -c "
 import sys, json
 for ln in sys.stdin:
     try: d = json.loads(ln)
