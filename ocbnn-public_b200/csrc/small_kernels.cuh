@@ -272,20 +272,21 @@ struct SmallLaunch {
     // One chain per thread (G = 1, the large-M case) has tuning variants selected by OCBNN_HMC_MB (resident CTAs per SM
     // the kernel is compiled for: register cap 65536 / (128 MB)) and OCBNN_HMC_U (points in flight per thread); measured
     // defaults in kDefaultHmc*.  Lane-split chains (G > 1, few chains) use one configuration.
+    // One chain per thread (G = 1, the large-M case): variants selected by OCBNN_HMC_MB (resident CTAs per SM the kernel is
+    // compiled for: register cap 65536 / (128 MB)) and OCBNN_HMC_U (points in flight per thread); measured defaults in
+    // kDefaultHmc*.  Lane-split chains (G > 1, few chains) run the same kernel with the gradient combined by a shuffle butterfly.  (A variant
+    // with per-lane slot ownership and a shared-memory reduction removed ~40 % of the per-lane instructions but was 25 % SLOWER at
+    // 4096 chains: at <2 warps per scheduler the serial shared-memory round trips cost more than the replicated arithmetic.)
     template <int G>
     static int hmc(const Problem& p, const EvalArgs& a, float* q, const float* p0, const double* u, long long m, int n_it, float eps,
                    float eps_half, int L, int restore, uint8_t* acc, float* h, int* flags, float* samples, int thin, cudaStream_t st) {
-#define OCBNN_HMC_GO(MBV, UV) return hmc_mb<G, MBV, UV>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st)
         if (G == 1) {
             static const int mb = [] { const char* e = getenv("OCBNN_HMC_MB"); return e ? atoi(e) : kDefaultHmcMb; }();
             static const int uu = [] { const char* e = getenv("OCBNN_HMC_U"); return e ? atoi(e) : kDefaultHmcU; }();
-            constexpr int G1 = G == 1 ? 1 : 0;      // instantiate the variants for G = 1 only
-            if (G1) {
-                if (uu >= 4 || mb <= 3) OCBNN_HMC_GO(G1 ? 3 : 4, G1 ? 4 : 2);
-            }
+            if (uu >= 4 || mb <= 3) return hmc_mb<1, 3, 4>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
+            return hmc_mb<1, 4, 2>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
         }
-        OCBNN_HMC_GO(4, 2);
-#undef OCBNN_HMC_GO
+        return hmc_mb<G, 4, 2>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
     }
     template <int G>
     static int sgld(const Problem& p, const EvalArgs& a, float* w, const float* noise, const float* he, const int* offs, long long m,

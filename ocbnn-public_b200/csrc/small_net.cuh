@@ -548,20 +548,12 @@ __device__ __forceinline__ void eval_segment(const EvalCtx& c, int rs, int lo, i
     lp += (double)vacc;
 }
 
-// log posterior value and gradient at the weights behind the view `q`.  Block-uniform control flow (contains
-// __syncthreads when the point set does not fit one tile or `restage` is set).  On return every lane of the group holds
-// the full g and lp.
-template <class N, int G, int U, class QV>
-__device__ __forceinline__ void evaluate(const EvalArgs& a, const EvalCtx& c, bool restage, const QV& q, float2 (&g)[N::NS],
-                                         float& lp_out, int lane) {
-    float2 w[N::NS];                                  // evaluation copy: W1 and b1 in scaled units (act_in_scale)
-#pragma unroll
-    for (int s = 0; s < N::NS; ++s) {
-        const float2 v = q[s];
-        w[s] = (s < N::SW2 && act_in_scale<N::ACT>() != 1.f) ? __fmul2_rn(v, f2(act_in_scale<N::ACT>())) : v;
-        g[s] = f2(0.f);
-    }
-    double lp = 0.0;
+// Point loop of one evaluation: raw accumulators g (see point_eval / use_moments) and the float64 value sum of the points
+// lane `lane` of the chain's G lanes is responsible for.  Block-uniform control flow (contains __syncthreads when the point
+// set does not fit one tile or `restage` is set).
+template <class N, int G, int U>
+__device__ __forceinline__ void eval_points(const EvalArgs& a, const EvalCtx& c, bool restage, const float2 (&w)[N::NS], float2 (&g)[N::NS],
+                                            double& lp, int lane) {
     const bool multi = c.npts > c.tile_cap;
     for (int begin = 0; begin < c.npts; begin += c.tile_cap) {
         const int count = min(c.tile_cap, c.npts - begin);
@@ -592,6 +584,22 @@ __device__ __forceinline__ void evaluate(const EvalArgs& a, const EvalCtx& c, bo
             }
         }
     }
+}
+
+// log posterior value and gradient at the weights behind the view `q`.  Block-uniform control flow (see eval_points).  On
+// return every lane of the group holds the full g and lp.
+template <class N, int G, int U, class QV>
+__device__ __forceinline__ void evaluate(const EvalArgs& a, const EvalCtx& c, bool restage, const QV& q, float2 (&g)[N::NS],
+                                         float& lp_out, int lane) {
+    float2 w[N::NS];                                  // evaluation copy: W1 and b1 in scaled units (act_in_scale)
+#pragma unroll
+    for (int s = 0; s < N::NS; ++s) {
+        const float2 v = q[s];
+        w[s] = (s < N::SW2 && act_in_scale<N::ACT>() != 1.f) ? __fmul2_rn(v, f2(act_in_scale<N::ACT>())) : v;
+        g[s] = f2(0.f);
+    }
+    double lp = 0.0;
+    eval_points<N, G, U>(a, c, restage, w, g, lp, lane);
     if (G > 1) {
 #pragma unroll
         for (int off = G / 2; off > 0; off >>= 1) {
