@@ -292,7 +292,7 @@ def main():
         m._hmc_draw = draw_from_host
         m.update_config(lanes=args.lanes, hmc_l=L)
         os.chdir(scratch)
-        m.hmc_run(qd, 1, True, collect_every=1, chunk=1)          # warm the side stream / allocator (untimed)
+        m.hmc_run(qd, min(K, 3), True, collect_every=1, chunk=1, samples_host=samples_h[:min(K, 3)])   # warm the streams / allocator / pinned pages (untimed)
         pos[0] = 0
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

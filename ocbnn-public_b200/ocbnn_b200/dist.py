@@ -61,3 +61,33 @@ def gather_cat(t, dim=0):
     dist.all_gather_into_tensor(out, t) if t.is_cuda else dist.all_gather(list(out.view((w, mx) + tuple(t.shape[1:])).unbind(0)), t)
     parts = [out[r * mx:r * mx + sizes[r]] for r in range(w)]
     return torch.cat(parts, 0).movedim(0, dim).contiguous()
+
+
+def gather_rows(t, n_total, out=None):
+    """All-gather of row shards laid out by shard(n_total): (rows_r, ...) on rank r -> (n_total, ...) everywhere.  The shard
+    sizes follow from n_total alone, so nothing is exchanged and nothing synchronises with the host (gather_cat asks the
+    other ranks for their sizes).  `out`: optional preallocated result."""
+    if not active():
+        return t
+    w = world()
+    sizes = [shard(n_total, r, w)[1] - shard(n_total, r, w)[0] for r in range(w)]
+    t = t.contiguous()
+    if out is None:
+        out = torch.empty((n_total,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    if all(sz == sizes[0] for sz in sizes):
+        if t.is_cuda:
+            dist.all_gather_into_tensor(out, t)
+        else:
+            dist.all_gather(list(out.split(sizes, 0)), t)
+        return out
+    mx = max(sizes)                             # ragged shards: pad to the largest, gather, drop the padding
+    if t.shape[0] < mx:
+        t = torch.cat([t, torch.zeros((mx - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)], 0)
+    tmp = torch.empty((w * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    if t.is_cuda:
+        dist.all_gather_into_tensor(tmp, t)
+    else:
+        dist.all_gather(list(tmp.split(mx, 0)), t)
+    torch.cat([tmp[r * mx:r * mx + sizes[r]] for r in range(w)], 0, out=out)
+    return out
+

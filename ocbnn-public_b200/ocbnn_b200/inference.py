@@ -269,12 +269,46 @@ class SVGDMixin:
                 "acc": torch.zeros(hi - lo, self.nweights, device=dev), "h": torch.empty(1, device=dev)}
 
     def svgd_epoch(self, st, epoch, with_data, use_tensor=None):
-        """One SVGD epoch on the device: gradients (K1), all-gather, bandwidth (K3a), phi (K3b), Adagrad (K3c)."""
+        """One SVGD epoch on the device: gradients (K1), all-gather, bandwidth (K3a), phi (K3b), Adagrad (K3c).
+
+        Single rank: the ~16 launches of an epoch are captured once per (minibatch offset, with_data, path) into a CUDA graph
+        and replayed (the epoch is launch-gap bound at a few thousand particles); `svgd_graph: false` in the config, a
+        multi-rank run (NCCL + host-driven select) or a failed capture use the eager path."""
+        if D.world() != 1 or not st.get("graph_ok", True) or not bool(getattr(self, "svgd_graph", True)):
+            return self._svgd_epoch_eager(st, epoch, with_data, use_tensor)
+        key = (_batch_for(self, epoch), bool(with_data), use_tensor)
+        graphs = st.setdefault("graphs", {})
+        ent = graphs.get(key)
+        if ent is None:                         # first use of this key: eager (also warms per-kernel attributes)
+            graphs[key] = "warm"
+            return self._svgd_epoch_eager(st, epoch, with_data, use_tensor)
+        if ent == "warm":
+            try:
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    self._svgd_epoch_eager(st, epoch, with_data, use_tensor)
+                graphs[key] = ent = g
+            except Exception as exc:            # capture not possible here: stay eager from now on
+                logging.warning(f"[{self.uid}] SVGD epoch graph capture failed ({exc}); running eagerly.")
+                st["graph_ok"] = False
+                graphs.clear()
+                torch.cuda.synchronize()
+                return self._svgd_epoch_eager(st, epoch, with_data, use_tensor)
+        ent.replay()
+        return st
+
+    def _svgd_epoch_eager(self, st, epoch, with_data, use_tensor=None):
         prob = st["prob"]                      # compiled once per infer(): the reference also fixes data and constraints per infer()
         X = st["X"]
         tensor = st["tensor"] if use_tensor is None else E.svgd_use_tensor(int(use_tensor), st["n"]) and st["tensor"]
         _, G = prob.logpost_grad(X, _batch_for(self, epoch), with_data, want_lp=False, out_grad=st["G"])
-        Xall, Gall = D.gather_cat(X, dim=0), D.gather_cat(G, dim=0)
+        if D.world() == 1:
+            Xall, Gall = X, G
+        else:                                   # shard sizes follow from n: no size exchange, no host sync; buffers reused
+            if "Xall" not in st:
+                st["Xall"], st["Gall"] = torch.empty(st["n"], self.nweights, device=X.device), torch.empty(st["n"], self.nweights, device=X.device)
+            Xall, Gall = D.gather_rows(X, st["n"], out=st["Xall"]), D.gather_rows(G, st["n"], out=st["Gall"])
         n, lo, rows = st["n"], st["lo"], st["hi"] - st["lo"]
         if D.world() == 1:
             E.svgd_bandwidth(Xall, st["ws"], st["h"], use_tensor=1 if tensor else 0)

@@ -42,5 +42,6 @@ for n in [int(a) for a in sys.argv[2:]] or [4096, 16384]:
     torch.cuda.synchronize(); t0 = time.perf_counter(); raw_epoch(); t1 = time.perf_counter(); torch.cuda.synchronize()
     r["host time of raw epoch"] = (t1 - t0) * 1e3
     st = m.svgd_setup(X.cpu(), use_tensor=use_t)
+    m.svgd_epoch(st, 1, True); m.svgd_epoch(st, 1, True)      # eager, then graph capture
     r["epoch (host API)"] = t(lambda: m.svgd_epoch(st, 1, True))
     print(wl, "n", n, "D", m.nweights, {k: f"{v:.3f} ms" for k, v in r.items()}, "particle-iters/s %.3e" % (n / (r["epoch (host API)"] * 1e-3)))

@@ -33,6 +33,7 @@ def _worker(rank, world, port, q):
     mine = full[lo:hi].clone()
     got = D.gather_cat(mine, dim=0)                       # ragged: 4 and 3 rows
     out["gather0"] = torch.equal(got, full)
+    out["gather_rows"] = torch.equal(D.gather_rows(mine, 7), full) and torch.equal(D.gather_rows(full[D.shard(6)[0]:D.shard(6)[1]].clone(), 6), full[:6])
     samples = full.reshape(1, 7, 3).repeat(2, 1, 1)       # (rounds, chains, D) sharded along dim 1
     got = D.gather_cat(samples[:, lo:hi].contiguous(), dim=1)
     out["gather1"] = torch.equal(got, samples)
@@ -62,7 +63,7 @@ def test_gloo_world2():
         assert p.exitcode == 0
     assert res[0]["shard"] == (0, 4) and res[1]["shard"] == (4, 7)
     for r in range(world):
-        assert res[r]["gather0"] and res[r]["gather1"]
+        assert res[r]["gather0"] and res[r]["gather1"] and res[r]["gather_rows"]
         assert res[r]["all_sum"] == 3.0 and res[r]["all_sum_"] == [3, 3, 3, 3]
     assert res[0]["pairs"] + res[1]["pairs"] == 11 * 10 // 2
 
@@ -72,5 +73,5 @@ def test_single_process_is_a_noop():
     assert not D.active() and D.rank() == 0 and D.world() == 1
     assert D.shard(10) == (0, 10)
     t = torch.ones(3)
-    assert D.gather_cat(t) is t and D.all_sum(torch.tensor([2.0])) == 2.0
+    assert D.gather_cat(t) is t and D.gather_rows(t, 3) is t and D.all_sum(torch.tensor([2.0])) == 2.0
     assert [D.shard(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
