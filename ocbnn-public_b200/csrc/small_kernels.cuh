@@ -281,12 +281,20 @@ struct SmallLaunch {
     static int hmc(const Problem& p, const EvalArgs& a, float* q, const float* p0, const double* u, long long m, int n_it, float eps,
                    float eps_half, int L, int restore, uint8_t* acc, float* h, int* flags, float* samples, int thin, cudaStream_t st) {
         if (G == 1) {
-            static const int mb = [] { const char* e = getenv("OCBNN_HMC_MB"); return e ? atoi(e) : kDefaultHmcMb; }();
+            // wide nets (32 float2 slots for [2,10,3]: 64 registers of weights + 64 of accumulators) spill at 128 registers/thread:
+            // they default to 2 CTAs/SM (255 registers)
+            // (measured, W3 = F2a classifier + Dirichlet COCP: 0.21 G steps/s at (4,2) with 4 KB of spills, 0.76 G at (2,2)); [2,10,1] (21 slots)
+            // gets 3 CTAs/SM (168 registers, no spills)
+            static const int mb = [] { const char* e = getenv("OCBNN_HMC_MB"); return e ? atoi(e) : (N::NS > 24 ? 2 : N::NS > 18 ? 3 : kDefaultHmcMb); }();
             static const int uu = [] { const char* e = getenv("OCBNN_HMC_U"); return e ? atoi(e) : kDefaultHmcU; }();
-            if (uu >= 4 || mb <= 3) return hmc_mb<1, 3, 4>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
-            return hmc_mb<1, 4, 2>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
+#define OCBNN_HMC_GO(MBV, UV) return hmc_mb<1, MBV, UV>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st)
+            if (mb <= 2) { if (uu <= 1) OCBNN_HMC_GO(2, 1); OCBNN_HMC_GO(2, 2); }
+            if (mb == 3) { if (uu <= 1) OCBNN_HMC_GO(3, 1); if (uu <= 2) OCBNN_HMC_GO(3, 2); OCBNN_HMC_GO(3, 4); }
+            if (uu >= 4) OCBNN_HMC_GO(3, 4);
+            OCBNN_HMC_GO(4, 2);
+#undef OCBNN_HMC_GO
         }
-        return hmc_mb<G, 4, 2>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
+        return hmc_mb<G, (N::NS > 24 ? 2 : N::NS > 18 ? 3 : 4), 2>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
     }
     template <int G>
     static int sgld(const Problem& p, const EvalArgs& a, float* w, const float* noise, const float* he, const int* offs, long long m,
