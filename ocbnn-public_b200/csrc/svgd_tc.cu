@@ -650,7 +650,7 @@ k_vt_split(const float* __restrict__ g, const float* __restrict__ xc_hi, const f
 
 // phi[t][c] = (O_G - (2/h)(O_X - xc_i[c] rowsum_t)) / n, summing the K splits
 __global__ void __launch_bounds__(256)
-k_phi_finalize(const float* __restrict__ o, int splits, const float* __restrict__ rowsum, const float* __restrict__ xc_hi,
+k_phi_finalize(const float* __restrict__ o, int splits, const float* __restrict__ rowsum, int rs_splits, const float* __restrict__ xc_hi,
                const float* __restrict__ xc_lo, const float* __restrict__ hptr, long long n, int d, int dp, long long row_begin, long long n_rows,
                float* __restrict__ phi) {
     const float c2 = 2.f / *hptr, invn = 1.f / (float)n;
@@ -667,8 +667,184 @@ k_phi_finalize(const float* __restrict__ o, int splits, const float* __restrict_
         }
         const long long i = row_begin + t;
         const float xi = xc_hi[i * dp + c] + xc_lo[i * dp + c];
-        phi[idx] = (og - c2 * (ox - xi * rowsum[t])) * invn;
+        float rsum = 0.f;                       // rs_splits partial row sums (fused path) or one finished sum
+        for (int sp = 0; sp < rs_splits; ++sp) rsum += rowsum[(long long)sp * n_rows + t];
+        phi[idx] = (og - c2 * (ox - xi * rsum)) * invn;
     }
+}
+
+// ---- K3b fused: K tiles generated on the fly -----------------------------------------------------------------------------
+// O[rows x BN] = K[rows x n] * Vt[BN x n]^T with K_tj = exp(-d2_tj / h) NEVER written to HBM: the four epilogue warps of
+// tc_gemm.cuh's layout double as SIMT producers of the A operand.  Per 32-column K block they read the 128 x 32 tile of d2
+// (coalesced 128-byte rows), evaluate the exponentials (MUFU.EX2), split them into tf32 hi / lo and store both tiles
+// straight into the 128-byte-swizzled K-major shared-memory layout the UMMA descriptor expects (16-byte chunk c of row r
+// at chunk position c ^ (r & 7)), fence the generic-proxy writes towards the async proxy and arrive on the stage's full
+// barrier next to the TMA transaction of the B tiles (Vt hi / lo).  Row sums of K ride along in registers.  Used when
+// [G | X] fits one N tile (2 dp <= 128, i.e. D <= 64): with more N tiles every one of them would regenerate K.
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+k_phi_fused(const float* __restrict__ d2, const float* __restrict__ hptr, long long n, long long n4, long long n_rows,
+            const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ o, long long ldo,
+            long long split_stride, float* __restrict__ rs_part, int num_kb, int kb_per_split) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + Cfg::kStages * Cfg::kStageBytes;          // full[stages], empty[stages], tmem_full, tmem_slot
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 1));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kBM;
+    const int kb_begin = blockIdx.z * kb_per_split;
+    const int kb_end = min(num_kb, kb_begin + kb_per_split);
+    const int nkb = kb_end - kb_begin;
+
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (Cfg::kStages + s); };
+    const uint32_t tmem_full_bar = bars + 8u * (2 * Cfg::kStages);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(full_bar(s), 1 + 4);          // the TMA thread (B tiles) + one arrival per producer warp (A tiles)
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % Cfg::kStages;
+                const uint32_t ph = (i / Cfg::kStages) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                const uint32_t st = base + s * Cfg::kStageBytes;
+                mbar_expect_tx(full_bar(s), 2 * Cfg::kTileB);
+                const int kx = (kb_begin + i) * kBK;
+                tma_load_2d(st + 2 * Cfg::kTileA, &tm_b_hi, full_bar(s), kx, 0);
+                tma_load_2d(st + 2 * Cfg::kTileA + Cfg::kTileB, &tm_b_lo, full_bar(s), kx, 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(kBM, BN);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % Cfg::kStages;
+                const uint32_t ph = (i / Cfg::kStages) & 1;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t st = base + s * Cfg::kStageBytes;
+                const uint64_t a_hi = make_kmajor_sw128_desc(st), a_lo = make_kmajor_sw128_desc(st + Cfg::kTileA);
+                const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * Cfg::kTileA), b_lo = make_kmajor_sw128_desc(st + 2 * Cfg::kTileA + Cfg::kTileB);
+#pragma unroll
+                for (int k = 0; k < kBK / kUmmaK; ++k) {
+                    const uint64_t adv = (uint64_t)((k * kUmmaK * 4) >> 4);
+                    umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, (i | k) != 0);
+                    umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
+                    umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, 1);
+                }
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        // ---- A producers: warp wp owns rows [32 wp, 32 wp + 32) of the tile; per pass 4 rows x 8 chunks of 16 bytes ----
+        const int wp = warp - 2, rr = lane >> 3, c = lane & 7;
+        const float sc = -1.4426950408889634f / __ldg(hptr);
+        float rs[8];
+#pragma unroll
+        for (int ps = 0; ps < 8; ++ps) rs[ps] = 0.f;
+        // the d2 tile of K block i + 1 is in flight (registers) while block i is evaluated: the loads do not touch the stage,
+        // so they are issued ahead of the empty-barrier wait and hide the L2/HBM latency behind a whole block of work
+        auto load_tile = [&](float4 (&dst)[8], int i) {
+            const long long jj = (long long)(kb_begin + i) * kBK + 4 * c;
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+                const long long t = m0 + 32 * wp + 4 * ps + rr;
+                dst[ps] = (i < nkb && t < n_rows && jj < n4) ? __ldg(reinterpret_cast<const float4*>(d2 + t * n4 + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        float4 v[8], nx[8];
+        load_tile(v, 0);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % Cfg::kStages;
+            const uint32_t ph = (i / Cfg::kStages) & 1;
+            const long long j = (long long)(kb_begin + i) * kBK + 4 * c;
+            load_tile(nx, i + 1);
+            mbar_wait(empty_bar(s), ph ^ 1);
+            uint8_t* stp = gen_base + s * Cfg::kStageBytes;
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+                const int r = 32 * wp + 4 * ps + rr;
+                const bool row_ok = m0 + r < n_rows;
+                float k[4] = {ex2_fast(v[ps].x * sc), ex2_fast(v[ps].y * sc), ex2_fast(v[ps].z * sc), ex2_fast(v[ps].w * sc)};
+                float hi[4], lo[4], sum = 0.f;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (!row_ok || j + e >= n) k[e] = 0.f;
+                    hi[e] = __uint_as_float(__float_as_uint(k[e]) & 0xFFFFE000u);
+                    lo[e] = k[e] - hi[e];
+                    sum += k[e];
+                }
+                const int off = r * 128 + ((c ^ (r & 7)) << 4);
+                *reinterpret_cast<float4*>(stp + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(stp + Cfg::kTileA + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                rs[ps] += sum;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(s));
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) v[ps] = nx[ps];
+        }
+        if (c == 0) {
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+                const long long t = m0 + 32 * wp + 4 * ps + rr;
+                if (t < n_rows) rs_part[(long long)blockIdx.z * n_rows + t] = rs[ps];
+            }
+        }
+        // ---- epilogue: TMEM lane quarter = warp % 4 ----
+        const int q = warp & 3;
+        if (nkb > 0) {
+            mbar_wait(tmem_full_bar, 0);
+            tc_fence_after();
+        }
+        const long long row = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int cc = 0; cc < BN; cc += 32) {
+            float acc[32];
+            if (nkb > 0) {
+                tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, acc);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+            }
+            if (row < n_rows) {
+                float* dst = o + (long long)blockIdx.z * split_stride + row * ldo + cc;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, Cfg::kTmemCols);
 }
 
 // centre + split X, squared distances of rows [row_begin, row_begin + n_rows) into the workspace
@@ -700,22 +876,52 @@ static int tc_prepare(const TcWs& w, const float* x, unsigned* hist0, bool* hist
 }
 
 static int tc_phi(const TcWs& w, const float* g, const float* h, float* phi, cudaStream_t st) {
-    k_kmat_split<<<(unsigned)(w.n_rows < 148 * 8 ? w.n_rows : 148 * 8), 256, 0, st>>>(w.d2, h, w.n, w.n4, w.n_rows, w.k_hi, w.k_lo, w.rowsum);
-    OCBNN_LAUNCH_CHECK();
+    // OCBNN_SVGD_FUSED=0 forces the unfused pipeline (K materialised as hi/lo matrices, TMA-fed GEMM)
+    static const bool fused_ok = [] { const char* e = getenv("OCBNN_SVGD_FUSED"); return !(e && e[0] == '0'); }();
     dim3 gv((unsigned)((w.n4 + 31) / 32), (unsigned)(2 * w.dp / 32));
     k_vt_split<<<gv, 256, 0, st>>>(g, w.xc_hi, w.xc_lo, w.n, w.n4, (int)w.d, (int)w.dp, w.vt_hi, w.vt_lo);
     OCBNN_LAUNCH_CHECK();
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     int rc;
-    if ((rc = make_tmap(&ta_hi, w.k_hi, w.n_rows, w.n4, kBM))) return rc;
-    if ((rc = make_tmap(&ta_lo, w.k_lo, w.n_rows, w.n4, kBM))) return rc;
     if ((rc = make_tmap(&tb_hi, w.vt_hi, 2 * w.dp, w.n4, w.bn))) return rc;
     if ((rc = make_tmap(&tb_lo, w.vt_lo, 2 * w.dp, w.n4, w.bn))) return rc;
+    if (fused_ok && 2 * w.dp <= w.bn) {
+        // one N tile: K tiles are generated inside the GEMM (k_phi_fused); K splits sized to ONE wave of CTAs
+        const long long tiles = (w.n_rows + kBM - 1) / kBM;
+        const int num_kb = (int)((w.n4 + kBK - 1) / kBK);
+        int splits = (int)(148 / tiles);
+        if (splits > w.splits) splits = w.splits;          // o[] is sized for w.splits
+        if (splits > num_kb) splits = num_kb;
+        if (splits < 1) splits = 1;
+        const int per = (num_kb + splits - 1) / splits;
+        float* rs_part = w.k_hi;                            // the K matrices are not materialised on this path: reuse their space
+        dim3 grid((unsigned)tiles, 1, (unsigned)splits);
+        if (w.bn == 64) {
+            auto kern = k_phi_fused<64>;
+            OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kSmemBytes));
+            kern<<<grid, kThreads, GemmCfg<64>::kSmemBytes, st>>>(w.d2, h, w.n, w.n4, w.n_rows, tb_hi, tb_lo, w.o, 2 * w.dp, w.n_rows * 2 * w.dp, rs_part,
+                                                                  num_kb, per);
+        } else {
+            auto kern = k_phi_fused<128>;
+            OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes));
+            kern<<<grid, kThreads, GemmCfg<128>::kSmemBytes, st>>>(w.d2, h, w.n, w.n4, w.n_rows, tb_hi, tb_lo, w.o, 2 * w.dp, w.n_rows * 2 * w.dp, rs_part,
+                                                                   num_kb, per);
+        }
+        OCBNN_LAUNCH_CHECK();
+        k_phi_finalize<<<grid_for_ll(w.n_rows * w.d), 256, 0, st>>>(w.o, splits, rs_part, splits, w.xc_hi, w.xc_lo, h, w.n, (int)w.d, (int)w.dp,
+                                                                  w.row_begin, w.n_rows, phi);
+        OCBNN_LAUNCH_CHECK();
+        return OCBNN_OK;
+    }
+    k_kmat_split<<<(unsigned)(w.n_rows < 148 * 8 ? w.n_rows : 148 * 8), 256, 0, st>>>(w.d2, h, w.n, w.n4, w.n_rows, w.k_hi, w.k_lo, w.rowsum);
+    OCBNN_LAUNCH_CHECK();
+    if ((rc = make_tmap(&ta_hi, w.k_hi, w.n_rows, w.n4, kBM))) return rc;
+    if ((rc = make_tmap(&ta_lo, w.k_lo, w.n_rows, w.n4, kBM))) return rc;
     EpiStore epi{w.o, 2 * w.dp, w.n_rows * 2 * w.dp, (int)w.n_rows, (int)(2 * w.dp)};
     rc = w.bn == 64 ? launch_gemm<64>(ta_hi, ta_lo, tb_hi, tb_lo, epi, w.n_rows, 2 * w.dp, w.n4, w.splits, st)
                     : launch_gemm<128>(ta_hi, ta_lo, tb_hi, tb_lo, epi, w.n_rows, 2 * w.dp, w.n4, w.splits, st);
     if (rc) return rc;
-    k_phi_finalize<<<grid_for_ll(w.n_rows * w.d), 256, 0, st>>>(w.o, w.splits, w.rowsum, w.xc_hi, w.xc_lo, h, w.n, (int)w.d, (int)w.dp, w.row_begin,
+    k_phi_finalize<<<grid_for_ll(w.n_rows * w.d), 256, 0, st>>>(w.o, w.splits, w.rowsum, 1, w.xc_hi, w.xc_lo, h, w.n, (int)w.d, (int)w.dp, w.row_begin,
                                                               w.n_rows, phi);
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
