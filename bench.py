@@ -439,7 +439,7 @@ def extras(m, prob, dev, args):
             ms = workloads.build("W4", seed=0, infer_nsamples=n)
             for ut, tag in ((1, "tcgen05"), (0, "simt")):
                 st = ms.svgd_setup(torch.randn(n, ms.nweights), use_tensor=ut)
-                t = _time_cuda(lambda: ms.svgd_epoch(st, 1, True), reps=3)
+                t = _time_cuda(lambda: ms.svgd_epoch(st, 1, True), reps=5, warm=3)
                 out[f"svgd_W4_n{n}_{tag}_particle_iters_per_s"] = n / t
         mg = workloads.build("W1", sampler="SGLD", seed=0)
         pg = mg.engine_problem()

@@ -137,6 +137,8 @@ static int pick_splits(long long n_rows, long long n4, int two_dp, int bn) {
     return (int)(s < 1 ? 1 : s);
 }
 
+static int fused_splits(long long n_rows, long long n4);      // K splits of the fused phi kernel (defined with it)
+
 static TcWs carve(void* workspace, long long n, long long d, long long row_begin, long long n_rows) {
     TcWs w{};
     w.n = n; w.d = d; w.n4 = (n + 3) / 4 * 4; w.dp = (d + 31) / 32 * 32; w.n_rows = n_rows; w.row_begin = row_begin;
@@ -157,7 +159,8 @@ static TcWs carve(void* workspace, long long n, long long d, long long row_begin
     w.vt_hi = take(2 * w.dp * w.n4);
     w.vt_lo = take(2 * w.dp * w.n4);
     w.rowsum = take(n_rows);
-    w.o = take((long long)w.splits * n_rows * 2 * w.dp);
+    const int fs = fused_splits(n_rows, w.n4);
+    w.o = take((long long)(w.splits > fs ? w.splits : fs) * n_rows * 2 * w.dp);
     w.sel = reinterpret_cast<unsigned long long*>(take(64));
     w.cand_cap = n_rows == n ? (n * n / 32 > (1 << 16) ? n * n / 32 : (1 << 16)) : 0;
     w.cand = take(w.cand_cap);
@@ -689,12 +692,31 @@ __device__ __forceinline__ float ex2_fast(float x) {
     return y;
 }
 
+// Two CTAs per SM (2 smem stages of 48 / 64 KB, 168 registers): the producers wait on d2 loads, a second CTA fills the gaps.
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+struct FusedCfg {
+    static constexpr int kStages = 2;
+    static constexpr int kTileA = kBM * kBK * 4;
+    static constexpr int kTileB = BN * kBK * 4;
+    static constexpr int kStageBytes = 2 * kTileA + 2 * kTileB;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+    static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+};
+constexpr int kFusedCtasPerSm = 2, kFusedMaxSplits = 16;
+static int fused_splits(long long n_rows, long long n4) {
+    const long long tiles = (n_rows + kBM - 1) / kBM, num_kb = (n4 + kBK - 1) / kBK;
+    long long sp = (148 * kFusedCtasPerSm) / tiles;
+    if (sp > kFusedMaxSplits) sp = kFusedMaxSplits;
+    if (sp > num_kb) sp = num_kb;
+    return (int)(sp < 1 ? 1 : sp);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 2)
 k_phi_fused(const float* __restrict__ d2, const float* __restrict__ hptr, long long n, long long n4, long long n_rows,
             const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ o, long long ldo,
             long long split_stride, float* __restrict__ rs_part, int num_kb, int kb_per_split) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = FusedCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -889,22 +911,19 @@ static int tc_phi(const TcWs& w, const float* g, const float* h, float* phi, cud
         // one N tile: K tiles are generated inside the GEMM (k_phi_fused); K splits sized to ONE wave of CTAs
         const long long tiles = (w.n_rows + kBM - 1) / kBM;
         const int num_kb = (int)((w.n4 + kBK - 1) / kBK);
-        int splits = (int)(148 / tiles);
-        if (splits > w.splits) splits = w.splits;          // o[] is sized for w.splits
-        if (splits > num_kb) splits = num_kb;
-        if (splits < 1) splits = 1;
+        const int splits = fused_splits(w.n_rows, w.n4);    // o[] is sized for it (carve)
         const int per = (num_kb + splits - 1) / splits;
         float* rs_part = w.k_hi;                            // the K matrices are not materialised on this path: reuse their space
         dim3 grid((unsigned)tiles, 1, (unsigned)splits);
         if (w.bn == 64) {
             auto kern = k_phi_fused<64>;
-            OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kSmemBytes));
-            kern<<<grid, kThreads, GemmCfg<64>::kSmemBytes, st>>>(w.d2, h, w.n, w.n4, w.n_rows, tb_hi, tb_lo, w.o, 2 * w.dp, w.n_rows * 2 * w.dp, rs_part,
+            OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<64>::kSmemBytes));
+            kern<<<grid, kThreads, FusedCfg<64>::kSmemBytes, st>>>(w.d2, h, w.n, w.n4, w.n_rows, tb_hi, tb_lo, w.o, 2 * w.dp, w.n_rows * 2 * w.dp, rs_part,
                                                                   num_kb, per);
         } else {
             auto kern = k_phi_fused<128>;
-            OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes));
-            kern<<<grid, kThreads, GemmCfg<128>::kSmemBytes, st>>>(w.d2, h, w.n, w.n4, w.n_rows, tb_hi, tb_lo, w.o, 2 * w.dp, w.n_rows * 2 * w.dp, rs_part,
+            OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<128>::kSmemBytes));
+            kern<<<grid, kThreads, FusedCfg<128>::kSmemBytes, st>>>(w.d2, h, w.n, w.n4, w.n_rows, tb_hi, tb_lo, w.o, 2 * w.dp, w.n_rows * 2 * w.dp, rs_part,
                                                                    num_kb, per);
         }
         OCBNN_LAUNCH_CHECK();
