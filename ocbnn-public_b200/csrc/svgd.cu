@@ -367,6 +367,8 @@ int tc_svgd_hist(long long n, long long d, long long row_begin, long long n_rows
                  cudaStream_t st);
 int tc_svgd_phi(const float* g, const float* h, long long n, long long d, long long row_begin, long long n_rows, float* phi, void* ws, cudaStream_t st);
 int tc_svgd_select_fast(long long n, long long d, void* ws, float* out_h, int mode, unsigned long long* dbg, cudaStream_t st);
+int tc_svgd_prepare_select(const float* x, long long n, long long d, void* ws, long long ws_bytes, float* out_h, int mode, unsigned long long* dbg,
+                           cudaStream_t st);
 } }
 
 // use_tensor: 0 exact fp32 SIMT kernels ; 1 tcgen05 path ; -1 choose (tensor path from 1024 particles up)
@@ -421,9 +423,8 @@ extern "C" OCBNN_API int ocbnn_svgd_bandwidth(const float* x, int64_t n, int64_t
     // passes, the algorithm the multi-GPU path all-reduces) | fallback (fast path with a sabotaged bracket: tests the in-kernel fallback)
     const int sel_mode = g_select_mode.load();
     if (tensor && sel_mode != 0 && n <= 2000000000ll) {
-        if ((rc = tc::tc_svgd_prepare(x, n, d, 0, n, tcws, workspace_bytes - (3 * kBins * sizeof(uint32_t) + 256), nullptr, nullptr, (cudaStream_t)stream)))
-            return rc;
-        return tc::tc_svgd_select_fast(n, d, tcws, out_h, sel_mode, reinterpret_cast<unsigned long long*>(state), (cudaStream_t)stream);
+        return tc::tc_svgd_prepare_select(x, n, d, tcws, workspace_bytes - (3 * kBins * sizeof(uint32_t) + 256), out_h, sel_mode,
+                                          reinterpret_cast<unsigned long long*>(state), (cudaStream_t)stream);
     }
     if (tensor) {                       // the pass-0 histogram rides on the distance pass when the direct kernel forms the distances
         k_zero_u32<<<(3 * kBins + 255) / 256, 256, 0, (cudaStream_t)stream>>>(hist, 3 * kBins);

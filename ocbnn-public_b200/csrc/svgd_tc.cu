@@ -137,7 +137,8 @@ static int pick_splits(long long n_rows, long long n4, int two_dp, int bn) {
     return (int)(s < 1 ? 1 : s);
 }
 
-static int fused_splits(long long n_rows, long long n4);      // K splits of the fused phi kernel (defined with it)
+static int fused_splits(long long n_rows, long long n4);
+long long tc_workspace_bytes(long long n, long long d, long long n_rows);      // K splits of the fused phi kernel (defined with it)
 
 static TcWs carve(void* workspace, long long n, long long d, long long row_begin, long long n_rows) {
     TcWs w{};
@@ -585,6 +586,157 @@ k_sel_final(const float* __restrict__ d2, const float* __restrict__ ssum, long l
     }
 }
 
+// ---- single-rank, D <= 64: distances and the select's counting pass in ONE symmetric kernel -------------------------------
+// k_sel_sample_x draws the pair sample straight from the centred particles (the bracket is needed before d2 exists);
+// k_d2_sym computes only the tiles on and above the diagonal of d2 (half the FMA work of k_d2_direct), writes each tile and,
+// through a shared-memory transpose, its mirror image, and classifies the pairs i < j of the tile against the bracket on the
+// way (zeros / below in registers, candidates compacted through warp-private staging + the linear histogram): no second
+// pass over d2 for the median.
+template <int DP>
+__global__ void __launch_bounds__(256)
+k_sel_sample_x(const float* __restrict__ hi, const float* __restrict__ lo, const float* __restrict__ ssum, long long n, int d,
+               float* __restrict__ samples) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kSelSamples) return;
+    const unsigned a = mix32((unsigned)idx * 2u + 0x9e3779b9u), b = mix32(a ^ 0x85ebca6bu);
+    long long i = (long long)(a % (unsigned)n), j = (long long)(b % (unsigned)n);
+    if (i == j) j = (j + 1) % n;
+    if (i > j) { const long long tmp = i; i = j; j = tmp; }
+    const float4* hi4 = reinterpret_cast<const float4*>(hi);
+    const float4* lo4 = reinterpret_cast<const float4*>(lo);
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < DP / 4; ++c) {
+        const float4 ah = __ldg(hi4 + i * (DP / 4) + c), al = __ldg(lo4 + i * (DP / 4) + c);
+        const float4 bh = __ldg(hi4 + j * (DP / 4) + c), bl = __ldg(lo4 + j * (DP / 4) + c);
+        float e;
+        e = (ah.x + al.x) - (bh.x + bl.x); acc = fmaf(e, e, acc);
+        e = (ah.y + al.y) - (bh.y + bl.y); acc = fmaf(e, e, acc);
+        e = (ah.z + al.z) - (bh.z + bl.z); acc = fmaf(e, e, acc);
+        e = (ah.w + al.w) - (bh.w + bl.w); acc = fmaf(e, e, acc);
+    }
+    samples[idx] = sqrtf(fmaxf(acc + 2.f * 1e-6f * (ssum[i] - ssum[j]) + (float)d * 1e-12f, 0.f));
+}
+
+template <int DP>
+__global__ void __launch_bounds__(256)
+k_d2_sym(const float* __restrict__ hi, const float* __restrict__ lo, const float* __restrict__ ssum, long long n, long long n4, int d,
+         float* __restrict__ d2, SelHdr* __restrict__ hdr, float* __restrict__ cand, long long cand_cap, unsigned* __restrict__ ghist) {
+    if (blockIdx.x < blockIdx.y) return;                        // tiles below the diagonal are the mirror images
+    constexpr int XS = DP + 4;
+    __shared__ __align__(16) float sm_x[2 * 64 * (XS > 33 ? XS : 33)];           // xi | xj, later the 64 x 65 tile of the mirror
+    __shared__ float stage[8][256];
+    __shared__ unsigned long long red[2][8];
+    float (*xi)[XS] = reinterpret_cast<float (*)[XS]>(sm_x);
+    float (*xj)[XS] = reinterpret_cast<float (*)[XS]>(sm_x + 64 * XS);
+    const long long t0 = (long long)blockIdx.y * 64, j0 = (long long)blockIdx.x * 64;
+    const bool diag = blockIdx.x == blockIdx.y;
+    for (int idx = threadIdx.x; idx < 64 * DP; idx += 256) {
+        const int rr = idx / DP, c = idx % DP;
+        const long long i = t0 + rr, j = j0 + rr;
+        xi[rr][c] = i < n ? hi[i * DP + c] + lo[i * DP + c] : 0.f;
+        xj[rr][c] = j < n ? hi[j * DP + c] + lo[j * DP + c] : 0.f;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // columns tx + 16 q, rows ty + 16 p (interleaved: conflict-free rows)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc[4][4] = {};
+#pragma unroll
+    for (int c = 0; c < DP; c += 4) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) a[p] = *reinterpret_cast<const float4*>(&xi[ty + 16 * p][c]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4*>(&xj[tx + 16 * q][c]);
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float e;
+                e = a[p].x - b[q].x; acc[p][q] = fmaf(e, e, acc[p][q]);
+                e = a[p].y - b[q].y; acc[p][q] = fmaf(e, e, acc[p][q]);
+                e = a[p].z - b[q].z; acc[p][q] = fmaf(e, e, acc[p][q]);
+                e = a[p].w - b[q].w; acc[p][q] = fmaf(e, e, acc[p][q]);
+            }
+    }
+    // ---- the tile itself, and the classification of its pairs i < j ----
+    const float lo_b = hdr->lo, hi_b = hdr->hi;
+    const float scale = hi_b > lo_b ? (float)kSelBins / (hi_b - lo_b) : 0.f;
+    const float eps = 1e-6f, deps2 = (float)d * 1e-12f;
+    float si[4], sj[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) si[p] = t0 + ty + 16 * p < n ? ssum[t0 + ty + 16 * p] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sj[q] = j0 + tx + 16 * q < n ? ssum[j0 + tx + 16 * q] : 0.f;
+    unsigned zeros = 0, below = 0, staged = 0;                  // staged: warp-uniform
+    auto flush = [&]() {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&hdr->ncand, staged);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((long long)base + staged > cand_cap) { if (lane == 0) hdr->overflow = 1u; }
+        else for (unsigned k = lane; k < staged; k += 32) cand[base + k] = stage[warp][k];
+        __syncwarp();
+        staged = 0;
+    };
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const long long t = t0 + ty + 16 * p;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long j = j0 + tx + 16 * q;
+            if (t < n && j < n4) d2[t * n4 + j] = j < n ? acc[p][q] : 0.f;
+            bool is_c = false;
+            float v = 0.f;
+            if (t < n && j < n && j > t) {
+                v = sqrtf(fmaxf(acc[p][q] + 2.f * eps * (si[p] - sj[q]) + deps2, 0.f));
+                if (v == 0.f) ++zeros;
+                else if (v < lo_b) ++below;
+                else is_c = v <= hi_b;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, is_c);
+            if (m) {
+                if (is_c) {
+                    stage[warp][staged + __popc(m & ((1u << lane) - 1u))] = v;
+                    atomicAdd(&ghist[sel_lbin(v, lo_b, scale)], 1u);
+                }
+                staged += __popc(m);
+                __syncwarp();
+                if (staged > 256 - 32) flush();
+            }
+        }
+    }
+    if (staged) flush();
+    unsigned long long z = zeros, b = below;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        z += __shfl_xor_sync(0xffffffffu, z, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+    }
+    if (lane == 0) { red[0][warp] = z; red[1][warp] = b; }
+    __syncthreads();                                             // also: everybody is done with xi / xj
+    if (threadIdx.x == 0) {
+        z = 0; b = 0;
+        for (int w = 0; w < 8; ++w) { z += red[0][w]; b += red[1][w]; }
+        if (z) atomicAdd(&hdr->zeros, z);
+        if (b) atomicAdd(&hdr->below, b);
+    }
+    if (diag) return;
+    // ---- mirror image: d2[j][t] = d2[t][j], transposed through shared memory so that both writes are coalesced ----
+    float (*tile)[65] = reinterpret_cast<float (*)[65]>(sm_x);
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tile[ty + 16 * p][tx + 16 * q] = acc[p][q];
+    __syncthreads();
+    const int col = threadIdx.x & 63;
+#pragma unroll 4
+    for (int rr = 0; rr < 16; ++rr) {
+        const int row = (threadIdx.x >> 6) + 4 * rr;
+        const long long jg = j0 + row, tg = t0 + col;           // row jg of d2, column tg
+        if (jg < n && tg < n4) d2[jg * n4 + tg] = tg < n ? tile[col][row] : 0.f;
+    }
+}
+
 // K = exp(-d2/h) split into tf32 hi/lo, row sums; one block per row
 __global__ void __launch_bounds__(256)
 k_kmat_split(const float* __restrict__ d2, const float* __restrict__ hptr, long long n, long long n4, long long n_rows, float* __restrict__ k_hi,
@@ -871,13 +1023,30 @@ k_phi_fused(const float* __restrict__ d2, const float* __restrict__ hptr, long l
 
 // centre + split X, squared distances of rows [row_begin, row_begin + n_rows) into the workspace
 // hist0: when non-NULL (and the distances are formed by the direct kernel) the pass-0 select histogram is fused into the pass
-static int tc_prepare(const TcWs& w, const float* x, unsigned* hist0, bool* hist0_done, cudaStream_t st) {
+// sel_mode > 0 (single rank, all rows, D <= 64): the bracket is sampled from X and k_d2_sym forms the distances AND does the
+// median select's counting pass; *sel_done tells the caller that only gather + final are left.
+static int tc_prepare(const TcWs& w, const float* x, unsigned* hist0, bool* hist0_done, cudaStream_t st, int sel_mode = 0, bool* sel_done = nullptr) {
     if (hist0_done) *hist0_done = false;
+    if (sel_done) *sel_done = false;
     k_colmean<<<(unsigned)w.dp, 256, 0, st>>>(x, w.n, (int)w.d, (int)w.dp, w.mean);
     OCBNN_LAUNCH_CHECK();
     k_center_split<<<(unsigned)((w.n * 32 + 255) / 256), 256, 0, st>>>(x, w.mean, w.n, (int)w.d, (int)w.dp, w.xc_hi, w.xc_lo, w.r, w.s);
     OCBNN_LAUNCH_CHECK();
     static const bool gram_small = [] { const char* e = getenv("OCBNN_SVGD_GRAM"); return e && e[0] == 't'; }();   // experiment: tensor Gram for small D too
+    if (w.dp <= 64 && !gram_small && sel_mode > 0 && w.n_rows == w.n && w.row_begin == 0) {
+        SelHdr* hdr = reinterpret_cast<SelHdr*>(w.sel);
+        if (w.dp == 32) k_sel_sample_x<32><<<kSelSamples / 256, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.s, w.n, (int)w.d, w.samples);
+        else k_sel_sample_x<64><<<kSelSamples / 256, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.s, w.n, (int)w.d, w.samples);
+        OCBNN_LAUNCH_CHECK();
+        k_sel_bracket<<<1, 1024, 0, st>>>(w.samples, hdr, w.ghist, sel_mode == 2 ? 1 : 0);
+        OCBNN_LAUNCH_CHECK();
+        dim3 grid((unsigned)((w.n + 63) / 64), (unsigned)((w.n + 63) / 64));
+        if (w.dp == 32) k_d2_sym<32><<<grid, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.s, w.n, w.n4, (int)w.d, w.d2, hdr, w.cand, w.cand_cap, w.ghist);
+        else k_d2_sym<64><<<grid, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.s, w.n, w.n4, (int)w.d, w.d2, hdr, w.cand, w.cand_cap, w.ghist);
+        OCBNN_LAUNCH_CHECK();
+        if (sel_done) *sel_done = true;
+        return OCBNN_OK;
+    }
     if (w.dp <= 64 && !gram_small) {
         dim3 grid((unsigned)((w.n4 + 63) / 64), (unsigned)((w.n_rows + 63) / 64));
         if (w.dp == 32) k_d2_direct<32><<<grid, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.s, w.n, w.n4, (int)w.d, w.row_begin, w.n_rows, w.d2, hist0);
@@ -972,6 +1141,22 @@ int tc_svgd_select_fast(long long n, long long d, void* ws, float* out_h, int mo
     OCBNN_LAUNCH_CHECK();
     k_sel_count<<<(unsigned)(n < 148 * 8 ? n : 148 * 8), 256, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, hdr, w.cand, w.cand_cap, w.ghist);
     OCBNN_LAUNCH_CHECK();
+    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap);
+    OCBNN_LAUNCH_CHECK();
+    k_sel_final<<<1, 1024, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, hdr, w.list2, w.cand_cap, out_h, dbg);
+    OCBNN_LAUNCH_CHECK();
+    return OCBNN_OK;
+}
+// prepare (centre, split, distances) + exact median in one go; for D <= 64 the counting pass rides on the distance kernel
+int tc_svgd_prepare_select(const float* x, long long n, long long d, void* ws, long long ws_bytes, float* out_h, int mode, unsigned long long* dbg,
+                           cudaStream_t st) {
+    OCBNN_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(n, d, n), OCBNN_EINVAL, "SVGD tensor path: workspace too small");
+    TcWs w = carve(ws, n, d, 0, n);
+    bool sel_done = false;
+    int rc = tc_prepare(w, x, nullptr, nullptr, st, mode, &sel_done);
+    if (rc) return rc;
+    if (!sel_done) return tc_svgd_select_fast(n, d, ws, out_h, mode, dbg, st);
+    SelHdr* hdr = reinterpret_cast<SelHdr*>(w.sel);
     k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap);
     OCBNN_LAUNCH_CHECK();
     k_sel_final<<<1, 1024, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, hdr, w.list2, w.cand_cap, out_h, dbg);
