@@ -51,7 +51,7 @@ k_logpost_small(EvalArgs a, const float* __restrict__ w, long long m, float* __r
 // registers.  The trajectory is a single loop around ONE inlined evaluate() (phase l = 0 is the evaluation at the start
 // of an iteration, needed at launch and after a restore-on-reject), which keeps the kernel small enough for the
 // instruction cache and the register allocator.
-template <class N, int G, int MB, int U>
+template <class N, int G, int MB, int U, bool WSM>
 __global__ void __launch_bounds__(kSmallThreads, MB)
 k_hmc_small(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, const double* __restrict__ u, long long m, int n_it,
             float eps, float eps_half, int L, int restore, uint8_t* __restrict__ out_acc, float* __restrict__ out_h,
@@ -115,7 +115,7 @@ k_hmc_small(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, 
 #pragma unroll
             for (int s = 0; s < N::NS; ++s) qs[s * kSmallThreads] = __fadd2_rn(qs[s * kSmallThreads], __fmul2_rn(f2(eps), ps[s * kSmallThreads]));
         }
-        evaluate<N, G, U>(a, c, first, qv, g, lp, lane);      // the first call stages the (fixed) point set
+        evaluate<N, G, U, SmemView, WSM>(a, c, first, qv, g, lp, lane);      // the first call stages the (fixed) point set
         first = false;
         if (l == 0) {
             begin_iteration();
@@ -255,13 +255,13 @@ struct SmallLaunch {
         OCBNN_LAUNCH_CHECK();
         return OCBNN_OK;
     }
-    template <int G, int MB, int U>
+    template <int G, int MB, int U, bool WSM = false>
     static int hmc_mb(const Problem& p, const EvalArgs& a, float* q, const float* p0, const double* u, long long m, int n_it, float eps,
                       float eps_half, int L, int restore, uint8_t* acc, float* h, int* flags, float* samples, int thin, cudaStream_t st) {
         int tile_cap;
         const size_t extra = sizeof(float) * 4 * N::NS * kSmallThreads;        // q and p columns of every thread
         size_t sm = smem_bytes(p, npts(a), tile_cap, extra) + extra;
-        auto k = k_hmc_small<N, G, MB, U>;
+        auto k = k_hmc_small<N, G, MB, U, WSM>;
         OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         long long blocks = (m * G + kSmallThreads - 1) / kSmallThreads;
         k<<<(unsigned)blocks, kSmallThreads, sm, st>>>(a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin,
@@ -288,6 +288,11 @@ struct SmallLaunch {
             static const int mb = [] { const char* e = getenv("OCBNN_HMC_MB"); return e ? atoi(e) : (N::NS > 24 ? 2 : N::NS > 18 ? 3 : kDefaultHmcMb); }();
             static const int uu = [] { const char* e = getenv("OCBNN_HMC_U"); return e ? atoi(e) : kDefaultHmcU; }();
 #define OCBNN_HMC_GO(MBV, UV) return hmc_mb<1, MBV, UV>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st)
+            // wide nets, default: weights read from the thread's shared-memory column (WSM) at 3 CTAs/SM; OCBNN_HMC_MB=2 selects the
+            // register-weights kernel at 2 CTAs/SM
+            static const bool wsm = N::NS > 24 && !getenv("OCBNN_HMC_MB");
+            // (measured on W3: WSM at 3 CTAs/SM 0.758 G steps/s = register weights at 2 CTAs/SM 0.759 G; WSM at 4 CTAs/SM spills: 0.53-0.63 G)
+            if (wsm) return hmc_mb<1, (N::NS > 24 ? 3 : 4), 2, (N::NS > 24)>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
             if (mb <= 2) { if (uu <= 1) OCBNN_HMC_GO(2, 1); OCBNN_HMC_GO(2, 2); }
             if (mb == 3) { if (uu <= 1) OCBNN_HMC_GO(3, 1); if (uu <= 2) OCBNN_HMC_GO(3, 2); OCBNN_HMC_GO(3, 4); }
             if (uu >= 4) OCBNN_HMC_GO(3, 4);

@@ -84,12 +84,16 @@ template <int ACT>
 __host__ __device__ constexpr float act_in_scale() { return ACT == OCBNN_ACT_RBF ? 1.2011224087864498f : 1.f; }
 template <int ACT>
 __host__ __device__ constexpr float act_grad_scale() { return ACT == OCBNN_ACT_RBF ? -1.6651092223153954f : 1.f; }
+// the same two constants when the evaluator reads UNSCALED weights (wide nets keep them in shared memory, see SmemView)
+template <int ACT, bool SCALED>
+__host__ __device__ constexpr float grad_scale_for() { return SCALED ? act_grad_scale<ACT>() : (ACT == OCBNN_ACT_RBF ? -2.f : 1.f); }
 
 // returns a = act(z) and m with da/dz' (up to act_grad_scale) = m
-template <int ACT>
+template <int ACT, bool SCALED = true>
 __device__ __forceinline__ void act_pair(float2 zs, float2& a, float2& m) {
     if (ACT == OCBNN_ACT_RBF) {                       // exp(-z^2), base.py:84
-        const float2 t = __fmul2_rn(zs, zs);
+        float2 t = __fmul2_rn(zs, zs);
+        if (!SCALED) t = __fmul2_rn(t, f2(1.4426950408889634f));
         a = make_float2(ex2_approx(-t.x), ex2_approx(-t.y));
         m = __fmul2_rn(zs, a);
     } else if (ACT == OCBNN_ACT_RELU) {               // max(z,0), base.py:86
@@ -109,7 +113,14 @@ struct RegView {
     const float2 (&a)[NS];
     __device__ __forceinline__ float2 operator[](int s) const { return a[s]; }
 };
-struct SmemView {
+template <int NS>
+struct RegW {                                   // evaluation weights in registers, W1 / b1 pre-scaled
+    static constexpr bool kScaled = true;
+    const float2 (&a)[NS];
+    __device__ __forceinline__ float2 operator[](int s) const { return a[s]; }
+};
+struct SmemView {                               // as evaluation weights: unscaled, one LDS.64 per use
+    static constexpr bool kScaled = false;
     const float2* base;
     int stride;
     // volatile asm: every use is its own load (a plain load at the top of an evaluation would be kept live in 2 x NS
@@ -332,10 +343,10 @@ struct HeadNegFixed {
 template <class N>
 __host__ __device__ constexpr bool use_moments() { return N::S0 == 1 && N::SK == 1 && N::ACT == OCBNN_ACT_RBF; }
 
-template <class N, class HEAD, int U>
-__device__ __forceinline__ void point_eval(const float2 (&w)[N::NS], float2 (&g)[N::NS], float& vacc, const float* const (&rec)[U],
+template <class N, class HEAD, int U, class WV>
+__device__ __forceinline__ void point_eval(const WV& w, float2 (&g)[N::NS], float& vacc, const float* const (&rec)[U],
                                            const FastConsts& fc) {
-    constexpr bool MOM = use_moments<N>();
+    constexpr bool MOM = use_moments<N>() && WV::kScaled;
     float2 a[U][N::HP], m[U][MOM ? 1 : N::HP];
     float x[U][N::S0], f[U][N::SK], df[U][N::SK], val[U];
     const float* prm[U];
@@ -356,7 +367,7 @@ __device__ __forceinline__ void point_eval(const float2 (&w)[N::NS], float2 (&g)
                 const float2 t = __fmul2_rn(z, z);
                 a[u][hp] = make_float2(ex2_approx(-t.x), ex2_approx(-t.y));
             } else {
-                act_pair<N::ACT>(z, a[u][hp], m[u][MOM ? 0 : hp]);
+                act_pair<N::ACT, WV::kScaled>(z, a[u][hp], m[u][MOM ? 0 : hp]);
             }
 #pragma unroll
             for (int k = 0; k < N::SK; ++k)
@@ -523,8 +534,8 @@ __device__ __forceinline__ void load_pri_slots(float4* pri_s, const EvalArgs& a)
 // U at a time; the (at most one per lane) leftover point goes through the U = 1 instantiation.
 // The point values are added in fp32 over up to 4 trips (4 U points) and then into the float64 sum: one F2F + DADD per 4
 // trips instead of per trip (F2F issues on the XU pipe, which the MUFU ops of these kernels already load the most).
-template <class N, int G, int U, class HEAD>
-__device__ __forceinline__ void eval_segment(const EvalCtx& c, int rs, int lo, int hi, const float2 (&w)[N::NS], float2 (&g)[N::NS],
+template <class N, int G, int U, class HEAD, class WV>
+__device__ __forceinline__ void eval_segment(const EvalCtx& c, int rs, int lo, int hi, const WV& w, float2 (&g)[N::NS],
                                              double& lp, int lane) {
     int j = lo + lane;
     float vacc = 0.f;
@@ -534,7 +545,7 @@ __device__ __forceinline__ void eval_segment(const EvalCtx& c, int rs, int lo, i
             const float* rec[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) rec[u] = c.tab + (j + u * G) * rs;
-            point_eval<N, HEAD, U>(w, g, vacc, rec, c.fc);
+            point_eval<N, HEAD, U, WV>(w, g, vacc, rec, c.fc);
         }
         lp += (double)vacc;
         vacc = 0.f;
@@ -542,7 +553,7 @@ __device__ __forceinline__ void eval_segment(const EvalCtx& c, int rs, int lo, i
     if (U > 1) {
         for (; j < hi; j += G) {
             const float* rec[1] = {c.tab + j * rs};
-            point_eval<N, HEAD, 1>(w, g, vacc, rec, c.fc);
+            point_eval<N, HEAD, 1, WV>(w, g, vacc, rec, c.fc);
         }
     }
     lp += (double)vacc;
@@ -551,8 +562,8 @@ __device__ __forceinline__ void eval_segment(const EvalCtx& c, int rs, int lo, i
 // Point loop of one evaluation: raw accumulators g (see point_eval / use_moments) and the float64 value sum of the points
 // lane `lane` of the chain's G lanes is responsible for.  Block-uniform control flow (contains __syncthreads when the point
 // set does not fit one tile or `restage` is set).
-template <class N, int G, int U>
-__device__ __forceinline__ void eval_points(const EvalArgs& a, const EvalCtx& c, bool restage, const float2 (&w)[N::NS], float2 (&g)[N::NS],
+template <class N, int G, int U, class WV>
+__device__ __forceinline__ void eval_points(const EvalArgs& a, const EvalCtx& c, bool restage, const WV& w, float2 (&g)[N::NS],
                                             double& lp, int lane) {
     const bool multi = c.npts > c.tile_cap;
     for (int begin = 0; begin < c.npts; begin += c.tile_cap) {
@@ -569,18 +580,18 @@ __device__ __forceinline__ void eval_points(const EvalArgs& a, const EvalCtx& c,
             seg_lo = c.seg_end[sg];
             if (lo >= hi) continue;
             if (sg == 0) {
-                if (a.lik_head == OCBNN_HEAD_LIK_GAUSS) eval_segment<N, G, U, HeadEach<OCBNN_HEAD_LIK_GAUSS>>(c, a.rs, lo, hi, w, g, lp, lane);
-                else if (a.lik_head == OCBNN_HEAD_LIK_SOFTMAX) eval_segment<N, G, U, HeadEach<OCBNN_HEAD_LIK_SOFTMAX>>(c, a.rs, lo, hi, w, g, lp, lane);
-                else eval_segment<N, G, U, HeadEach<OCBNN_HEAD_LIK_BERNOULLI>>(c, a.rs, lo, hi, w, g, lp, lane);
+                if (a.lik_head == OCBNN_HEAD_LIK_GAUSS) eval_segment<N, G, U, HeadEach<OCBNN_HEAD_LIK_GAUSS>, WV>(c, a.rs, lo, hi, w, g, lp, lane);
+                else if (a.lik_head == OCBNN_HEAD_LIK_SOFTMAX) eval_segment<N, G, U, HeadEach<OCBNN_HEAD_LIK_SOFTMAX>, WV>(c, a.rs, lo, hi, w, g, lp, lane);
+                else eval_segment<N, G, U, HeadEach<OCBNN_HEAD_LIK_BERNOULLI>, WV>(c, a.rs, lo, hi, w, g, lp, lane);
             } else if (sg == 1) {
-                eval_segment<N, G, U, HeadEach<OCBNN_HEAD_POS_GAUSS>>(c, a.rs, lo, hi, w, g, lp, lane);
+                eval_segment<N, G, U, HeadEach<OCBNN_HEAD_POS_GAUSS>, WV>(c, a.rs, lo, hi, w, g, lp, lane);
             } else if (sg == 2) {
-                if (a.neg_n1 == 2 && a.neg_n2 == 0) eval_segment<N, G, U, HeadNegFixed<2, 0>>(c, a.rs, lo, hi, w, g, lp, lane);
-                else if (a.neg_n1 == 0 && a.neg_n2 == 1) eval_segment<N, G, U, HeadNegFixed<0, 1>>(c, a.rs, lo, hi, w, g, lp, lane);
-                else if (a.neg_n1 == 1 && a.neg_n2 == 0) eval_segment<N, G, U, HeadNegFixed<1, 0>>(c, a.rs, lo, hi, w, g, lp, lane);
-                else eval_segment<N, G, U, HeadEach<OCBNN_HEAD_NEG_EXP>>(c, a.rs, lo, hi, w, g, lp, lane);
+                if (a.neg_n1 == 2 && a.neg_n2 == 0) eval_segment<N, G, U, HeadNegFixed<2, 0>, WV>(c, a.rs, lo, hi, w, g, lp, lane);
+                else if (a.neg_n1 == 0 && a.neg_n2 == 1) eval_segment<N, G, U, HeadNegFixed<0, 1>, WV>(c, a.rs, lo, hi, w, g, lp, lane);
+                else if (a.neg_n1 == 1 && a.neg_n2 == 0) eval_segment<N, G, U, HeadNegFixed<1, 0>, WV>(c, a.rs, lo, hi, w, g, lp, lane);
+                else eval_segment<N, G, U, HeadEach<OCBNN_HEAD_NEG_EXP>, WV>(c, a.rs, lo, hi, w, g, lp, lane);
             } else {
-                eval_segment<N, G, U, HeadEach<OCBNN_HEAD_DIRICHLET>>(c, a.rs, lo, hi, w, g, lp, lane);
+                eval_segment<N, G, U, HeadEach<OCBNN_HEAD_DIRICHLET>, WV>(c, a.rs, lo, hi, w, g, lp, lane);
             }
         }
     }
@@ -588,18 +599,26 @@ __device__ __forceinline__ void eval_points(const EvalArgs& a, const EvalCtx& c,
 
 // log posterior value and gradient at the weights behind the view `q`.  Block-uniform control flow (see eval_points).  On
 // return every lane of the group holds the full g and lp.
-template <class N, int G, int U, class QV>
+template <class N, int G, int U, class QV, bool WSM = false>
 __device__ __forceinline__ void evaluate(const EvalArgs& a, const EvalCtx& c, bool restage, const QV& q, float2 (&g)[N::NS],
                                          float& lp_out, int lane) {
-    float2 w[N::NS];                                  // evaluation copy: W1 and b1 in scaled units (act_in_scale)
-#pragma unroll
-    for (int s = 0; s < N::NS; ++s) {
-        const float2 v = q[s];
-        w[s] = (s < N::SW2 && act_in_scale<N::ACT>() != 1.f) ? __fmul2_rn(v, f2(act_in_scale<N::ACT>())) : v;
-        g[s] = f2(0.f);
-    }
+    // WSM: the point loop reads the (unscaled) weights through the view q itself - one LDS.64 per use - instead of a scaled
+    // register copy.  For nets whose 2 x NS weight + accumulator registers do not fit next to the point temporaries.
+    constexpr bool SC = !WSM;
     double lp = 0.0;
-    eval_points<N, G, U>(a, c, restage, w, g, lp, lane);
+#pragma unroll
+    for (int s = 0; s < N::NS; ++s) g[s] = f2(0.f);
+    float2 w[WSM ? 1 : N::NS];                        // evaluation copy: W1 and b1 in scaled units (act_in_scale)
+    if constexpr (WSM) {
+        eval_points<N, G, U>(a, c, restage, q, g, lp, lane);
+    } else {
+#pragma unroll
+        for (int s = 0; s < N::NS; ++s) {
+            const float2 v = q[s];
+            w[WSM ? 0 : s] = (s < N::SW2 && act_in_scale<N::ACT>() != 1.f) ? __fmul2_rn(v, f2(act_in_scale<N::ACT>())) : v;
+        }
+        eval_points<N, G, U>(a, c, restage, RegW<WSM ? 1 : N::NS>{w}, g, lp, lane);
+    }
     if (G > 1) {
 #pragma unroll
         for (int off = G / 2; off > 0; off >>= 1) {
@@ -611,12 +630,12 @@ __device__ __forceinline__ void evaluate(const EvalArgs& a, const EvalCtx& c, bo
             lp += __shfl_xor_sync(0xffffffffu, lp, off);
         }
     }
-    if (use_moments<N>()) {      // (A0, A1, A2) in the (W2, b1, W1) slots -> sum_p df z' a [x] (see point_eval); W2 slot already final
+    if (use_moments<N>() && !WSM) {      // (A0, A1, A2) in the (W2, b1, W1) slots -> sum_p df z' a [x] (see point_eval); W2 slot already final
 #pragma unroll
         for (int hp = 0; hp < N::HP; ++hp) {
             const float2 A0 = g[N::SW2 + hp], A1 = g[N::SB1 + hp], A2 = g[N::SW1 + hp];
-            g[N::SB1 + hp] = __ffma2_rn(w[N::SW1 + hp], A1, __fmul2_rn(w[N::SB1 + hp], A0));
-            g[N::SW1 + hp] = __ffma2_rn(w[N::SW1 + hp], A2, __fmul2_rn(w[N::SB1 + hp], A1));
+            g[N::SB1 + hp] = __ffma2_rn(w[WSM ? 0 : N::SW1 + hp], A1, __fmul2_rn(w[WSM ? 0 : N::SB1 + hp], A0));
+            g[N::SW1 + hp] = __ffma2_rn(w[WSM ? 0 : N::SW1 + hp], A2, __fmul2_rn(w[WSM ? 0 : N::SB1 + hp], A1));
         }
     }
     // Gaussian prior over the weights (isotropic, or the AOCP diagonal Gaussian): base.py:106-133, added to the rescaled
@@ -628,10 +647,10 @@ __device__ __forceinline__ void evaluate(const EvalArgs& a, const EvalCtx& c, bo
         const float2 diff = __fadd2_rn(q[s], make_float2(-mv.x, -mv.y));
         const float2 t = __fmul2_rn(diff, make_float2(mv.z, mv.w));
         if (s < N::SW2 && N::SK == 1) {               // accumulated without the w2 factor (point_eval)
-            const float2 sc = __fmul2_rn(q[N::SW2 + (s % N::HP)], f2(act_grad_scale<N::ACT>()));
+            const float2 sc = __fmul2_rn(q[N::SW2 + (s % N::HP)], f2(grad_scale_for<N::ACT, SC>()));
             g[s] = __ffma2_rn(g[s], sc, make_float2(-t.x, -t.y));
-        } else if (s < N::SW2 && act_grad_scale<N::ACT>() != 1.f) {
-            g[s] = __ffma2_rn(g[s], f2(act_grad_scale<N::ACT>()), make_float2(-t.x, -t.y));
+        } else if (s < N::SW2 && grad_scale_for<N::ACT, SC>() != 1.f) {
+            g[s] = __ffma2_rn(g[s], f2(grad_scale_for<N::ACT, SC>()), make_float2(-t.x, -t.y));
         } else {
             g[s] = __fadd2_rn(g[s], make_float2(-t.x, -t.y));
         }
