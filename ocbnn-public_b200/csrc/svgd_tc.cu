@@ -112,13 +112,13 @@ k_split_tf32(const float* __restrict__ x, long long rows, long long cols, long l
 
 // =========================================================================================================================
 // SVGD tensor pipeline.  Workspace layout (floats unless noted), n4 = n rounded up to 4, dp = D rounded up to 32:
-//   hdr (256 B) | mean[dp] | r[n] | s[n] | xc_hi[n x dp] | xc_lo[n x dp] | d2[n_rows x n4] | k_hi, k_lo[n_rows x n4] |
+//   hdr (256 B) | mean[dp] | r[n] | s[n] | xc[n x dp] | xc_hi[n x dp] | xc_lo[n x dp] | d2[n_rows x n4] | k_hi, k_lo[n_rows x n4] |
 //   vt_hi, vt_lo[2dp x n4] | rowsum[n_rows] | o[splits x n_rows x 2dp] | select header | select candidates[n^2/32]
 // =========================================================================================================================
 struct TcWs {
     long long n, d, n4, dp, n_rows, row_begin;
     int splits, bn;
-    float *mean, *r, *s, *xc_hi, *xc_lo, *d2, *k_hi, *k_lo, *vt_hi, *vt_lo, *rowsum, *o;
+    float *mean, *r, *s, *xc, *xc_hi, *xc_lo, *d2, *k_hi, *k_lo, *vt_hi, *vt_lo, *rowsum, *o;
     float *cand, *list2, *samples;   // bracket select: candidates, short list (cand_cap floats each), pair sample
     unsigned* ghist;                  // bracket select: linear histogram over the bracket
     unsigned long long* sel; // bracket-select header: see SelHdr
@@ -152,6 +152,7 @@ static TcWs carve(void* workspace, long long n, long long d, long long row_begin
     w.mean = take(w.dp);
     w.r = take(n);
     w.s = take(n);
+    w.xc = take(n * w.dp);
     w.xc_hi = take(n * w.dp);
     w.xc_lo = take(n * w.dp);
     w.d2 = take(n_rows * w.n4);
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(256) k_colmean(const float* __restrict__ x, lo
 
 // one warp per row: xc = x - mean split into tf32 hi/lo (zero padded to dp), r = ||xc||^2, s = sum xc
 __global__ void __launch_bounds__(256)
-k_center_split(const float* __restrict__ x, const float* __restrict__ mean, long long n, int d, int dp, float* __restrict__ hi,
+k_center_split(const float* __restrict__ x, const float* __restrict__ mean, long long n, int d, int dp, float* __restrict__ xc, float* __restrict__ hi,
                float* __restrict__ lo, float* __restrict__ r, float* __restrict__ ssum) {
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -201,6 +202,7 @@ k_center_split(const float* __restrict__ x, const float* __restrict__ mean, long
     for (int c = lane; c < dp; c += 32) {
         const float v = c < d ? x[row * d + c] - mean[c] : 0.f;
         const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        xc[row * dp + c] = v;
         hi[row * dp + c] = h;
         lo[row * dp + c] = v - h;
         rr += (double)v * (double)v;
@@ -594,33 +596,30 @@ k_sel_final(const float* __restrict__ d2, const float* __restrict__ ssum, long l
 // pass over d2 for the median.
 template <int DP>
 __global__ void __launch_bounds__(256)
-k_sel_sample_x(const float* __restrict__ hi, const float* __restrict__ lo, const float* __restrict__ ssum, long long n, int d,
-               float* __restrict__ samples) {
+k_sel_sample_x(const float* __restrict__ xc, const float* __restrict__ ssum, long long n, int d, float* __restrict__ samples) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= kSelSamples) return;
     const unsigned a = mix32((unsigned)idx * 2u + 0x9e3779b9u), b = mix32(a ^ 0x85ebca6bu);
     long long i = (long long)(a % (unsigned)n), j = (long long)(b % (unsigned)n);
     if (i == j) j = (j + 1) % n;
     if (i > j) { const long long tmp = i; i = j; j = tmp; }
-    const float4* hi4 = reinterpret_cast<const float4*>(hi);
-    const float4* lo4 = reinterpret_cast<const float4*>(lo);
+    const float4* x4 = reinterpret_cast<const float4*>(xc);
     float acc = 0.f;
 #pragma unroll
     for (int c = 0; c < DP / 4; ++c) {
-        const float4 ah = __ldg(hi4 + i * (DP / 4) + c), al = __ldg(lo4 + i * (DP / 4) + c);
-        const float4 bh = __ldg(hi4 + j * (DP / 4) + c), bl = __ldg(lo4 + j * (DP / 4) + c);
+        const float4 a = __ldg(x4 + i * (DP / 4) + c), b = __ldg(x4 + j * (DP / 4) + c);
         float e;
-        e = (ah.x + al.x) - (bh.x + bl.x); acc = fmaf(e, e, acc);
-        e = (ah.y + al.y) - (bh.y + bl.y); acc = fmaf(e, e, acc);
-        e = (ah.z + al.z) - (bh.z + bl.z); acc = fmaf(e, e, acc);
-        e = (ah.w + al.w) - (bh.w + bl.w); acc = fmaf(e, e, acc);
+        e = a.x - b.x; acc = fmaf(e, e, acc);
+        e = a.y - b.y; acc = fmaf(e, e, acc);
+        e = a.z - b.z; acc = fmaf(e, e, acc);
+        e = a.w - b.w; acc = fmaf(e, e, acc);
     }
     samples[idx] = sqrtf(fmaxf(acc + 2.f * 1e-6f * (ssum[i] - ssum[j]) + (float)d * 1e-12f, 0.f));
 }
 
 template <int DP>
 __global__ void __launch_bounds__(256)
-k_d2_sym(const float* __restrict__ hi, const float* __restrict__ lo, const float* __restrict__ ssum, long long n, long long n4, int d,
+k_d2_sym(const float* __restrict__ xc, const float* __restrict__ ssum, long long n, long long n4, int d,
          float* __restrict__ d2, SelHdr* __restrict__ hdr, float* __restrict__ cand, long long cand_cap, unsigned* __restrict__ ghist) {
     if (blockIdx.x < blockIdx.y) return;                        // tiles below the diagonal are the mirror images
     constexpr int XS = DP + 4;
@@ -631,11 +630,12 @@ k_d2_sym(const float* __restrict__ hi, const float* __restrict__ lo, const float
     float (*xj)[XS] = reinterpret_cast<float (*)[XS]>(sm_x + 64 * XS);
     const long long t0 = (long long)blockIdx.y * 64, j0 = (long long)blockIdx.x * 64;
     const bool diag = blockIdx.x == blockIdx.y;
-    for (int idx = threadIdx.x; idx < 64 * DP; idx += 256) {
-        const int rr = idx / DP, c = idx % DP;
+    for (int idx = threadIdx.x; idx < 64 * (DP / 4); idx += 256) {
+        const int rr = idx / (DP / 4), c = idx % (DP / 4);
         const long long i = t0 + rr, j = j0 + rr;
-        xi[rr][c] = i < n ? hi[i * DP + c] + lo[i * DP + c] : 0.f;
-        xj[rr][c] = j < n ? hi[j * DP + c] + lo[j * DP + c] : 0.f;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(&xi[rr][4 * c]) = i < n ? __ldg(reinterpret_cast<const float4*>(xc + i * DP) + c) : z4;
+        *reinterpret_cast<float4*>(&xj[rr][4 * c]) = j < n ? __ldg(reinterpret_cast<const float4*>(xc + j * DP) + c) : z4;
     }
     __syncthreads();
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // columns tx + 16 q, rows ty + 16 p (interleaved: conflict-free rows)
@@ -1030,19 +1030,19 @@ static int tc_prepare(const TcWs& w, const float* x, unsigned* hist0, bool* hist
     if (sel_done) *sel_done = false;
     k_colmean<<<(unsigned)w.dp, 256, 0, st>>>(x, w.n, (int)w.d, (int)w.dp, w.mean);
     OCBNN_LAUNCH_CHECK();
-    k_center_split<<<(unsigned)((w.n * 32 + 255) / 256), 256, 0, st>>>(x, w.mean, w.n, (int)w.d, (int)w.dp, w.xc_hi, w.xc_lo, w.r, w.s);
+    k_center_split<<<(unsigned)((w.n * 32 + 255) / 256), 256, 0, st>>>(x, w.mean, w.n, (int)w.d, (int)w.dp, w.xc, w.xc_hi, w.xc_lo, w.r, w.s);
     OCBNN_LAUNCH_CHECK();
     static const bool gram_small = [] { const char* e = getenv("OCBNN_SVGD_GRAM"); return e && e[0] == 't'; }();   // experiment: tensor Gram for small D too
     if (w.dp <= 64 && !gram_small && sel_mode > 0 && w.n_rows == w.n && w.row_begin == 0) {
         SelHdr* hdr = reinterpret_cast<SelHdr*>(w.sel);
-        if (w.dp == 32) k_sel_sample_x<32><<<kSelSamples / 256, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.s, w.n, (int)w.d, w.samples);
-        else k_sel_sample_x<64><<<kSelSamples / 256, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.s, w.n, (int)w.d, w.samples);
+        if (w.dp == 32) k_sel_sample_x<32><<<kSelSamples / 256, 256, 0, st>>>(w.xc, w.s, w.n, (int)w.d, w.samples);
+        else k_sel_sample_x<64><<<kSelSamples / 256, 256, 0, st>>>(w.xc, w.s, w.n, (int)w.d, w.samples);
         OCBNN_LAUNCH_CHECK();
         k_sel_bracket<<<1, 1024, 0, st>>>(w.samples, hdr, w.ghist, sel_mode == 2 ? 1 : 0);
         OCBNN_LAUNCH_CHECK();
         dim3 grid((unsigned)((w.n + 63) / 64), (unsigned)((w.n + 63) / 64));
-        if (w.dp == 32) k_d2_sym<32><<<grid, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.s, w.n, w.n4, (int)w.d, w.d2, hdr, w.cand, w.cand_cap, w.ghist);
-        else k_d2_sym<64><<<grid, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.s, w.n, w.n4, (int)w.d, w.d2, hdr, w.cand, w.cand_cap, w.ghist);
+        if (w.dp == 32) k_d2_sym<32><<<grid, 256, 0, st>>>(w.xc, w.s, w.n, w.n4, (int)w.d, w.d2, hdr, w.cand, w.cand_cap, w.ghist);
+        else k_d2_sym<64><<<grid, 256, 0, st>>>(w.xc, w.s, w.n, w.n4, (int)w.d, w.d2, hdr, w.cand, w.cand_cap, w.ghist);
         OCBNN_LAUNCH_CHECK();
         if (sel_done) *sel_done = true;
         return OCBNN_OK;

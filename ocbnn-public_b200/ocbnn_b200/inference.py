@@ -302,6 +302,21 @@ class SVGDMixin:
         prob = st["prob"]                      # compiled once per infer(): the reference also fixes data and constraints per infer()
         X = st["X"]
         tensor = st["tensor"] if use_tensor is None else E.svgd_use_tensor(int(use_tensor), st["n"]) and st["tensor"]
+        if D.world() == 1:                      # gradients (K1) on a side stream: they overlap the distance / bandwidth chain, which
+            main = torch.cuda.current_stream()  # depends on X only and has narrow kernels (the one-CTA bracket)
+            side = st.get("side")
+            if side is None:
+                side = st["side"] = torch.cuda.Stream(device=X.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                _, G = prob.logpost_grad(X, _batch_for(self, epoch), with_data, want_lp=False, out_grad=st["G"])
+            E.svgd_bandwidth(X, st["ws"], st["h"], use_tensor=1 if tensor else 0)
+            main.wait_stream(side)
+            n, lo, rows = st["n"], st["lo"], st["hi"] - st["lo"]
+            phi = E.svgd_phi(X, G, st["h"], lo, rows, st["ws"], 2 if tensor else 0, out=st["phi"])
+            E.adagrad_step(X, st["acc"], phi, self.svgd_init_lr, -1.0)
+            st["phi"] = phi
+            return st
         _, G = prob.logpost_grad(X, _batch_for(self, epoch), with_data, want_lp=False, out_grad=st["G"])
         if D.world() == 1:
             Xall, Gall = X, G
