@@ -140,6 +140,8 @@ static int pick_splits(long long n_rows, long long n4, int two_dp, int bn) {
 static int fused_splits(long long n_rows, long long n4);
 long long tc_workspace_bytes(long long n, long long d, long long n_rows);      // K splits of the fused phi kernel (defined with it)
 
+constexpr int kSelSamplesHost = 32768;      // = kSelSamples (pair sample of the bracket select, defined with its kernels)
+
 static TcWs carve(void* workspace, long long n, long long d, long long row_begin, long long n_rows) {
     TcWs w{};
     w.n = n; w.d = d; w.n4 = (n + 3) / 4 * 4; w.dp = (d + 31) / 32 * 32; w.n_rows = n_rows; w.row_begin = row_begin;
@@ -167,7 +169,7 @@ static TcWs carve(void* workspace, long long n, long long d, long long row_begin
     w.cand_cap = n_rows == n ? (n * n / 32 > (1 << 16) ? n * n / 32 : (1 << 16)) : 0;
     w.cand = take(w.cand_cap);
     w.list2 = take(w.cand_cap);
-    w.samples = take(n_rows == n ? 65536 : 0);
+    w.samples = take(n_rows == n ? kSelSamplesHost : 0);
     w.ghist = reinterpret_cast<unsigned*>(take(n_rows == n ? 4096 : 0));
     w.bytes = p - reinterpret_cast<char*>(workspace);
     return w;
@@ -323,10 +325,10 @@ k_hist_d2(const float* __restrict__ d2, const float* __restrict__ ssum, long lon
 // ---- K3a, single-rank fast path: exact lower median by bracket + count + compact ---------------------------------------
 // The radix-select histograms above pay for contention: the n(n-1)/2 distances of a particle cloud cluster in a handful of
 // top-bit bins.  With all rows on one GPU the median is found without a contended histogram:
-//   k_sel_sample   65536 pseudo-random pairs (i < j), their distances read from d2;
+//   k_sel_sample   32768 pseudo-random pairs (i < j), their distances read from d2;
 //   k_sel_bracket  one CTA histograms the sample linearly between its min and max and takes the bin edges of the sample
-//                  quantiles 0.5 -/+ 0.011 (5.6 sigma of the sample-rank error) as a bracket [lo, hi] that holds the true
-//                  median and ~2.5 % of all distances;
+//                  quantiles 0.5 -/+ 0.0155 (5.6 sigma of the sample-rank error) as a bracket [lo, hi] that holds the true
+//                  median and ~3.3 % of all distances;
 //   k_sel_count    one pass over the upper triangle of d2: counts exact zeros and values below lo in registers, appends the
 //                  values inside the bracket to a candidate list (warp-private shared-memory staging, one global atomic per
 //                  ~200 candidates) and counts them in a 4096-bin LINEAR histogram over the bracket (uniform occupancy, so
@@ -354,7 +356,7 @@ __device__ __forceinline__ unsigned mix32(unsigned x) {
     return x;
 }
 
-constexpr int kSelSamples = 65536, kSelBins = 4096;
+constexpr int kSelSamples = kSelSamplesHost, kSelBins = 4096;
 
 __global__ void __launch_bounds__(256)
 k_sel_sample(const float* __restrict__ d2, const float* __restrict__ ssum, long long n, long long n4, int d, float* __restrict__ samples) {
@@ -434,7 +436,7 @@ k_sel_bracket(const float* __restrict__ samples, SelHdr* __restrict__ hdr, unsig
     for (int k = 0; k < PT; ++k)
         if (v[k] != 0.f) atomicAdd(&sh[min(kSelBins - 1, (int)((v[k] - mn) * scale))], 1u);
     __syncthreads();
-    const float delta = 0.011f, width = scale > 0.f ? 1.f / scale : 0.f;
+    const float delta = 0.0155f, width = scale > 0.f ? 1.f / scale : 0.f;      // 5.6 sigma of the sample-rank error at 32768 samples
     const unsigned r_lo = (unsigned)fmaxf(0.f, floorf((0.5f - delta) * (float)cnt)), r_hi = min(cnt ? cnt - 1 : 0u, (unsigned)ceilf((0.5f + delta) * (float)cnt));
     unsigned long long dummy;
     const int b_lo = block_find_bin<1024, 4>(sh, r_lo, &dummy, wsum, &s_bin, &s_res);
