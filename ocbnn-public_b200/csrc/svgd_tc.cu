@@ -344,7 +344,8 @@ struct SelHdr {                 // 64 bytes in the workspace
     unsigned long long zeros, below;
     unsigned n2, bin;           // short list length, hit bin
     unsigned long long resid;   // rank inside the hit bin
-    unsigned long long pad[2];
+    float lo2, hi2;             // sqrtf(v2) >= lo  <=>  v2 >= lo2 ;  sqrtf(v2) <= hi  <=>  v2 <= hi2  (exact, see k_sel_bracket)
+    unsigned long long pad[1];
 };
 
 __device__ __forceinline__ float pair_dist(const float* __restrict__ d2, const float* __restrict__ ssum, long long n4, int d, long long i, long long j) {
@@ -446,6 +447,17 @@ k_sel_bracket(const float* __restrict__ samples, SelHdr* __restrict__ hdr, unsig
         if (cnt == 0) { lo = 0.f; hi = 0.f; }
         if (sabotage) { lo = mx * 4.f + 1.f; hi = mx * 8.f + 2.f; }
         hdr->lo = lo; hdr->hi = hi;
+        // the counting pass classifies in the squared domain (no sqrt per pair): sqrtf is monotone, so the smallest float whose
+        // root reaches lo and the largest whose root does not exceed hi give exactly the same classification
+        float a = lo * lo, b = hi * hi;
+        for (int it = 0; it < 8 && a > 0.f && sqrtf(a) >= lo; ++it) a = __uint_as_float(__float_as_uint(a) - 1u);
+        for (int it = 0; it < 16 && sqrtf(a) < lo; ++it) a = __uint_as_float(__float_as_uint(a) + 1u);
+        for (int it = 0; it < 8 && sqrtf(b) <= hi; ++it) b = __uint_as_float(__float_as_uint(b) + 1u);
+        for (int it = 0; it < 16 && b > 0.f && sqrtf(b) > hi; ++it) b = __uint_as_float(__float_as_uint(b) - 1u);
+        const bool exact = (lo == 0.f || (sqrtf(a) >= lo && (a == 0.f || sqrtf(__uint_as_float(__float_as_uint(a) - 1u)) < lo))) &&
+                           sqrtf(b) <= hi && sqrtf(__uint_as_float(__float_as_uint(b) + 1u)) > hi;
+        hdr->lo2 = exact ? a : -1.f;              // -1: thresholds not established (never observed) -> the pass takes the sqrt
+        hdr->hi2 = b;
         hdr->ncand = 0u; hdr->overflow = 0u; hdr->zeros = 0ull; hdr->below = 0ull; hdr->n2 = 0u; hdr->bin = 0u; hdr->resid = 0ull;
     }
 }
@@ -624,47 +636,54 @@ __global__ void __launch_bounds__(256)
 k_d2_sym(const float* __restrict__ xc, const float* __restrict__ ssum, long long n, long long n4, int d,
          float* __restrict__ d2, SelHdr* __restrict__ hdr, float* __restrict__ cand, long long cand_cap, unsigned* __restrict__ ghist) {
     if (blockIdx.x < blockIdx.y) return;                        // tiles below the diagonal are the mirror images
-    constexpr int XS = DP + 4;
-    __shared__ __align__(16) float sm_x[2 * 64 * (XS > 33 ? XS : 33)];           // xi | xj, later the 64 x 65 tile of the mirror
+    // operands transposed in shared memory, [dim][row'] with row' = 4 (row % 16) + row / 16, so that the 4 rows (4 columns) of a
+    // thread's register tile are ONE LDS.128 per dimension and the difference / square-accumulate run as packed FADD2 / FFMA2
+    constexpr int RS = 64 + 4;
+    __shared__ __align__(16) float sm_x[(2 * DP * RS > 64 * 65) ? 2 * DP * RS : 64 * 65];     // xiT | xjT, later the 64 x 65 tile of the mirror
     __shared__ float stage[8][256];
     __shared__ unsigned long long red[2][8];
-    float (*xi)[XS] = reinterpret_cast<float (*)[XS]>(sm_x);
-    float (*xj)[XS] = reinterpret_cast<float (*)[XS]>(sm_x + 64 * XS);
+    float (*xiT)[RS] = reinterpret_cast<float (*)[RS]>(sm_x);
+    float (*xjT)[RS] = reinterpret_cast<float (*)[RS]>(sm_x + DP * RS);
     const long long t0 = (long long)blockIdx.y * 64, j0 = (long long)blockIdx.x * 64;
     const bool diag = blockIdx.x == blockIdx.y;
     for (int idx = threadIdx.x; idx < 64 * (DP / 4); idx += 256) {
-        const int rr = idx / (DP / 4), c = idx % (DP / 4);
+        const int rr = idx % 64, c = idx / 64;                 // consecutive threads: consecutive rows (conflict-free transposed stores)
+        const int rp = 4 * (rr & 15) + (rr >> 4);
         const long long i = t0 + rr, j = j0 + rr;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(&xi[rr][4 * c]) = i < n ? __ldg(reinterpret_cast<const float4*>(xc + i * DP) + c) : z4;
-        *reinterpret_cast<float4*>(&xj[rr][4 * c]) = j < n ? __ldg(reinterpret_cast<const float4*>(xc + j * DP) + c) : z4;
+        const float4 a = i < n ? __ldg(reinterpret_cast<const float4*>(xc + i * DP) + c) : z4;
+        const float4 b = j < n ? __ldg(reinterpret_cast<const float4*>(xc + j * DP) + c) : z4;
+        xiT[4 * c + 0][rp] = a.x; xiT[4 * c + 1][rp] = a.y; xiT[4 * c + 2][rp] = a.z; xiT[4 * c + 3][rp] = a.w;
+        xjT[4 * c + 0][rp] = b.x; xjT[4 * c + 1][rp] = b.y; xjT[4 * c + 2][rp] = b.z; xjT[4 * c + 3][rp] = b.w;
     }
     __syncthreads();
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // columns tx + 16 q, rows ty + 16 p (interleaved: conflict-free rows)
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // columns tx + 16 q, rows ty + 16 p
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float acc[4][4] = {};
+    float2 acc2[4][2];
 #pragma unroll
-    for (int c = 0; c < DP; c += 4) {
-        float4 a[4], b[4];
+    for (int p = 0; p < 4; ++p) acc2[p][0] = acc2[p][1] = make_float2(0.f, 0.f);
+#pragma unroll 8
+    for (int c = 0; c < DP; ++c) {
+        const float4 a = *reinterpret_cast<const float4*>(&xiT[c][4 * ty]);
+        const float4 b = *reinterpret_cast<const float4*>(&xjT[c][4 * tx]);
+        const float2 b01 = make_float2(b.x, b.y), b23 = make_float2(b.z, b.w);
+        const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-        for (int p = 0; p < 4; ++p) a[p] = *reinterpret_cast<const float4*>(&xi[ty + 16 * p][c]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4*>(&xj[tx + 16 * q][c]);
-#pragma unroll
-        for (int p = 0; p < 4; ++p)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float e;
-                e = a[p].x - b[q].x; acc[p][q] = fmaf(e, e, acc[p][q]);
-                e = a[p].y - b[q].y; acc[p][q] = fmaf(e, e, acc[p][q]);
-                e = a[p].z - b[q].z; acc[p][q] = fmaf(e, e, acc[p][q]);
-                e = a[p].w - b[q].w; acc[p][q] = fmaf(e, e, acc[p][q]);
-            }
+        for (int p = 0; p < 4; ++p) {
+            const float2 na = make_float2(-av[p], -av[p]);
+            const float2 e0 = __fadd2_rn(b01, na), e1 = __fadd2_rn(b23, na);
+            acc2[p][0] = __ffma2_rn(e0, e0, acc2[p][0]);
+            acc2[p][1] = __ffma2_rn(e1, e1, acc2[p][1]);
+        }
     }
-    // ---- the tile itself, and the classification of its pairs i < j ----
-    const float lo_b = hdr->lo, hi_b = hdr->hi;
+    float acc[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { acc[p][0] = acc2[p][0].x; acc[p][1] = acc2[p][0].y; acc[p][2] = acc2[p][1].x; acc[p][3] = acc2[p][1].y; }
+    // ---- the tile itself, and the classification of its pairs i < j (squared domain; only candidates take the root) ----
+    const float lo_b = hdr->lo, hi_b = hdr->hi, lo2 = hdr->lo2, hi2 = hdr->hi2;
+    const bool sq = lo2 >= 0.f;
     const float scale = hi_b > lo_b ? (float)kSelBins / (hi_b - lo_b) : 0.f;
-    const float eps = 1e-6f, deps2 = (float)d * 1e-12f;
+    const float eps2 = 2e-6f, deps2 = (float)d * 1e-12f;
     float si[4], sj[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) si[p] = t0 + ty + 16 * p < n ? ssum[t0 + ty + 16 * p] : 0.f;
@@ -683,21 +702,29 @@ k_d2_sym(const float* __restrict__ xc, const float* __restrict__ ssum, long long
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         const long long t = t0 + ty + 16 * p;
+        float* drow = d2 + t * n4 + j0 + tx;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const long long j = j0 + tx + 16 * q;
-            if (t < n && j < n4) d2[t * n4 + j] = j < n ? acc[p][q] : 0.f;
+            if (t < n && j < n4) drow[16 * q] = j < n ? acc[p][q] : 0.f;
             bool is_c = false;
-            float v = 0.f;
+            const float v2 = fmaxf(acc[p][q] + eps2 * (si[p] - sj[q]) + deps2, 0.f);      // same expression as k_hist_d2 / k_sel_count
             if (t < n && j < n && j > t) {
-                v = sqrtf(fmaxf(acc[p][q] + 2.f * eps * (si[p] - sj[q]) + deps2, 0.f));
-                if (v == 0.f) ++zeros;
-                else if (v < lo_b) ++below;
-                else is_c = v <= hi_b;
+                if (sq) {
+                    if (v2 == 0.f) ++zeros;
+                    else if (v2 < lo2) ++below;
+                    else is_c = v2 <= hi2;
+                } else {
+                    const float v = sqrtf(v2);
+                    if (v == 0.f) ++zeros;
+                    else if (v < lo_b) ++below;
+                    else is_c = v <= hi_b;
+                }
             }
             const unsigned m = __ballot_sync(0xffffffffu, is_c);
             if (m) {
                 if (is_c) {
+                    const float v = sqrtf(v2);
                     stage[warp][staged + __popc(m & ((1u << lane) - 1u))] = v;
                     atomicAdd(&ghist[sel_lbin(v, lo_b, scale)], 1u);
                 }
@@ -715,7 +742,7 @@ k_d2_sym(const float* __restrict__ xc, const float* __restrict__ ssum, long long
         b += __shfl_xor_sync(0xffffffffu, b, off);
     }
     if (lane == 0) { red[0][warp] = z; red[1][warp] = b; }
-    __syncthreads();                                             // also: everybody is done with xi / xj
+    __syncthreads();                                             // also: everybody is done with xiT / xjT
     if (threadIdx.x == 0) {
         z = 0; b = 0;
         for (int w = 0; w < 8; ++w) { z += red[0][w]; b += red[1][w]; }
