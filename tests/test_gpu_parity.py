@@ -351,3 +351,35 @@ def test_k6_aocp_at_recid_scale():
     lo, go = orc.aocp_objective_binary(spec, g["aocp_params"], prob=dict(xs=xs, p=xs[:, 1]), dtype=np.float64)
     assert abs(float(loss) - lo) <= 2e-5 * abs(lo)
     assert rel_err(grad.cpu().numpy().T, go.T).max() < 1e-4
+
+
+def test_hmc_run_host_samples_and_svgd_graph_equivalence():
+    """hmc_run(samples_host=...) delivers the same samples as the device tensor it returns; the CUDA-graph replay of the SVGD
+    epoch is bit-identical to the eager epoch."""
+    import os, tempfile
+    from ocbnn_b200 import workloads
+    os.chdir(tempfile.mkdtemp())
+    m = workloads.build("W2", seed=0)
+    m.update_config(rng="device", hmc_l=5)
+    M, n_it = 257, 6
+    q = (0.5 * torch.randn(M, m.nweights, generator=torch.Generator().manual_seed(2))).cuda()
+    host = torch.empty(n_it // 2, M, m.nweights).pin_memory()
+    torch.manual_seed(11)
+    acc, smp = m.hmc_run(q, n_it, True, collect_every=2, chunk=2, samples_host=host)
+    torch.cuda.synchronize()
+    assert smp.shape == host.shape and torch.equal(smp.cpu(), host)
+    assert int(acc.sum()) > 0
+
+    ms = workloads.build("W4", seed=0, infer_nsamples=1100)
+    X0 = torch.randn(1100, ms.nweights, generator=torch.Generator().manual_seed(3))
+    st_g = ms.svgd_setup(X0)
+    ms.update_config(svgd_graph=False)
+    st_e = ms.svgd_setup(X0)
+    for ep in range(1, 6):                      # graph path: eager, capture + replay, replay, ...
+        ms.update_config(svgd_graph=True)
+        ms.svgd_epoch(st_g, ep, True)
+        ms.update_config(svgd_graph=False)
+        ms.svgd_epoch(st_e, ep, True)
+    torch.cuda.synchronize()
+    assert "graphs" in st_g and any(not isinstance(v, str) for v in st_g["graphs"].values())
+    assert torch.equal(st_g["X"], st_e["X"]) and torch.equal(st_g["h"], st_e["h"])
