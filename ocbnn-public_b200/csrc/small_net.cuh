@@ -235,24 +235,78 @@ struct FastHead<OCBNN_HEAD_POS_GAUSS, SK> {
         head_pos_gauss(f[0], prm, hc, val, df[0]);
     }
 };
+// log-softmax with MUFU approximations (ex2 / lg2 / rcp, ~2^-22 relative): ~25 instructions for SK = 3 instead of ~100 with
+// expf / logf / IEEE reciprocal; the classifier kernels are fma-pipe/issue bound, and the heads were 40 % of their instructions
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <int SK>
+__device__ __forceinline__ void log_softmax_fast(const float (&f)[SK], float (&p)[SK], float (&logp)[SK]) {
+    float mx = f[0];
+#pragma unroll
+    for (int k = 1; k < SK; ++k) mx = fmaxf(mx, f[k]);
+    float t[SK], se = 0.f;
+#pragma unroll
+    for (int k = 0; k < SK; ++k) {
+        t[k] = (f[k] - mx) * 1.4426950408889634f;
+        p[k] = ex2_approx(t[k]);
+        se += p[k];
+    }
+    const float l2 = lg2_approx(se), rs = rcp_approx(se);
+#pragma unroll
+    for (int k = 0; k < SK; ++k) {
+        logp[k] = (t[k] - l2) * 0.6931471805599453f;
+        p[k] *= rs;
+    }
+}
+// positive_dirichlet_cocp (base.py:498-511), see heads.cuh::head_dirichlet
 template <int SK>
 struct FastHead<OCBNN_HEAD_DIRICHLET, SK> {
     static __device__ __forceinline__ void run(const float (&f)[SK], const float* __restrict__ prm, const FastConsts&, float& val, float (&df)[SK]) {
-        head_dirichlet<SK>(f, prm, val, df);
+        float p[SK], logp[SK];
+        log_softmax_fast<SK>(f, p, logp);
+        float tot = 0.f;
+        val = 0.f;
+#pragma unroll
+        for (int k = 0; k < SK; ++k) {
+            tot += prm[k];
+            val = fmaf(prm[k], logp[k], val);
+        }
+#pragma unroll
+        for (int k = 0; k < SK; ++k) df[k] = fmaf(-tot, p[k], prm[k]);
     }
 };
+// ClassifierMixin.log_likelihood (base.py:432-444), see heads.cuh::head_lik_softmax
 template <int SK>
 struct FastHead<OCBNN_HEAD_LIK_SOFTMAX, SK> {
     static __device__ __forceinline__ void run(const float (&f)[SK], const float* __restrict__ prm, const FastConsts&, float& val, float (&df)[SK]) {
-        head_lik_softmax<SK>(f, prm, val, df);
+        float p[SK], logp[SK];
+        log_softmax_fast<SK>(f, p, logp);
+        const int y = (int)prm[0];
+        val = 0.f;
+#pragma unroll
+        for (int k = 0; k < SK; ++k) {
+            const bool hit = k == y;
+            val = hit ? logp[k] : val;
+            df[k] = (hit ? 1.f : 0.f) - p[k];
+        }
     }
 };
+// BinaryClassifierMixin.log_likelihood (base.py:524-542) in the overflow-free form t z - softplus(z), see heads.cuh::head_lik_bernoulli
 template <int SK>
 struct FastHead<OCBNN_HEAD_LIK_BERNOULLI, SK> {
     static __device__ __forceinline__ void run(const float (&f)[SK], const float* __restrict__ prm, const FastConsts&, float& val, float (&df)[SK]) {
 #pragma unroll
         for (int k = 0; k < SK; ++k) df[k] = 0.f;
-        head_lik_bernoulli(f[0], prm, val, df[0]);
+        const float z = f[0], t = prm[0];
+        const float e = ex2_approx(-fabsf(z) * 1.4426950408889634f);        // in (0,1]
+        const float ope = 1.f + e;
+        const float sp = fmaf(lg2_approx(ope), 0.6931471805599453f, fmaxf(z, 0.f));   // softplus(z)
+        const float r = rcp_approx(ope);
+        val = fmaf(t, z, -sp);
+        df[0] = t - ((z >= 0.f) ? r : e * r);
     }
 };
 
