@@ -288,10 +288,10 @@ struct SmallLaunch {
             static const int mb = [] { const char* e = getenv("OCBNN_HMC_MB"); return e ? atoi(e) : (N::NS > 24 ? 2 : N::NS > 18 ? 3 : kDefaultHmcMb); }();
             static const int uu = [] { const char* e = getenv("OCBNN_HMC_U"); return e ? atoi(e) : kDefaultHmcU; }();
 #define OCBNN_HMC_GO(MBV, UV) return hmc_mb<1, MBV, UV>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st)
-            // wide nets, default: weights read from the thread's shared-memory column (WSM) at 3 CTAs/SM; OCBNN_HMC_MB=2 selects the
-            // register-weights kernel at 2 CTAs/SM
-            static const bool wsm = N::NS > 24 && !getenv("OCBNN_HMC_MB");
-            // (measured on W3: WSM at 3 CTAs/SM 0.758 G steps/s = register weights at 2 CTAs/SM 0.759 G; WSM at 4 CTAs/SM spills: 0.53-0.63 G)
+            // wide nets: OCBNN_HMC_WSM=1 selects the variant that reads the weights from the thread's shared-memory column (WSM) at
+            // 3 CTAs/SM.  Measured on W3 after the MUFU heads: register weights at 2 CTAs/SM 0.974 G steps/s, WSM at 3 CTAs/SM 0.890 G
+            // (45 extra LDS per point), WSM at 4 CTAs/SM spills (0.53-0.63 G).  Default: register weights.
+            static const bool wsm = N::NS > 24 && getenv("OCBNN_HMC_WSM") != nullptr;
             if (wsm) return hmc_mb<1, (N::NS > 24 ? 3 : 4), 2, (N::NS > 24)>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
             if (mb <= 2) { if (uu <= 1) OCBNN_HMC_GO(2, 1); OCBNN_HMC_GO(2, 2); }
             if (mb == 3) { if (uu <= 1) OCBNN_HMC_GO(3, 1); if (uu <= 2) OCBNN_HMC_GO(3, 2); OCBNN_HMC_GO(3, 4); }
