@@ -5,6 +5,7 @@
 // invariant; centring removes the cancellation in the Gram form of the distance).  The exact fp32 SIMT arm in svgd.cu is
 // the parity reference of this path.  Also exports the GEMM building block itself for testing.
 #include <cstdlib>
+#include <type_traits>
 #include <cudaTypedefs.h>
 #include "tc_gemm.cuh"
 
@@ -344,13 +345,17 @@ struct SelHdr {                 // 64 bytes in the workspace
     unsigned long long zeros, below;
     unsigned n2, bin;           // short list length, hit bin
     unsigned long long resid;   // rank inside the hit bin
-    float lo2, hi2;             // sqrtf(v2) >= lo  <=>  v2 >= lo2 ;  sqrtf(v2) <= hi  <=>  v2 <= hi2  (exact, see k_sel_bracket)
-    unsigned long long pad[1];
+    unsigned long long pad[2];
 };
+// The whole select works on w = d^2 (the eps-perturbed SQUARED distance): sqrt is monotone, so the k-th smallest distance is
+// the root of the k-th smallest w, exact zeros are the same pairs, and no pair needs a square root - only the answer does.
 
-__device__ __forceinline__ float pair_dist(const float* __restrict__ d2, const float* __restrict__ ssum, long long n4, int d, long long i, long long j) {
+__device__ __forceinline__ float pair_w(float d2v, float si, float sj, int d) {        // ||x_i - x_j + eps||^2 from the centred form
     const float eps = 1e-6f, deps2 = (float)d * 1e-12f;
-    return sqrtf(fmaxf(d2[i * n4 + j] + 2.f * eps * (ssum[i] - ssum[j]) + deps2, 0.f));
+    return fmaxf(d2v + 2.f * eps * (si - sj) + deps2, 0.f);
+}
+__device__ __forceinline__ float pair_dist(const float* __restrict__ d2, const float* __restrict__ ssum, long long n4, int d, long long i, long long j) {
+    return pair_w(d2[i * n4 + j], ssum[i], ssum[j], d);
 }
 __device__ __forceinline__ unsigned mix32(unsigned x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
@@ -447,17 +452,6 @@ k_sel_bracket(const float* __restrict__ samples, SelHdr* __restrict__ hdr, unsig
         if (cnt == 0) { lo = 0.f; hi = 0.f; }
         if (sabotage) { lo = mx * 4.f + 1.f; hi = mx * 8.f + 2.f; }
         hdr->lo = lo; hdr->hi = hi;
-        // the counting pass classifies in the squared domain (no sqrt per pair): sqrtf is monotone, so the smallest float whose
-        // root reaches lo and the largest whose root does not exceed hi give exactly the same classification
-        float a = lo * lo, b = hi * hi;
-        for (int it = 0; it < 8 && a > 0.f && sqrtf(a) >= lo; ++it) a = __uint_as_float(__float_as_uint(a) - 1u);
-        for (int it = 0; it < 16 && sqrtf(a) < lo; ++it) a = __uint_as_float(__float_as_uint(a) + 1u);
-        for (int it = 0; it < 8 && sqrtf(b) <= hi; ++it) b = __uint_as_float(__float_as_uint(b) + 1u);
-        for (int it = 0; it < 16 && b > 0.f && sqrtf(b) > hi; ++it) b = __uint_as_float(__float_as_uint(b) - 1u);
-        const bool exact = (lo == 0.f || (sqrtf(a) >= lo && (a == 0.f || sqrtf(__uint_as_float(__float_as_uint(a) - 1u)) < lo))) &&
-                           sqrtf(b) <= hi && sqrtf(__uint_as_float(__float_as_uint(b) + 1u)) > hi;
-        hdr->lo2 = exact ? a : -1.f;              // -1: thresholds not established (never observed) -> the pass takes the sqrt
-        hdr->hi2 = b;
         hdr->ncand = 0u; hdr->overflow = 0u; hdr->zeros = 0ull; hdr->below = 0ull; hdr->n2 = 0u; hdr->bin = 0u; hdr->resid = 0ull;
     }
 }
@@ -472,7 +466,6 @@ k_sel_count(const float* __restrict__ d2, const float* __restrict__ ssum, long l
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float lo = hdr->lo, hi = hdr->hi;
     const float scale = hi > lo ? (float)kSelBins / (hi - lo) : 0.f;
-    const float eps = 1e-6f, deps2 = (float)d * 1e-12f;
     unsigned zeros = 0, below = 0, staged = 0;      // staged: warp-uniform
     auto flush = [&]() {
         unsigned base = 0;
@@ -490,7 +483,7 @@ k_sel_count(const float* __restrict__ d2, const float* __restrict__ ssum, long l
             bool is_c = false;
             float v = 0.f;
             if (j > i && j < n) {
-                v = sqrtf(fmaxf(d2[i * n4 + j] + 2.f * eps * (si - ssum[j]) + deps2, 0.f));
+                v = pair_w(d2[i * n4 + j], si, ssum[j], d);
                 if (v == 0.f) ++zeros;
                 else if (v < lo) ++below;
                 else is_c = v <= hi;
@@ -594,7 +587,7 @@ k_sel_final(const float* __restrict__ d2, const float* __restrict__ ssum, long l
             const int b = block_find_bin<1024, 2>(sh, r, &r, wsum, &s_bin, &s_res);
             prefix |= pass == 0 ? ((unsigned)b << 21) : pass == 1 ? ((unsigned)b << 10) : (unsigned)b;
         }
-        med = __uint_as_float(prefix);
+        med = sqrtf(__uint_as_float(prefix));           // the select ran on squared distances
     }
     if (t == 0) {
         if (out_h) *out_h = __fdiv_rn(__fmul_rn(med, med), (float)log((double)n));
@@ -628,7 +621,7 @@ k_sel_sample_x(const float* __restrict__ xc, const float* __restrict__ ssum, lon
         e = a.z - b.z; acc = fmaf(e, e, acc);
         e = a.w - b.w; acc = fmaf(e, e, acc);
     }
-    samples[idx] = sqrtf(fmaxf(acc + 2.f * 1e-6f * (ssum[i] - ssum[j]) + (float)d * 1e-12f, 0.f));
+    samples[idx] = pair_w(acc, ssum[i], ssum[j], d);
 }
 
 template <int DP>
@@ -640,14 +633,20 @@ k_d2_sym(const float* __restrict__ xc, const float* __restrict__ ssum, long long
     // thread's register tile are ONE LDS.128 per dimension and the difference / square-accumulate run as packed FADD2 / FFMA2
     constexpr int RS = 64 + 4;
     __shared__ __align__(16) float sm_x[(2 * DP * RS > 64 * 65) ? 2 * DP * RS : 64 * 65];     // xiT | xjT, later the 64 x 65 tile of the mirror
-    __shared__ float stage[8][256];
+    constexpr unsigned kStageCap = 2048;
+    __shared__ float stage[kStageCap];
     __shared__ unsigned long long red[2][8];
+    __shared__ unsigned s_cnt, s_base;
+    if (threadIdx.x == 0) s_cnt = 0u;
     float (*xiT)[RS] = reinterpret_cast<float (*)[RS]>(sm_x);
     float (*xjT)[RS] = reinterpret_cast<float (*)[RS]>(sm_x + DP * RS);
     const long long t0 = (long long)blockIdx.y * 64, j0 = (long long)blockIdx.x * 64;
     const bool diag = blockIdx.x == blockIdx.y;
     for (int idx = threadIdx.x; idx < 64 * (DP / 4); idx += 256) {
-        const int rr = idx % 64, c = idx / 64;                 // consecutive threads: consecutive rows (conflict-free transposed stores)
+        // a warp takes rows {0-7, 16-23, 32-39, 48-55} (+8 on odd turns) of one 4-dimension chunk: their transposed positions
+        // rp are 32 different banks, so the scalar transposed stores below are conflict free
+        const int g = idx & 31, blk = idx >> 5;
+        const int rr = (g & 7) + 16 * (g >> 3) + 8 * (blk & 1), c = blk >> 1;
         const int rp = 4 * (rr & 15) + (rr >> 4);
         const long long i = t0 + rr, j = j0 + rr;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -679,62 +678,52 @@ k_d2_sym(const float* __restrict__ xc, const float* __restrict__ ssum, long long
     float acc[4][4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) { acc[p][0] = acc2[p][0].x; acc[p][1] = acc2[p][0].y; acc[p][2] = acc2[p][1].x; acc[p][3] = acc2[p][1].y; }
-    // ---- the tile itself, and the classification of its pairs i < j (squared domain; only candidates take the root) ----
-    const float lo_b = hdr->lo, hi_b = hdr->hi, lo2 = hdr->lo2, hi2 = hdr->hi2;
-    const bool sq = lo2 >= 0.f;
+    // ---- the tile itself, and the classification of its pairs i < j (on squared distances; branch-free counting, one
+    //      staging flush per warp: at most 16 x 32 candidates) ----
+    const float lo_b = hdr->lo, hi_b = hdr->hi;
     const float scale = hi_b > lo_b ? (float)kSelBins / (hi_b - lo_b) : 0.f;
-    const float eps2 = 2e-6f, deps2 = (float)d * 1e-12f;
     float si[4], sj[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) si[p] = t0 + ty + 16 * p < n ? ssum[t0 + ty + 16 * p] : 0.f;
 #pragma unroll
     for (int q = 0; q < 4; ++q) sj[q] = j0 + tx + 16 * q < n ? ssum[j0 + tx + 16 * q] : 0.f;
-    unsigned zeros = 0, below = 0, staged = 0;                  // staged: warp-uniform
-    auto flush = [&]() {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&hdr->ncand, staged);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if ((long long)base + staged > cand_cap) { if (lane == 0) hdr->overflow = 1u; }
-        else for (unsigned k = lane; k < staged; k += 32) cand[base + k] = stage[warp][k];
-        __syncwarp();
-        staged = 0;
-    };
+    // candidates are staged per CTA (shared-memory counter) and appended with ONE global atomic per CTA: per-warp appends put
+    // ~16 K atomics on the same address at n = 4096 (2 M at n = 32768) and serialised in the L2
+    unsigned zeros = 0, below = 0;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // interior tiles strictly above the diagonal (all but O(n/64) of them) need no bounds or j > i tests
+    const bool interior = !diag && t0 + 64 <= n && j0 + 64 <= n;
+    auto classify = [&](auto interior_tag) {
+        constexpr bool IN = decltype(interior_tag)::value;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const long long t = t0 + ty + 16 * p;
-        float* drow = d2 + t * n4 + j0 + tx;
+        for (int p = 0; p < 4; ++p) {
+            const long long t = t0 + ty + 16 * p;
+            float* drow = d2 + t * n4 + j0 + tx;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const long long j = j0 + tx + 16 * q;
-            if (t < n && j < n4) drow[16 * q] = j < n ? acc[p][q] : 0.f;
-            bool is_c = false;
-            const float v2 = fmaxf(acc[p][q] + eps2 * (si[p] - sj[q]) + deps2, 0.f);      // same expression as k_hist_d2 / k_sel_count
-            if (t < n && j < n && j > t) {
-                if (sq) {
-                    if (v2 == 0.f) ++zeros;
-                    else if (v2 < lo2) ++below;
-                    else is_c = v2 <= hi2;
-                } else {
-                    const float v = sqrtf(v2);
-                    if (v == 0.f) ++zeros;
-                    else if (v < lo_b) ++below;
-                    else is_c = v <= hi_b;
+            for (int q = 0; q < 4; ++q) {
+                const long long j = j0 + tx + 16 * q;
+                if (IN) drow[16 * q] = acc[p][q];
+                else if (t < n && j < n4) drow[16 * q] = j < n ? acc[p][q] : 0.f;
+                const float v = pair_w(acc[p][q], si[p], sj[q], d);
+                const bool valid = IN || (t < n && j < n && j > t);
+                zeros += (valid && v == 0.f) ? 1u : 0u;
+                below += (valid && v > 0.f && v < lo_b) ? 1u : 0u;
+                const bool is_c = valid && v >= lo_b && v <= hi_b && v > 0.f;
+                const unsigned m = __ballot_sync(0xffffffffu, is_c);
+                if (m) {
+                    unsigned wb = 0;
+                    if (lane == 0) wb = atomicAdd(&s_cnt, (unsigned)__popc(m));
+                    wb = __shfl_sync(0xffffffffu, wb, 0);
+                    if (is_c) {
+                        const unsigned pos = wb + __popc(m & lt_mask);
+                        if (pos < kStageCap) stage[pos] = v;
+                        atomicAdd(&ghist[sel_lbin(v, lo_b, scale)], 1u);
+                    }
                 }
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, is_c);
-            if (m) {
-                if (is_c) {
-                    const float v = sqrtf(v2);
-                    stage[warp][staged + __popc(m & ((1u << lane) - 1u))] = v;
-                    atomicAdd(&ghist[sel_lbin(v, lo_b, scale)], 1u);
-                }
-                staged += __popc(m);
-                __syncwarp();
-                if (staged > 256 - 32) flush();
             }
         }
-    }
-    if (staged) flush();
+    };
+    if (interior) classify(std::true_type{}); else classify(std::false_type{});
     unsigned long long z = zeros, b = below;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -742,13 +731,22 @@ k_d2_sym(const float* __restrict__ xc, const float* __restrict__ ssum, long long
         b += __shfl_xor_sync(0xffffffffu, b, off);
     }
     if (lane == 0) { red[0][warp] = z; red[1][warp] = b; }
-    __syncthreads();                                             // also: everybody is done with xiT / xjT
+    __syncthreads();                                             // also: everybody is done with xiT / xjT, staging complete
+    const unsigned cnt = s_cnt;
     if (threadIdx.x == 0) {
         z = 0; b = 0;
         for (int w = 0; w < 8; ++w) { z += red[0][w]; b += red[1][w]; }
         if (z) atomicAdd(&hdr->zeros, z);
         if (b) atomicAdd(&hdr->below, b);
+        unsigned base = 0;
+        if (cnt) base = atomicAdd(&hdr->ncand, cnt);
+        if (cnt > kStageCap || (long long)base + cnt > cand_cap) { hdr->overflow = 1u; base = 0xFFFFFFFFu; }
+        s_base = base;
     }
+    __syncthreads();
+    if (cnt && s_base != 0xFFFFFFFFu)
+        for (unsigned k = threadIdx.x; k < cnt; k += 256) cand[s_base + k] = stage[k];
+    __syncthreads();                                             // stage / sm_x are reused below
     if (diag) return;
     // ---- mirror image: d2[j][t] = d2[t][j], transposed through shared memory so that both writes are coalesced ----
     float (*tile)[65] = reinterpret_cast<float (*)[65]>(sm_x);
@@ -758,11 +756,16 @@ k_d2_sym(const float* __restrict__ xc, const float* __restrict__ ssum, long long
         for (int q = 0; q < 4; ++q) tile[ty + 16 * p][tx + 16 * q] = acc[p][q];
     __syncthreads();
     const int col = threadIdx.x & 63;
+    float* mrow = d2 + (j0 + (threadIdx.x >> 6)) * n4 + t0 + col;
 #pragma unroll 4
     for (int rr = 0; rr < 16; ++rr) {
         const int row = (threadIdx.x >> 6) + 4 * rr;
-        const long long jg = j0 + row, tg = t0 + col;           // row jg of d2, column tg
-        if (jg < n && tg < n4) d2[jg * n4 + tg] = tg < n ? tile[col][row] : 0.f;
+        if (interior) {
+            mrow[(long long)(4 * rr) * n4] = tile[col][row];
+        } else {
+            const long long jg = j0 + row, tg = t0 + col;       // row jg of d2, column tg
+            if (jg < n && tg < n4) d2[jg * n4 + tg] = tg < n ? tile[col][row] : 0.f;
+        }
     }
 }
 
