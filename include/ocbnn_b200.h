@@ -172,6 +172,19 @@ OCBNN_API int ocbnn_svgd_select_update(int32_t pass, uint32_t *hist, uint64_t *s
  * hold (bracket hit, candidates, values below the bracket, exact zeros). */
 OCBNN_API int ocbnn_svgd_bandwidth(const float *x, int64_t n, int64_t d, float *out_h, int32_t use_tensor, void *workspace,
                                    int64_t workspace_bytes, void *stream);
+/* Bracket select across ranks (tensor path; every rank holds all particles and the distances of rows [row_begin, row_begin + n_rows),
+ * left in `workspace` by ocbnn_svgd_prepare).  Stage 1 samples the bracket from X (identical on every rank), counts this rank's pairs
+ * and returns the device reduce buffer (reduce_words u64: counters + linear histogram) which the caller all-reduces as int64 sums;
+ * stage 2 gathers this rank's candidates of the hit bin; stage 3 is a 3-pass radix select over those short lists: _sel_hist fills
+ * hist[pass] (2048 u32, all-reduced by the caller), _sel_update advances the select state and, after pass 2, writes h.  If the bracket
+ * missed, stage 3 runs over the distance rows instead (same result).  Replaces inference.py:208-217 for sharded particles. */
+OCBNN_API int ocbnn_svgd_sel_count(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, void *workspace, uint64_t **reduce_buf,
+                                   int64_t *reduce_words, void *stream);
+OCBNN_API int ocbnn_svgd_sel_gather(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, void *workspace, void *stream);
+OCBNN_API int ocbnn_svgd_sel_hist(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t pass, uint32_t *hist, uint64_t *select_state,
+                                  void *workspace, void *stream);
+OCBNN_API int ocbnn_svgd_sel_update(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t pass, const uint32_t *hist,
+                                    uint64_t *select_state, void *workspace, float *out_h, void *stream);
 /* median-select algorithm of ocbnn_svgd_bandwidth's tensor path: 1 bracket select (default), 0 the 3-pass radix select,
  * 2 bracket select with a sabotaged bracket (exercises the fallback; tests).  mode < 0 queries.  Returns the previous mode. */
 OCBNN_API int ocbnn_svgd_select_mode(int32_t mode);

@@ -369,6 +369,12 @@ int tc_svgd_phi(const float* g, const float* h, long long n, long long d, long l
 int tc_svgd_select_fast(long long n, long long d, void* ws, float* out_h, int mode, unsigned long long* dbg, cudaStream_t st);
 int tc_svgd_prepare_select(const float* x, long long n, long long d, void* ws, long long ws_bytes, float* out_h, int mode, unsigned long long* dbg,
                            cudaStream_t st);
+int tc_svgd_sel_count(long long n, long long d, long long row_begin, long long n_rows, void* ws, unsigned long long** red64_out, int mode, cudaStream_t st);
+int tc_svgd_sel_gather(long long n, long long d, long long row_begin, long long n_rows, void* ws, cudaStream_t st);
+int tc_svgd_sel_hist(long long n, long long d, long long row_begin, long long n_rows, int pass, unsigned* hist, const unsigned long long* state, void* ws,
+                     cudaStream_t st);
+int tc_svgd_sel_update(long long n, long long d, long long row_begin, long long n_rows, int pass, const unsigned* hist, unsigned long long* state, void* ws,
+                       float* out_h, cudaStream_t st);
 } }
 
 // use_tensor: 0 exact fp32 SIMT kernels ; 1 tcgen05 path ; -1 choose (tensor path from 1024 particles up)
@@ -403,10 +409,43 @@ extern "C" OCBNN_API int ocbnn_svgd_hist_pass_prepared(int64_t n, int64_t d, int
 // 1 fast (default), 0 legacy, 2 fast with a sabotaged bracket; initial value from OCBNN_SVGD_SELECT = fast | legacy | fallback
 static std::atomic<int> g_select_mode{[] { const char* e = getenv("OCBNN_SVGD_SELECT"); return !e ? 1 : e[0] == 'l' ? 0 : (e[0] == 'f' && e[1] == 'a' && e[2] == 'l') ? 2 : 1; }()};
 // sets the median-select algorithm of ocbnn_svgd_bandwidth's single-rank tensor path (mode < 0: query only); returns the previous mode
+static int g_select_mode_value() { return g_select_mode.load(); }
 extern "C" OCBNN_API int ocbnn_svgd_select_mode(int32_t mode) {
     const int prev = g_select_mode.load();
     if (mode >= 0 && mode <= 2) g_select_mode.store(mode);
     return prev;
+}
+
+// ---- bracket select across ranks (tensor path; see svgd_tc.cu).  stage 1 .. 3; the caller all-reduces (int64 sums) the reduce
+// buffer after stage 1 and hist[pass] after every stage-3 histogram.  workspace = the tensor workspace (after the 3*2048*4+256 B header).
+extern "C" OCBNN_API int ocbnn_svgd_sel_count(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, void* workspace, uint64_t** reduce_buf,
+                                              int64_t* reduce_words, void* stream) {
+    OCBNN_REQUIRE(workspace && n >= 2 && row_begin >= 0 && row_begin + n_rows <= n, OCBNN_EINVAL, "ocbnn_svgd_sel_count: bad argument");
+    unsigned long long* rb = nullptr;
+    int rc = tc::tc_svgd_sel_count(n, d, row_begin, n_rows, workspace, &rb, g_select_mode_value(), (cudaStream_t)stream);
+    if (reduce_buf) *reduce_buf = reinterpret_cast<uint64_t*>(rb);
+    if (reduce_words) *reduce_words = 4 + 2048;
+    return rc;
+}
+extern "C" OCBNN_API int ocbnn_svgd_sel_gather(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, void* workspace, void* stream) {
+    OCBNN_REQUIRE(workspace, OCBNN_EINVAL, "ocbnn_svgd_sel_gather: bad argument");
+    return tc::tc_svgd_sel_gather(n, d, row_begin, n_rows, workspace, (cudaStream_t)stream);
+}
+extern "C" OCBNN_API int ocbnn_svgd_sel_hist(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t pass, uint32_t* hist, uint64_t* select_state,
+                                             void* workspace, void* stream) {
+    OCBNN_REQUIRE(workspace && hist && select_state && pass >= 0 && pass < 3, OCBNN_EINVAL, "ocbnn_svgd_sel_hist: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pass == 0) {
+        k_zero_u32<<<(3 * kBins + 255) / 256, 256, 0, st>>>(hist, 3 * kBins);
+        OCBNN_LAUNCH_CHECK();
+    }
+    return tc::tc_svgd_sel_hist(n, d, row_begin, n_rows, pass, hist, reinterpret_cast<const unsigned long long*>(select_state), workspace, st);
+}
+extern "C" OCBNN_API int ocbnn_svgd_sel_update(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t pass, const uint32_t* hist,
+                                               uint64_t* select_state, void* workspace, float* out_h, void* stream) {
+    OCBNN_REQUIRE(workspace && hist && select_state && pass >= 0 && pass < 3, OCBNN_EINVAL, "ocbnn_svgd_sel_update: bad argument");
+    return tc::tc_svgd_sel_update(n, d, row_begin, n_rows, pass, hist, reinterpret_cast<unsigned long long*>(select_state), workspace, out_h,
+                                  (cudaStream_t)stream);
 }
 
 extern "C" OCBNN_API int ocbnn_svgd_bandwidth(const float* x, int64_t n, int64_t d, float* out_h, int32_t use_tensor, void* workspace,

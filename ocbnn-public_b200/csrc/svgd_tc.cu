@@ -122,6 +122,7 @@ struct TcWs {
     float *mean, *r, *s, *xc, *xc_hi, *xc_lo, *d2, *k_hi, *k_lo, *vt_hi, *vt_lo, *rowsum, *o;
     float *cand, *list2, *samples;   // bracket select: candidates, short list (cand_cap floats each), pair sample
     unsigned* ghist;                  // bracket select: linear histogram over the bracket
+    unsigned long long* red64;        // multi-rank bracket select: [zeros, below, candidates, overflow | ghist as 2048 u64] summed over ranks
     unsigned long long* sel; // bracket-select header: see SelHdr
     long long cand_cap;
     unsigned* hist;
@@ -167,11 +168,12 @@ static TcWs carve(void* workspace, long long n, long long d, long long row_begin
     const int fs = fused_splits(n_rows, w.n4);
     w.o = take((long long)(w.splits > fs ? w.splits : fs) * n_rows * 2 * w.dp);
     w.sel = reinterpret_cast<unsigned long long*>(take(64));
-    w.cand_cap = n_rows == n ? (n * n / 32 > (1 << 16) ? n * n / 32 : (1 << 16)) : 0;
+    w.cand_cap = n_rows * n / 16 > (1 << 16) ? n_rows * n / 16 : (1 << 16);      // ~2x the pairs a 3.3 % bracket keeps of this rank's rows
     w.cand = take(w.cand_cap);
     w.list2 = take(w.cand_cap);
-    w.samples = take(n_rows == n ? kSelSamplesHost : 0);
-    w.ghist = reinterpret_cast<unsigned*>(take(n_rows == n ? 4096 : 0));
+    w.samples = take(kSelSamplesHost);
+    w.ghist = reinterpret_cast<unsigned*>(take(4096));
+    w.red64 = reinterpret_cast<unsigned long long*>(take(2 * (4 + 2048)));
     w.bytes = p - reinterpret_cast<char*>(workspace);
     return w;
 }
@@ -345,7 +347,8 @@ struct SelHdr {                 // 64 bytes in the workspace
     unsigned long long zeros, below;
     unsigned n2, bin;           // short list length, hit bin
     unsigned long long resid;   // rank inside the hit bin
-    unsigned long long pad[2];
+    unsigned long long ncand_tot;   // candidates over all ranks (multi-rank flow; = ncand on one rank)
+    unsigned ok, pad32;             // multi-rank flow: bracket hit (set by k_sel_gather)
 };
 // The whole select works on w = d^2 (the eps-perturbed SQUARED distance): sqrt is monotone, so the k-th smallest distance is
 // the root of the k-th smallest w, exact zeros are the same pairs, and no pair needs a square root - only the answer does.
@@ -459,8 +462,8 @@ k_sel_bracket(const float* __restrict__ samples, SelHdr* __restrict__ hdr, unsig
 __device__ __forceinline__ int sel_lbin(float v, float lo, float scale) { return min(kSelBins - 1, max(0, (int)((v - lo) * scale))); }
 
 __global__ void __launch_bounds__(256)
-k_sel_count(const float* __restrict__ d2, const float* __restrict__ ssum, long long n, long long n4, int d, SelHdr* __restrict__ hdr,
-            float* __restrict__ cand, long long cand_cap, unsigned* __restrict__ ghist) {
+k_sel_count(const float* __restrict__ d2, const float* __restrict__ ssum, long long n, long long n4, int d, long long row_begin, long long n_rows,
+            SelHdr* __restrict__ hdr, float* __restrict__ cand, long long cand_cap, unsigned* __restrict__ ghist) {
     __shared__ float stage[8][256];
     __shared__ unsigned long long red[2][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -476,14 +479,15 @@ k_sel_count(const float* __restrict__ d2, const float* __restrict__ ssum, long l
         __syncwarp();
         staged = 0;
     };
-    for (long long i = blockIdx.x; i < n; i += gridDim.x) {
+    for (long long t = blockIdx.x; t < n_rows; t += gridDim.x) {          // d2 holds rows [row_begin, row_begin + n_rows)
+        const long long i = row_begin + t;
         const float si = ssum[i];
         for (long long j0 = (i + 1) / 256 * 256; j0 < n; j0 += 256) {
             const long long j = j0 + threadIdx.x;
             bool is_c = false;
             float v = 0.f;
             if (j > i && j < n) {
-                v = pair_w(d2[i * n4 + j], si, ssum[j], d);
+                v = pair_w(d2[t * n4 + j], si, ssum[j], d);
                 if (v == 0.f) ++zeros;
                 else if (v < lo) ++below;
                 else is_c = v <= hi;
@@ -517,22 +521,24 @@ k_sel_count(const float* __restrict__ d2, const float* __restrict__ ssum, long l
     }
 }
 
-__device__ __forceinline__ bool sel_ok(const SelHdr* hdr, long long n, unsigned long long* rank_out) {
+__device__ __forceinline__ bool sel_ok(const SelHdr* hdr, long long n, unsigned long long* rank_out, unsigned long long ncand_tot) {
     const unsigned long long pairs = (unsigned long long)n * (unsigned long long)(n - 1) / 2ull;
     const unsigned long long nz = pairs - hdr->zeros;
     const unsigned long long rank = nz ? (nz - 1) / 2 : 0;                      // LOWER median (torch.median)
     *rank_out = rank;
-    return !hdr->overflow && nz > 0 && rank >= hdr->below && rank < hdr->below + hdr->ncand;
+    return !hdr->overflow && nz > 0 && rank >= hdr->below && rank < hdr->below + ncand_tot;
 }
 
 __global__ void __launch_bounds__(256)
 k_sel_gather(long long n, SelHdr* __restrict__ hdr, const unsigned* __restrict__ ghist, const float* __restrict__ cand, float* __restrict__ list2,
-             long long cap2) {
+             long long cap2, int multi) {
     __shared__ unsigned wsum[8];
     __shared__ int s_bin;
     __shared__ unsigned long long s_res;
     unsigned long long rank, resid;
-    if (!sel_ok(hdr, n, &rank)) return;                 // uniform over the grid: k_sel_final takes the fallback
+    const bool ok = sel_ok(hdr, n, &rank, multi ? hdr->ncand_tot : hdr->ncand);
+    if (multi && blockIdx.x == 0 && threadIdx.x == 0) hdr->ok = ok ? 1u : 0u;
+    if (!ok) return;                                    // uniform over the grid: the final stage takes the fallback
     const int b1 = block_find_bin<256, 16>(ghist, rank - hdr->below, &resid, wsum, &s_bin, &s_res);
     if (blockIdx.x == 0 && threadIdx.x == 0) { hdr->bin = (unsigned)b1; hdr->resid = resid; }
     const float lo = hdr->lo, hi = hdr->hi;
@@ -556,7 +562,7 @@ k_sel_final(const float* __restrict__ d2, const float* __restrict__ ssum, long l
     __shared__ unsigned long long s_res;
     const int t = threadIdx.x;
     unsigned long long rank;
-    const bool ok = sel_ok(hdr, n, &rank) && (long long)hdr->n2 <= cap2;
+    const bool ok = sel_ok(hdr, n, &rank, hdr->ncand) && (long long)hdr->n2 <= cap2;
     const unsigned long long pairs = (unsigned long long)n * (unsigned long long)(n - 1) / 2ull;
     float med = nanf("");                               // torch: median of an empty tensor
     if (pairs != hdr->zeros) {
@@ -595,6 +601,89 @@ k_sel_final(const float* __restrict__ d2, const float* __restrict__ ssum, long l
     }
 }
 
+// ---- bracket select across ranks ---------------------------------------------------------------------------------------
+// Every rank holds all particles (all-gather) and the distances of ITS rows.  The bracket is sampled from X, so every rank
+// derives the same [lo, hi] with no communication; each rank counts / compacts the pairs of its rows (k_sel_count); ONE
+// all-reduce sums the counters and the linear histogram (k_sel_pack / k_sel_unpack around it); every rank finds the same
+// hit bin and gathers its own candidates of that bin (k_sel_gather); the final radix select runs over those short lists with
+// the 2048-bin histogram all-reduced between the three passes (k_hist_sel / k_select_update_sel) - or, if the bracket
+// missed, over the ranks' distance rows like the legacy select.  All decisions are taken on the device.
+__global__ void __launch_bounds__(256)
+k_sel_pack(const SelHdr* __restrict__ hdr, const unsigned* __restrict__ ghist, unsigned long long* __restrict__ red64) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2048) red64[4 + i] = (unsigned long long)ghist[2 * i] | ((unsigned long long)ghist[2 * i + 1] << 32);
+    if (i == 0) { red64[0] = hdr->zeros; red64[1] = hdr->below; red64[2] = hdr->ncand; red64[3] = hdr->overflow; }
+}
+__global__ void __launch_bounds__(256)
+k_sel_unpack(SelHdr* __restrict__ hdr, unsigned* __restrict__ ghist, const unsigned long long* __restrict__ red64) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2048) { ghist[2 * i] = (unsigned)red64[4 + i]; ghist[2 * i + 1] = (unsigned)(red64[4 + i] >> 32); }
+    if (i == 0) { hdr->zeros = red64[0]; hdr->below = red64[1]; hdr->ncand_tot = red64[2]; hdr->overflow = red64[3] ? 1u : 0u; }
+}
+// radix-select histogram pass of the final stage: over this rank's short list (bracket hit) or over its distance rows (miss)
+__global__ void __launch_bounds__(256)
+k_hist_sel(const float* __restrict__ d2, const float* __restrict__ ssum, long long n, long long n4, int d, long long row_begin, long long n_rows,
+           const SelHdr* __restrict__ hdr, const float* __restrict__ list2, long long cap2, int pass, unsigned* __restrict__ hist,
+           const unsigned long long* __restrict__ state) {
+    __shared__ unsigned sh[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh[i] = 0u;
+    __syncthreads();
+    const unsigned prefix = pass > 0 ? (unsigned)state[0] : 0u;
+    auto add = [&](unsigned bits) {
+        unsigned bin = 0xFFFFFFFFu;
+        if (bits != 0u) {
+            if (pass == 0) bin = bits >> 21;
+            else if (pass == 1) { if ((bits >> 21) == (prefix >> 21)) bin = (bits >> 10) & 2047u; }
+            else if ((bits >> 10) == (prefix >> 10)) bin = bits & 1023u;
+        }
+        hist_add_warp(sh, bin);
+    };
+    if (hdr->ok) {
+        const long long n2 = min((long long)hdr->n2, cap2);
+        for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < n2; i0 += (long long)gridDim.x * blockDim.x) {
+            const long long i = i0 + threadIdx.x;
+            add(i < n2 ? __float_as_uint(list2[i]) : 0u);
+        }
+    } else {
+        for (long long t = blockIdx.x; t < n_rows; t += gridDim.x) {
+            const long long i = row_begin + t;
+            const float si = ssum[i];
+            for (long long j0 = (i + 1) / 256 * 256; j0 < n; j0 += 256) {
+                const long long j = j0 + threadIdx.x;
+                add((j > i && j < n) ? __float_as_uint(pair_w(d2[t * n4 + j], si, ssum[j], d)) : 0u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < 2048; b += blockDim.x)
+        if (sh[b]) atomicAdd(&hist[pass * 2048 + b], sh[b]);
+}
+// after the all-reduce of pass p: locate the bin of the wanted rank; after pass 2 emit h (one CTA of 1024 threads)
+__global__ void __launch_bounds__(1024)
+k_select_update_sel(int pass, const unsigned* __restrict__ hist, unsigned long long* __restrict__ state, long long n, const SelHdr* __restrict__ hdr,
+                    float* __restrict__ out_h) {
+    __shared__ unsigned wsum[32];
+    __shared__ int s_bin;
+    __shared__ unsigned long long s_res;
+    const unsigned long long pairs = (unsigned long long)n * (unsigned long long)(n - 1) / 2ull;
+    const unsigned long long nz = pairs - hdr->zeros;
+    unsigned long long rank = pass == 0 ? (hdr->ok ? hdr->resid : (nz ? (nz - 1) / 2 : 0)) : state[1];
+    __syncthreads();
+    unsigned long long resid;
+    const int b = block_find_bin<1024, 2>(hist + pass * 2048, rank, &resid, wsum, &s_bin, &s_res);
+    if (threadIdx.x == 0) {
+        unsigned prefix = pass == 0 ? 0u : (unsigned)state[0];
+        prefix |= pass == 0 ? ((unsigned)b << 21) : pass == 1 ? ((unsigned)b << 10) : (unsigned)b;
+        state[0] = prefix;
+        state[1] = resid;
+        if (pass == 2 && out_h) {
+            float med = sqrtf(__uint_as_float(prefix));                    // the select ran on squared distances
+            if (nz == 0) med = nanf("");
+            *out_h = __fdiv_rn(__fmul_rn(med, med), (float)log((double)n));
+        }
+    }
+}
+
 // ---- single-rank, D <= 64: distances and the select's counting pass in ONE symmetric kernel -------------------------------
 // k_sel_sample_x draws the pair sample straight from the centred particles (the bracket is needed before d2 exists);
 // k_d2_sym computes only the tiles on and above the diagonal of d2 (half the FMA work of k_d2_direct), writes each tile and,
@@ -622,6 +711,25 @@ k_sel_sample_x(const float* __restrict__ xc, const float* __restrict__ ssum, lon
         e = a.w - b.w; acc = fmaf(e, e, acc);
     }
     samples[idx] = pair_w(acc, ssum[i], ssum[j], d);
+}
+
+// pair sample for D > 64 (one warp per pair; the distance is only a bracket estimate)
+__global__ void __launch_bounds__(256)
+k_sel_sample_wide(const float* __restrict__ xc, const float* __restrict__ ssum, long long n, int d, int dp, float* __restrict__ samples) {
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (idx >= kSelSamples) return;
+    const unsigned a = mix32((unsigned)idx * 2u + 0x9e3779b9u), b = mix32(a ^ 0x85ebca6bu);
+    long long i = (long long)(a % (unsigned)n), j = (long long)(b % (unsigned)n);
+    if (i == j) j = (j + 1) % n;
+    if (i > j) { const long long tmp = i; i = j; j = tmp; }
+    float acc = 0.f;
+    for (int c = lane; c < dp; c += 32) {
+        const float e = xc[i * dp + c] - xc[j * dp + c];
+        acc = fmaf(e, e, acc);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) samples[idx] = pair_w(acc, ssum[i], ssum[j], d);
 }
 
 template <int DP>
@@ -1171,9 +1279,9 @@ int tc_svgd_select_fast(long long n, long long d, void* ws, float* out_h, int mo
     OCBNN_LAUNCH_CHECK();
     k_sel_bracket<<<1, 1024, 0, st>>>(w.samples, hdr, w.ghist, mode == 2 ? 1 : 0);
     OCBNN_LAUNCH_CHECK();
-    k_sel_count<<<(unsigned)(n < 148 * 8 ? n : 148 * 8), 256, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, hdr, w.cand, w.cand_cap, w.ghist);
+    k_sel_count<<<(unsigned)(n < 148 * 8 ? n : 148 * 8), 256, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, 0, n, hdr, w.cand, w.cand_cap, w.ghist);
     OCBNN_LAUNCH_CHECK();
-    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap);
+    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap, 0);
     OCBNN_LAUNCH_CHECK();
     k_sel_final<<<1, 1024, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, hdr, w.list2, w.cand_cap, out_h, dbg);
     OCBNN_LAUNCH_CHECK();
@@ -1189,9 +1297,57 @@ int tc_svgd_prepare_select(const float* x, long long n, long long d, void* ws, l
     if (rc) return rc;
     if (!sel_done) return tc_svgd_select_fast(n, d, ws, out_h, mode, dbg, st);
     SelHdr* hdr = reinterpret_cast<SelHdr*>(w.sel);
-    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap);
+    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap, 0);
     OCBNN_LAUNCH_CHECK();
     k_sel_final<<<1, 1024, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, hdr, w.list2, w.cand_cap, out_h, dbg);
+    OCBNN_LAUNCH_CHECK();
+    return OCBNN_OK;
+}
+// multi-rank bracket select, stage 1 (after tc_svgd_prepare): bracket from X, counting pass over this rank's rows, counters packed
+// into the reduce buffer (*red64_out, 4 + 2048 u64: the caller all-reduces it as int64 sums)
+int tc_svgd_sel_count(long long n, long long d, long long row_begin, long long n_rows, void* ws, unsigned long long** red64_out, int mode, cudaStream_t st) {
+    TcWs w = carve(ws, n, d, row_begin, n_rows);
+    SelHdr* hdr = reinterpret_cast<SelHdr*>(w.sel);
+    if (red64_out) *red64_out = w.red64;
+    if (w.dp == 32) k_sel_sample_x<32><<<kSelSamples / 256, 256, 0, st>>>(w.xc, w.s, w.n, (int)w.d, w.samples);
+    else if (w.dp == 64) k_sel_sample_x<64><<<kSelSamples / 256, 256, 0, st>>>(w.xc, w.s, w.n, (int)w.d, w.samples);
+    else k_sel_sample_wide<<<kSelSamples / 8, 256, 0, st>>>(w.xc, w.s, w.n, (int)w.d, (int)w.dp, w.samples);
+    OCBNN_LAUNCH_CHECK();
+    k_sel_bracket<<<1, 1024, 0, st>>>(w.samples, hdr, w.ghist, mode == 2 ? 1 : 0);
+    OCBNN_LAUNCH_CHECK();
+    if (n_rows > 0) {
+        k_sel_count<<<(unsigned)(n_rows < 148 * 8 ? n_rows : 148 * 8), 256, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, row_begin, n_rows, hdr, w.cand, w.cand_cap,
+                                                                                   w.ghist);
+        OCBNN_LAUNCH_CHECK();
+    }
+    k_sel_pack<<<8, 256, 0, st>>>(hdr, w.ghist, w.red64);
+    OCBNN_LAUNCH_CHECK();
+    return OCBNN_OK;
+}
+// stage 2 (after the all-reduce of the reduce buffer): global counters in, this rank's candidates of the hit bin gathered
+int tc_svgd_sel_gather(long long n, long long d, long long row_begin, long long n_rows, void* ws, cudaStream_t st) {
+    TcWs w = carve(ws, n, d, row_begin, n_rows);
+    SelHdr* hdr = reinterpret_cast<SelHdr*>(w.sel);
+    k_sel_unpack<<<8, 256, 0, st>>>(hdr, w.ghist, w.red64);
+    OCBNN_LAUNCH_CHECK();
+    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap, 1);
+    OCBNN_LAUNCH_CHECK();
+    return OCBNN_OK;
+}
+// stage 3, per radix pass: local histogram (the caller all-reduces hist[pass]) ...
+int tc_svgd_sel_hist(long long n, long long d, long long row_begin, long long n_rows, int pass, unsigned* hist, const unsigned long long* state, void* ws,
+                     cudaStream_t st) {
+    TcWs w = carve(ws, n, d, row_begin, n_rows);
+    k_hist_sel<<<148, 256, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, row_begin, n_rows, reinterpret_cast<const SelHdr*>(w.sel), w.list2, w.cand_cap, pass, hist,
+                                    state);
+    OCBNN_LAUNCH_CHECK();
+    return OCBNN_OK;
+}
+// ... and the rank bookkeeping / final h
+int tc_svgd_sel_update(long long n, long long d, long long row_begin, long long n_rows, int pass, const unsigned* hist, unsigned long long* state, void* ws,
+                       float* out_h, cudaStream_t st) {
+    TcWs w = carve(ws, n, d, row_begin, n_rows);
+    k_select_update_sel<<<1, 1024, 0, st>>>(pass, hist, state, n, reinterpret_cast<const SelHdr*>(w.sel), out_h);
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }

@@ -81,6 +81,11 @@ _SIGS = {
     "ocbnn_svgd_select_update": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ocbnn_svgd_bandwidth": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "ocbnn_svgd_select_mode": (C.c_int, [C.c_int32]),
+    "ocbnn_svgd_sel_count": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p]),
+    "ocbnn_svgd_sel_gather": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ocbnn_svgd_sel_hist": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ocbnn_svgd_sel_update": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
     "ocbnn_svgd_prepare": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "ocbnn_svgd_hist_pass_prepared": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p]),
@@ -296,6 +301,32 @@ def svgd_select_mode(mode=-1):
     """Median-select algorithm of svgd_bandwidth's tensor path: 1 bracket select (default), 0 radix select, 2 sabotaged bracket
     (tests the in-kernel fallback); returns the previous mode."""
     return int(lib().ocbnn_svgd_select_mode(int(mode)))
+
+
+def svgd_sel_count(n, d, row_begin, n_rows, workspace):
+    """Stage 1 of the bracket select across ranks.  Returns the reduce buffer as an int64 view INTO the workspace (all-reduce it
+    in place with SUM before svgd_sel_gather)."""
+    ws = workspace[SVGD_HDR_BYTES // 8:]
+    ptr, words = C.c_void_p(), C.c_int64()
+    check(lib().ocbnn_svgd_sel_count(int(n), int(d), int(row_begin), int(n_rows), _ptr(ws), C.byref(ptr), C.byref(words), _stream()))
+    off = (ptr.value - workspace.data_ptr()) // 8
+    return workspace[off:off + words.value]
+
+
+def svgd_sel_gather(n, d, row_begin, n_rows, workspace):
+    ws = workspace[SVGD_HDR_BYTES // 8:]
+    check(lib().ocbnn_svgd_sel_gather(int(n), int(d), int(row_begin), int(n_rows), _ptr(ws), _stream()))
+
+
+def svgd_sel_hist(n, d, row_begin, n_rows, pass_, hist, state, workspace):
+    ws = workspace[SVGD_HDR_BYTES // 8:]
+    check(lib().ocbnn_svgd_sel_hist(int(n), int(d), int(row_begin), int(n_rows), int(pass_), _ptr(hist), _ptr(state), _ptr(ws), _stream()))
+
+
+def svgd_sel_update(n, d, row_begin, n_rows, pass_, hist, state, workspace, out_h):
+    ws = workspace[SVGD_HDR_BYTES // 8:]
+    check(lib().ocbnn_svgd_sel_update(int(n), int(d), int(row_begin), int(n_rows), int(pass_), _ptr(hist), _ptr(state), _ptr(ws), _ptr(out_h),
+                                      _stream()))
 
 
 def svgd_prepare(X, row_begin, n_rows, workspace, use_tensor=1):

@@ -327,6 +327,18 @@ class SVGDMixin:
         n, lo, rows = st["n"], st["lo"], st["hi"] - st["lo"]
         if D.world() == 1:
             E.svgd_bandwidth(Xall, st["ws"], st["h"], use_tensor=1 if tensor else 0)
+        elif tensor and E.svgd_select_mode(-1) != 0:
+            # exact global median by the bracket select across ranks: one all-reduce of the counters + linear histogram, then three
+            # 8 KB all-reduces of the radix histograms over the short candidate lists (OCBNN_SVGD_SELECT=legacy: radix select below)
+            d_ = self.nweights
+            E.svgd_prepare(Xall, lo, rows, st["ws"])
+            red = E.svgd_sel_count(n, d_, lo, rows, st["ws"])
+            D.all_sum_(red)
+            E.svgd_sel_gather(n, d_, lo, rows, st["ws"])
+            for p in range(3):
+                E.svgd_sel_hist(n, d_, lo, rows, p, st["hist"], st["state"], st["ws"])
+                D.all_sum_(st["hist"][p * 2048:(p + 1) * 2048])
+                E.svgd_sel_update(n, d_, lo, rows, p, st["hist"], st["state"], st["ws"], st["h"])
         else:                                   # exact global median: all-reduce the select histograms between passes
             if tensor:
                 E.svgd_prepare(Xall, lo, rows, st["ws"])

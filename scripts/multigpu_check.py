@@ -64,6 +64,35 @@ def main():
     if rank == 0:
         print(f"SVGD {world} ranks vs 1 rank: particles rel diff {rel:.2e}, bandwidth rel diff {hrel:.2e} (n=257, 3 epochs)")
 
+    # ---- SVGD tensor path: bracket select across ranks (and the legacy radix select) vs one rank ---------------------------
+    from ocbnn_b200 import engine as E
+    for n_t, wl in ((2500, "W4"), (1100, "W7")):
+        mt = workloads.build(wl, seed=0, infer_nsamples=n_t)
+        if mt.aocp_mean is not None:
+            Xt = mt.aocp_mean[None] + 3 * mt.aocp_std[None] * torch.randn(n_t, mt.nweights, generator=g)
+        else:
+            Xt = torch.randn(n_t, mt.nweights, generator=g)
+        res = {}
+        for mode in (1, 0):
+            E.svgd_select_mode(mode)
+            stt = mt.svgd_setup(Xt, use_tensor=1)
+            for ep in range(1, 3):
+                mt.svgd_epoch(stt, ep, True)
+            res[mode] = (D.gather_cat(stt["X"], 0), stt["h"].clone())
+        E.svgd_select_mode(1)
+        D.active = lambda: False
+        st1 = mt.svgd_setup(Xt, use_tensor=1)
+        mt.update_config(svgd_graph=False)
+        for ep in range(1, 3):
+            mt.svgd_epoch(st1, ep, True)
+        D.active = saved
+        h_same = bool(res[1][1] == res[0][1]) and bool(res[1][1] == st1["h"])
+        rel = float((res[1][0] - st1["X"]).norm() / st1["X"].norm())
+        ok &= h_same and rel < 1e-5
+        if rank == 0:
+            print(f"SVGD tensor path {wl} n={n_t}: bandwidth bit-identical (bracket select x{world}, radix select x{world}, 1 rank) = {h_same}, "
+                  f"particles rel diff {rel:.2e}")
+
     # ---- BBB: all-reduce of the (D,2) gradient ----------------------------------------------------------------------------
     mb = workloads.build("W1", sampler="BBB", seed=0)
     k = 64
