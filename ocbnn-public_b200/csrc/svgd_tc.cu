@@ -969,8 +969,8 @@ k_phi_finalize(const float* __restrict__ o, int splits, const float* __restrict_
 }
 
 // ---- K3b fused: K tiles generated on the fly -----------------------------------------------------------------------------
-// O[rows x BN] = K[rows x n] * Vt[BN x n]^T with K_tj = exp(-d2_tj / h) NEVER written to HBM: the four epilogue warps of
-// tc_gemm.cuh's layout double as SIMT producers of the A operand.  Per 32-column K block they read the 128 x 32 tile of d2
+// O[rows x BN] = K[rows x n] * Vt[BN x n]^T with K_tj = exp(-d2_tj / h) NEVER written to HBM: eight SIMT warps (the four epilogue
+// warps of tc_gemm.cuh's layout plus four more) produce the A operand.  Per 32-column K block they read the 128 x 32 tile of d2
 // (coalesced 128-byte rows), evaluate the exponentials (MUFU.EX2), split them into tf32 hi / lo and store both tiles
 // straight into the 128-byte-swizzled K-major shared-memory layout the UMMA descriptor expects (16-byte chunk c of row r
 // at chunk position c ^ (r & 7)), fence the generic-proxy writes towards the async proxy and arrive on the stage's full
@@ -995,6 +995,8 @@ struct FusedCfg {
     static constexpr int kTmemCols = BN < 32 ? 32 : BN;
 };
 constexpr int kFusedCtasPerSm = 2, kFusedMaxSplits = 16;
+constexpr int kFusedProducers = 8;                       // producer warps (warps 2..9; warps 2..5 are also the epilogue warps)
+constexpr int kFusedThreads = 32 * (2 + kFusedProducers);
 static int fused_splits(long long n_rows, long long n4) {
     const long long tiles = (n_rows + kBM - 1) / kBM, num_kb = (n4 + kBK - 1) / kBK;
     long long sp = (148 * kFusedCtasPerSm) / tiles;
@@ -1004,7 +1006,7 @@ static int fused_splits(long long n_rows, long long n4) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kFusedThreads, 2)
 k_phi_fused(const float* __restrict__ d2, const float* __restrict__ hptr, long long n, long long n4, long long n_rows,
             const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ o, long long ldo,
             long long split_stride, float* __restrict__ rs_part, int num_kb, int kb_per_split) {
@@ -1026,7 +1028,7 @@ k_phi_fused(const float* __restrict__ d2, const float* __restrict__ hptr, long l
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) {
-            mbar_init(full_bar(s), 1 + 4);          // the TMA thread (B tiles) + one arrival per producer warp (A tiles)
+            mbar_init(full_bar(s), 1 + kFusedProducers);          // the TMA thread (B tiles) + one arrival per producer warp (A tiles)
             mbar_init(empty_bar(s), 1);
         }
         mbar_init(tmem_full_bar, 1);
@@ -1074,23 +1076,24 @@ k_phi_fused(const float* __restrict__ d2, const float* __restrict__ hptr, long l
             umma_commit(tmem_full_bar);
         }
     } else {
-        // ---- A producers: warp wp owns rows [32 wp, 32 wp + 32) of the tile; per pass 4 rows x 8 chunks of 16 bytes ----
+        // ---- A producers: 8 warps, warp wp owns rows [16 wp, 16 wp + 16) of the tile; per pass 4 rows x 8 chunks of 16 bytes ----
+        constexpr int NP = 128 / kFusedProducers / 4;           // passes per warp and K block
         const int wp = warp - 2, rr = lane >> 3, c = lane & 7;
         const float sc = -1.4426950408889634f / __ldg(hptr);
-        float rs[8];
+        float rs[NP];
 #pragma unroll
-        for (int ps = 0; ps < 8; ++ps) rs[ps] = 0.f;
+        for (int ps = 0; ps < NP; ++ps) rs[ps] = 0.f;
         // the d2 tile of K block i + 1 is in flight (registers) while block i is evaluated: the loads do not touch the stage,
         // so they are issued ahead of the empty-barrier wait and hide the L2/HBM latency behind a whole block of work
-        auto load_tile = [&](float4 (&dst)[8], int i) {
+        auto load_tile = [&](float4 (&dst)[NP], int i) {
             const long long jj = (long long)(kb_begin + i) * kBK + 4 * c;
 #pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-                const long long t = m0 + 32 * wp + 4 * ps + rr;
+            for (int ps = 0; ps < NP; ++ps) {
+                const long long t = m0 + 4 * NP * wp + 4 * ps + rr;
                 dst[ps] = (i < nkb && t < n_rows && jj < n4) ? __ldg(reinterpret_cast<const float4*>(d2 + t * n4 + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        float4 v[8], nx[8];
+        float4 v[NP], nx[NP];
         load_tile(v, 0);
         for (int i = 0; i < nkb; ++i) {
             const int s = i % Cfg::kStages;
@@ -1100,8 +1103,8 @@ k_phi_fused(const float* __restrict__ d2, const float* __restrict__ hptr, long l
             mbar_wait(empty_bar(s), ph ^ 1);
             uint8_t* stp = gen_base + s * Cfg::kStageBytes;
 #pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-                const int r = 32 * wp + 4 * ps + rr;
+            for (int ps = 0; ps < NP; ++ps) {
+                const int r = 4 * NP * wp + 4 * ps + rr;
                 const bool row_ok = m0 + r < n_rows;
                 float k[4] = {ex2_fast(v[ps].x * sc), ex2_fast(v[ps].y * sc), ex2_fast(v[ps].z * sc), ex2_fast(v[ps].w * sc)};
                 float hi[4], lo[4], sum = 0.f;
@@ -1124,15 +1127,16 @@ k_phi_fused(const float* __restrict__ d2, const float* __restrict__ hptr, long l
             __syncwarp();
             if (lane == 0) mbar_arrive(full_bar(s));
 #pragma unroll
-            for (int ps = 0; ps < 8; ++ps) v[ps] = nx[ps];
+            for (int ps = 0; ps < NP; ++ps) v[ps] = nx[ps];
         }
         if (c == 0) {
 #pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-                const long long t = m0 + 32 * wp + 4 * ps + rr;
+            for (int ps = 0; ps < NP; ++ps) {
+                const long long t = m0 + 4 * NP * wp + 4 * ps + rr;
                 if (t < n_rows) rs_part[(long long)blockIdx.z * n_rows + t] = rs[ps];
             }
         }
+        if (warp >= 6) goto done;                               // warps 6..9 only produce
         // ---- epilogue: TMEM lane quarter = warp % 4 ----
         const int q = warp & 3;
         if (nkb > 0) {
@@ -1156,6 +1160,7 @@ k_phi_fused(const float* __restrict__ d2, const float* __restrict__ hptr, long l
             }
         }
     }
+done:
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_d, Cfg::kTmemCols);
@@ -1227,12 +1232,12 @@ static int tc_phi(const TcWs& w, const float* g, const float* h, float* phi, cud
         if (w.bn == 64) {
             auto kern = k_phi_fused<64>;
             OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<64>::kSmemBytes));
-            kern<<<grid, kThreads, FusedCfg<64>::kSmemBytes, st>>>(w.d2, h, w.n, w.n4, w.n_rows, tb_hi, tb_lo, w.o, 2 * w.dp, w.n_rows * 2 * w.dp, rs_part,
+            kern<<<grid, kFusedThreads, FusedCfg<64>::kSmemBytes, st>>>(w.d2, h, w.n, w.n4, w.n_rows, tb_hi, tb_lo, w.o, 2 * w.dp, w.n_rows * 2 * w.dp, rs_part,
                                                                   num_kb, per);
         } else {
             auto kern = k_phi_fused<128>;
             OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<128>::kSmemBytes));
-            kern<<<grid, kThreads, FusedCfg<128>::kSmemBytes, st>>>(w.d2, h, w.n, w.n4, w.n_rows, tb_hi, tb_lo, w.o, 2 * w.dp, w.n_rows * 2 * w.dp, rs_part,
+            kern<<<grid, kFusedThreads, FusedCfg<128>::kSmemBytes, st>>>(w.d2, h, w.n, w.n4, w.n_rows, tb_hi, tb_lo, w.o, 2 * w.dp, w.n_rows * 2 * w.dp, rs_part,
                                                                    num_kb, per);
         }
         OCBNN_LAUNCH_CHECK();
