@@ -39,6 +39,7 @@ import torch  # noqa: E402
 
 METRIC = "hmc_chain_leapfrog_steps_per_s"
 UNIT = "chain-leapfrog-steps/s"
+WORKLOAD_NAME = "W2 repro/F1a.yaml HMC + negative-exponential COCP (100 constraint points), toy1 (6 points), [1,10,1] rbf, posterior"
 
 
 def parse():
@@ -194,7 +195,7 @@ def run_reference(args):
     rate, cores, M, t_step, how = cpu_hmc_rate(arr, args.leapfrog, seconds=max(20.0, 8.0 * (args.steps + args.warmup)), steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "W2 repro/F1a.yaml HMC + negative-exponential COCP, toy1, [1,10,1] rbf", "chains": M,
+            "config": {"workload": WORKLOAD_NAME, "chains": M,
                        "leapfrog_l": args.leapfrog},
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{M} chains x 1 HMC iteration (L={args.leapfrog}) per step on {cores} host cores; {how}"},
@@ -363,7 +364,7 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "W2 repro/F1a.yaml HMC + negative-exponential COCP (100 constraint points), toy1 (6 points), [1,10,1] rbf, posterior",
+            "config": {"workload": WORKLOAD_NAME if args.workload.upper() == "W2" else f"{args.workload.upper()} (see ocbnn_b200/workloads.py)",
                        "chains_per_gpu": M, "chains_total": world * M, "leapfrog_l": L, "hmc_epsilon": m.hmc_epsilon, "lanes_per_chain": args.lanes or "auto",
                        "l2": "flushed between timed steps (256 MiB write)", "accept_rate": accept_rate},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
