@@ -1,4 +1,4 @@
-"""ctypes wrapper of oracle/_ref/libocbnn_oracle.so (C restatement of the oracle, OpenMP over chains).
+"""ctypes wrapper of oracle/_ref/libocbnn_oracle.so (C restatement of the oracle; chains fanned out over host threads here).
 TEST INFRASTRUCTURE ONLY — the multi-core CPU baseline of bench.py and a cross-check of the numpy oracle."""
 import ctypes as C
 import math

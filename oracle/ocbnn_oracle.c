@@ -1,5 +1,5 @@
 /*
- * ocbnn_oracle.c — plain C restatement (fp32, closed-form gradients, OpenMP over chains) of the OC-BNN log posterior,
+ * ocbnn_oracle.c — plain C restatement (fp32, closed-form gradients; single-threaded, callers fan chains out over host threads) of the OC-BNN log posterior,
  * its gradient and the HMC iteration.  TEST INFRASTRUCTURE ONLY: built by oracle/Makefile into oracle/_ref/libocbnn_oracle.so
  * and used by tests/ (cross-check against the numpy oracle and the golden vectors of the unmodified reference) and by
  * bench.py's CPU legs (cpu_baseline / --impl reference) as the multi-core CPU baseline.  Never linked or loaded by the product.

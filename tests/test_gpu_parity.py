@@ -383,3 +383,48 @@ def test_hmc_run_host_samples_and_svgd_graph_equivalence():
     torch.cuda.synchronize()
     assert "graphs" in st_g and any(not isinstance(v, str) for v in st_g["graphs"].values())
     assert torch.equal(st_g["X"], st_e["X"]) and torch.equal(st_g["h"], st_e["h"])
+
+
+def test_full_size_properties_hmc_262144_chains_and_svgd_4096_particles():
+    """BASELINE.json's full sizes through size-independent properties.
+    HMC (W2, 262144 chains, L = 50): chains are independent, so 512 distinct chains replicated 512 times each give
+    bit-identical replicas wherever they sit in the launch, and every accept flag equals the reference's rule applied to the
+    returned energies.  SVGD (W4, 4096 particles): the update is equivariant under a permutation of the particles (bandwidth
+    invariant, phi rows permuted)."""
+    import os, tempfile
+    from ocbnn_b200 import workloads
+    os.chdir(tempfile.mkdtemp())
+    m = workloads.build("W2", seed=0)
+    prob = m.engine_problem()
+    base, reps, L = 512, 512, 50
+    g = torch.Generator().manual_seed(5)
+    q0 = 0.5 * torch.randn(base, m.nweights, generator=g)
+    p0 = torch.randn(1, base, m.nweights, generator=g)
+    u = torch.rand(1, base, generator=g, dtype=torch.float64)
+    perm = torch.randperm(base * reps, generator=g)
+    src = (torch.arange(base * reps) % base)[perm]                    # chain slot -> which distinct chain it replicates
+    q = q0[src].cuda().contiguous()
+    acc, H, flags = prob.hmc_iterate(q, p0[:, src].cuda().contiguous(), u[:, src].cuda().contiguous(), m.hmc_epsilon, L, True, want_h=True)
+    assert int(flags.max()) == 0
+    qc, ac, Hc = q.cpu(), acc.cpu()[0], H.cpu()[0]
+    first = torch.full((base,), -1, dtype=torch.long)
+    first[src.flip(0)] = torch.arange(base * reps - 1, -1, -1)         # first slot of every distinct chain
+    assert torch.equal(qc, qc[first[src]]) and torch.equal(ac, ac[first[src]]) and torch.equal(Hc, Hc[first[src]])
+    # the Metropolis-Hastings decision is the reference's: u < exp(U0 - U1 + K0 - K1) evaluated in fp32 (inference.py:74)
+    dH = ((Hc[:, 0] - Hc[:, 2]) + Hc[:, 1]) - Hc[:, 3]
+    assert torch.isfinite(dH).all()
+    assert torch.equal(ac.bool(), u[0, src] < torch.exp(dH).double())
+
+    ms = workloads.build("W4", seed=0, infer_nsamples=4096)
+    X = torch.randn(4096, ms.nweights, generator=g)
+    G = 5 * torch.randn(4096, ms.nweights, generator=g)
+    pm = torch.randperm(4096, generator=g)
+    out = []
+    for Xi, Gi in ((X, G), (X[pm], G[pm])):
+        Xd, Gd = Xi.cuda().contiguous(), Gi.cuda().contiguous()
+        ws = E.svgd_workspace(4096, ms.nweights, Xd.device, use_tensor=1)
+        h = E.svgd_bandwidth(Xd, ws, use_tensor=1)
+        out.append((float(h), E.svgd_phi(Xd, Gd, h, 0, 4096, ws, use_tensor=2).cpu()))
+    assert abs(out[0][0] - out[1][0]) <= 2e-6 * out[0][0]
+    rel = (out[0][1][pm] - out[1][1]).norm(dim=1) / out[0][1][pm].norm(dim=1)
+    assert float(rel.max()) < 1e-5, float(rel.max())
