@@ -450,6 +450,22 @@ def extras(m, prob, dev, args):
         he = np.full(T, 0.003, dtype=np.float32)
         t = _time_cuda(lambda: pg.sgld_iterate(w, noise, he, None, 1, True), reps=2)
         out["sgld_W1_chain_steps_per_s"] = M * T / t
+        # HMC on the classifier workload (F2a: [2,10,3] + Dirichlet COCP) and BBB on the credit shape (W6: K1 generic net + K5)
+        m3 = workloads.build("W3", seed=0)
+        p3 = m3.engine_problem()
+        M3 = 131072
+        q3 = 0.5 * torch.randn(M3, m3.nweights, device=dev)
+        p03 = torch.randn(1, M3, m3.nweights, device=dev)
+        u3 = torch.rand(1, M3, device=dev, dtype=torch.float64)
+        t = _time_cuda(lambda: p3.hmc_iterate(q3, p03, u3, m3.hmc_epsilon, L, True, want_flags=False), reps=2)
+        out["hmc_W3_classifier_chain_leapfrog_steps_per_s"] = M3 * L / t
+        k = 4096
+        mb = workloads.build("W6", seed=0, bbb_esamples=k)
+        qp = torch.cat([0.3 * torch.randn(mb.nweights, 1), torch.ones(mb.nweights, 1) * -3.0], 1).to(dev).contiguous()
+        acc = torch.zeros_like(qp)
+        eps = torch.randn(k, mb.nweights, device=dev)
+        t = _time_cuda(lambda: mb.bbb_epoch(qp, acc, eps, 1, True, k_total=k), reps=2)
+        out["bbb_W6_mc_sample_evals_per_s"] = k / t
     finally:
         os.chdir(cwd)
     return out
