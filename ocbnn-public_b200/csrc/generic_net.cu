@@ -31,7 +31,7 @@ struct GenLayout {
     int wtot;                        // floats in the padded weight block
     int arow[OCBNN_MAX_LAYERS + 1];  // first activation row of layer l (rows of length TS)
     int rows_tot;                    // activation rows (A_0, then Z_l/A_l pairs)
-    int maxw;                        // widest padded layer (dZ ping-pong buffers)
+    int maxw;                        // widest padded layer
     int tp, ts;                      // points per tile, row stride
     int act;
     int d;                           // compact weight count
@@ -72,7 +72,6 @@ static GenLayout make_layout(const Problem& p, int tp) {
 static size_t gen_smem_bytes(const GenLayout& L, int rs) {
     size_t f = 2 * (size_t)L.wtot                 // weights + gradient
                + (size_t)L.rows_tot * L.ts        // activations
-               + 2 * (size_t)L.maxw * L.ts        // dZ ping-pong
                + (size_t)L.tp * rs                // staged records
                + 64;                              // reduction scratch
     return f * sizeof(float);
@@ -264,8 +263,8 @@ __device__ __forceinline__ int gen_backward_weights(float* __restrict__ gW, floa
 // dZprev[d][p] = (sum_o W[d][o] dZ[o][p]) * act'(Zprev[d][p]).  4 rows d x PT points per thread.  Rows d >= s_in read the
 // (finite) shared memory that follows W_l and are written as zero.
 template <int PT>
-__device__ __forceinline__ void gen_backward_input_tiles(const float* __restrict__ W, const float* __restrict__ dZ, const float* __restrict__ Zprev,
-                                                         const float* __restrict__ Aprev, float* __restrict__ dZprev, int s_in, int ws, int wsp,
+__device__ __forceinline__ void gen_backward_input_tiles(const float* __restrict__ W, const float* __restrict__ dZ, const float* Zprev,
+                                                         const float* __restrict__ Aprev, float* dZprev, int s_in, int ws, int wsp,
                                                          int tp, int ts, int act, int first) {
     // wsp: padded width of the previous layer (rows of dZprev to produce)
     const int ND = wsp >> 2, npt = tp / PT, ntile = ND * npt;
@@ -314,8 +313,8 @@ __device__ __forceinline__ void gen_backward_input_tiles(const float* __restrict
         }
     }
 }
-__device__ __forceinline__ void gen_backward_input(const float* __restrict__ W, const float* __restrict__ dZ, const float* __restrict__ Zprev,
-                                                   const float* __restrict__ Aprev, float* __restrict__ dZprev, int s_in, int ws, int wsp, int tp,
+__device__ __forceinline__ void gen_backward_input(const float* __restrict__ W, const float* __restrict__ dZ, const float* Zprev,
+                                                   const float* __restrict__ Aprev, float* dZprev, int s_in, int ws, int wsp, int tp,
                                                    int ts, int act, int first) {
     first %= (int)blockDim.x;
     if (!kSmallTiles || (wsp >> 2) * (tp >> 2) * 5 >= (int)blockDim.x * 4) gen_backward_input_tiles<4>(W, dZ, Zprev, Aprev, dZprev, s_in, ws, wsp, tp, ts, act, first);
@@ -356,9 +355,7 @@ k_logpost_generic(EvalArgs a, GenLayout L, const float* __restrict__ w, long lon
     float* Ws = smem;
     float* Gs = Ws + L.wtot;
     float* Act = Gs + L.wtot;
-    float* dZa = Act + (size_t)L.rows_tot * L.ts;
-    float* dZb = dZa + (size_t)L.maxw * L.ts;
-    float* rec = dZb + (size_t)L.maxw * L.ts;
+    float* rec = Act + (size_t)L.rows_tot * L.ts;
     double* red = reinterpret_cast<double*>(rec + (((size_t)L.tp * a.rs + 1) & ~(size_t)1));
 
     EvalCtx c = make_ctx(a, rec, nullptr, L.tp);
@@ -399,29 +396,29 @@ k_logpost_generic(EvalArgs a, GenLayout L, const float* __restrict__ w, long lon
                 __syncthreads();
                 Ain = Aout;
             }
-            // heads: dZ_K (weighted) and the value
-            float* dZ = dZa;
-            float* dZo = dZb;
+            // heads: dZ_K (weighted) and the value.  dZ_l overwrites Z_l in place (every element is read by the thread that
+            // rewrites it: the head reads its point's outputs first, the input-gradient tiles read act'(Z) where they store),
+            // so the backward pass needs no buffers of its own and more CTAs fit an SM.
             {
-                const float* Zl = Act + (size_t)L.arow[nl] * ts;
-                for (int i = threadIdx.x; i < L.ws[nl] * ts; i += blockDim.x) dZ[i] = 0.f;
-                __syncthreads();
+                float* Zl = Act + (size_t)L.arow[nl] * ts;
                 if (threadIdx.x < count) {
                     const float* r = rec + threadIdx.x * a.rs;
                     int kind = __float_as_int(r[a.s0]);
-                    lp += (double)head_dispatch(sk, kind, Zl, ts, threadIdx.x, r + a.s0 + 2, c.hc, r[a.s0 + 1], dZ);
+                    lp += (double)head_dispatch(sk, kind, Zl, ts, threadIdx.x, r + a.s0 + 2, c.hc, r[a.s0 + 1], Zl);
                 }
+                const int dead = tp - count;                         // points beyond the tile: zero gradient (pad rows are zero already)
+                for (int i = threadIdx.x; i < L.ws[nl] * dead; i += blockDim.x) Zl[(i / dead) * ts + count + i % dead] = 0.f;
                 __syncthreads();
             }
             for (int l = nl; l >= 1; --l) {
+                const float* dZ = Act + (size_t)L.arow[l] * ts;
                 const float* Aprev = (l == 1) ? Act : Act + ((size_t)L.arow[l - 1] + L.ws[l - 1]) * ts;
                 const int used = gen_backward_weights(Gs + L.woff[l], Gs + L.boff[l], Aprev, dZ, L.s[l - 1], L.s[l], L.ws[l], tp, ts);
                 if (l > 1) {
-                    const float* Zprev = Act + (size_t)L.arow[l - 1] * ts;
-                    gen_backward_input(Ws + L.woff[l], dZ, Zprev, Aprev, dZo, L.s[l - 1], L.ws[l], L.ws[l - 1], tp, ts, L.act, used);
+                    float* Zprev = Act + (size_t)L.arow[l - 1] * ts;
+                    gen_backward_input(Ws + L.woff[l], dZ, Zprev, Aprev, Zprev, L.s[l - 1], L.ws[l], L.ws[l - 1], tp, ts, L.act, used);
                 }
                 __syncthreads();
-                float* t = dZ; dZ = dZo; dZo = t;
             }
         }
         // Gaussian prior, value reduction, compact gradient write-out
