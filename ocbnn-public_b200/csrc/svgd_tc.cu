@@ -142,6 +142,11 @@ static int pick_splits(long long n_rows, long long n4, int two_dp, int bn) {
 static int fused_splits(long long n_rows, long long n4);
 long long tc_workspace_bytes(long long n, long long d, long long n_rows);      // K splits of the fused phi kernel (defined with it)
 
+static bool fused_enabled() {          // OCBNN_SVGD_FUSED=0 forces the unfused phi pipeline (K materialised as hi/lo matrices, TMA-fed GEMM)
+    static const bool on = [] { const char* e = getenv("OCBNN_SVGD_FUSED"); return !(e && e[0] == '0'); }();
+    return on;
+}
+constexpr int kFusedMaxSplitsHost = 16; // = kFusedMaxSplits
 constexpr int kSelSamplesHost = 32768;      // = kSelSamples (pair sample of the bracket select, defined with its kernels)
 
 static TcWs carve(void* workspace, long long n, long long d, long long row_begin, long long n_rows) {
@@ -160,8 +165,11 @@ static TcWs carve(void* workspace, long long n, long long d, long long row_begin
     w.xc_hi = take(n * w.dp);
     w.xc_lo = take(n * w.dp);
     w.d2 = take(n_rows * w.n4);
-    w.k_hi = take(n_rows * w.n4);
-    w.k_lo = take(n_rows * w.n4);
+    // the K matrices (hi / lo, n_rows x n4 each) exist only on the unfused path; the fused phi kernel (one N tile) keeps K on
+    // chip and needs only the per-split row sums there (2/3 of the workspace at large n)
+    const bool fused = fused_enabled() && 2 * w.dp <= w.bn;
+    w.k_hi = take(fused ? (long long)kFusedMaxSplitsHost * n_rows : n_rows * w.n4);
+    w.k_lo = take(fused ? 0 : n_rows * w.n4);
     w.vt_hi = take(2 * w.dp * w.n4);
     w.vt_lo = take(2 * w.dp * w.n4);
     w.rowsum = take(n_rows);
@@ -994,7 +1002,7 @@ struct FusedCfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
     static constexpr int kTmemCols = BN < 32 ? 32 : BN;
 };
-constexpr int kFusedCtasPerSm = 2, kFusedMaxSplits = 16;
+constexpr int kFusedCtasPerSm = 2, kFusedMaxSplits = kFusedMaxSplitsHost;
 constexpr int kFusedProducers = 8;                       // producer warps (warps 2..9; warps 2..5 are also the epilogue warps)
 constexpr int kFusedThreads = 32 * (2 + kFusedProducers);
 static int fused_splits(long long n_rows, long long n4) {
@@ -1212,8 +1220,7 @@ static int tc_prepare(const TcWs& w, const float* x, unsigned* hist0, bool* hist
 }
 
 static int tc_phi(const TcWs& w, const float* g, const float* h, float* phi, cudaStream_t st) {
-    // OCBNN_SVGD_FUSED=0 forces the unfused pipeline (K materialised as hi/lo matrices, TMA-fed GEMM)
-    static const bool fused_ok = [] { const char* e = getenv("OCBNN_SVGD_FUSED"); return !(e && e[0] == '0'); }();
+    const bool fused_ok = fused_enabled();
     dim3 gv((unsigned)((w.n4 + 31) / 32), (unsigned)(2 * w.dp / 32));
     k_vt_split<<<gv, 256, 0, st>>>(g, w.xc_hi, w.xc_lo, w.n, w.n4, (int)w.d, (int)w.dp, w.vt_hi, w.vt_lo);
     OCBNN_LAUNCH_CHECK();
