@@ -215,6 +215,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # NCCL's own messages (e.g. its version banner) stay off stdout: one JSON line
         dist.init_process_group("nccl", device_id=dev)
     from ocbnn_b200 import engine, workloads
 
