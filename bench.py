@@ -460,6 +460,14 @@ def extras(m, prob, dev, args):
         u3 = torch.rand(1, M3, device=dev, dtype=torch.float64)
         t = _time_cuda(lambda: p3.hmc_iterate(q3, p03, u3, m3.hmc_epsilon, L, True, want_flags=False), reps=2)
         out["hmc_W3_classifier_chain_leapfrog_steps_per_s"] = M3 * L / t
+        m4 = workloads.build("W4P", seed=0)         # F4 shape: [2,10,1] binary classifier, toy5 (20 points), AOCP prior
+        p4 = m4.engine_problem()
+        M4 = 262144
+        q4 = (m4.aocp_mean[None] + m4.aocp_std[None] * torch.randn(M4, m4.nweights)).to(dev).contiguous()
+        p04 = torch.randn(1, M4, m4.nweights, device=dev)
+        u4 = torch.rand(1, M4, device=dev, dtype=torch.float64)
+        t = _time_cuda(lambda: p4.hmc_iterate(q4, p04, u4, m4.hmc_epsilon, L, True, want_flags=False), reps=2)
+        out["hmc_W4P_binary_aocp_chain_leapfrog_steps_per_s"] = M4 * L / t
         k = 4096
         mb = workloads.build("W6", seed=0, bbb_esamples=k)
         qp = torch.cat([0.3 * torch.randn(mb.nweights, 1), torch.ones(mb.nweights, 1) * -3.0], 1).to(dev).contiguous()

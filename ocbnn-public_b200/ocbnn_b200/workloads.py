@@ -86,7 +86,8 @@ def ifunc_f3b(X):          # run_toys.py:192 — y must avoid (1, 2.5) for x in 
 
 def build(workload, config_path="bench_cfg.yaml", sampler=None, seed=0, **overrides):
     """Model for a named workload of SURVEY §8(d): W1 (example.yaml), W2 (F1a.yaml + negative COCP), W3 (F2a.yaml + Dirichlet
-    COCP), W4 (F3b.yaml SVGD + negative COCP), W6 (credit.yaml shape), W7 (recid.yaml shape, AOCP prior)."""
+    COCP), W4 (F3b.yaml SVGD + negative COCP), W4P (F4.yaml shape: binary classifier + AOCP prior), W6 (credit.yaml shape), W7 (recid.yaml
+    shape, AOCP prior)."""
     from . import models as M
     torch.manual_seed(seed)
     w = workload.upper()
@@ -108,6 +109,16 @@ def build(workload, config_path="bench_cfg.yaml", sampler=None, seed=0, **overri
         m = cls(uid=w, configfile=write_config(config_path, **overrides))
         m.load(**toy4())
         m.add_deterministic_constraint(constrained_domain=(-1.0, 1.0), interval_func=ifunc_f3b, prior_type="negative_exponential_cocp")
+        m.update_config(use_ocbnn=True)
+    elif w in ("W4P", "W4'"):                     # F4-shaped: binary classifier on toy5 with an AOCP diagonal-Gaussian prior (run_toys.py:267-286)
+        cls = getattr(M, f"BNN{sampler or 'HMC'}BinaryClassifier")
+        kw = dict(ocp_nsamples=1000, aocp_std_multiplier=30)
+        kw.update(overrides)
+        m = cls(uid="W4P", configfile=write_config(config_path, **kw))
+        m.load(**toy5())
+        g = torch.Generator().manual_seed(7)
+        params = torch.stack([0.5 * torch.randn(m.nweights, generator=g), -0.5 + 0.3 * torch.randn(m.nweights, generator=g)], 1)
+        m._set_aocp(params)                       # synthetic stand-in for repro/F4_aocp.pt (same shape and scale)
         m.update_config(use_ocbnn=True)
     elif w == "W6":
         cls = getattr(M, f"BNN{sampler or 'BBB'}Classifier")
