@@ -345,10 +345,9 @@ k_hist_d2(const float* __restrict__ d2, const float* __restrict__ ssum, long lon
 //                  ~200 candidates) and counts them in a 4096-bin LINEAR histogram over the bracket (uniform occupancy, so
 //                  the global atomics do not collide);
 //   k_sel_gather   every CTA locates the histogram bin that holds the wanted rank and the candidates of that bin are
-//                  appended to a second, short list;
-//   k_sel_final    one CTA radix-selects (11 + 11 + 10 bits) inside the short list and emits h = med^2 / ln n.  If the
-//                  bracket missed (never observed; probability ~1e-8 per call) or a list overflowed, the same CTA falls
-//                  back to the 3-pass radix select over d2.  Exact either way.
+//                  appended to a second, short list; the LAST CTA to finish radix-selects (11 + 11 + 10 bits) inside the
+//                  short list and emits h = med^2 / ln n.  If the bracket missed (never observed; probability ~1e-8 per
+//                  call) or a list overflowed, that CTA falls back to the 3-pass radix select over d2.  Exact either way.
 struct SelHdr {                 // 64 bytes in the workspace
     float lo, hi;
     unsigned ncand, overflow;
@@ -356,7 +355,7 @@ struct SelHdr {                 // 64 bytes in the workspace
     unsigned n2, bin;           // short list length, hit bin
     unsigned long long resid;   // rank inside the hit bin
     unsigned long long ncand_tot;   // candidates over all ranks (multi-rank flow; = ncand on one rank)
-    unsigned ok, pad32;             // multi-rank flow: bracket hit (set by k_sel_gather)
+    unsigned ok, done;              // multi-rank flow: bracket hit (set by k_sel_gather); single rank: CTAs of k_sel_gather that have finished
 };
 // The whole select works on w = d^2 (the eps-perturbed SQUARED distance): sqrt is monotone, so the k-th smallest distance is
 // the root of the k-th smallest w, exact zeros are the same pairs, and no pair needs a square root - only the answer does.
@@ -463,7 +462,7 @@ k_sel_bracket(const float* __restrict__ samples, SelHdr* __restrict__ hdr, unsig
         if (cnt == 0) { lo = 0.f; hi = 0.f; }
         if (sabotage) { lo = mx * 4.f + 1.f; hi = mx * 8.f + 2.f; }
         hdr->lo = lo; hdr->hi = hi;
-        hdr->ncand = 0u; hdr->overflow = 0u; hdr->zeros = 0ull; hdr->below = 0ull; hdr->n2 = 0u; hdr->bin = 0u; hdr->resid = 0ull;
+        hdr->ncand = 0u; hdr->overflow = 0u; hdr->zeros = 0ull; hdr->below = 0ull; hdr->n2 = 0u; hdr->bin = 0u; hdr->resid = 0ull; hdr->done = 0u;
     }
 }
 
@@ -537,49 +536,25 @@ __device__ __forceinline__ bool sel_ok(const SelHdr* hdr, long long n, unsigned 
     return !hdr->overflow && nz > 0 && rank >= hdr->below && rank < hdr->below + ncand_tot;
 }
 
-__global__ void __launch_bounds__(256)
-k_sel_gather(long long n, SelHdr* __restrict__ hdr, const unsigned* __restrict__ ghist, const float* __restrict__ cand, float* __restrict__ list2,
-             long long cap2, int multi) {
-    __shared__ unsigned wsum[8];
-    __shared__ int s_bin;
-    __shared__ unsigned long long s_res;
-    unsigned long long rank, resid;
-    const bool ok = sel_ok(hdr, n, &rank, multi ? hdr->ncand_tot : hdr->ncand);
-    if (multi && blockIdx.x == 0 && threadIdx.x == 0) hdr->ok = ok ? 1u : 0u;
-    if (!ok) return;                                    // uniform over the grid: the final stage takes the fallback
-    const int b1 = block_find_bin<256, 16>(ghist, rank - hdr->below, &resid, wsum, &s_bin, &s_res);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { hdr->bin = (unsigned)b1; hdr->resid = resid; }
-    const float lo = hdr->lo, hi = hdr->hi;
-    const float scale = hi > lo ? (float)kSelBins / (hi - lo) : 0.f;
-    const unsigned ncand = hdr->ncand;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += gridDim.x * blockDim.x) {
-        const float v = cand[i];
-        if (sel_lbin(v, lo, scale) == b1) {
-            const unsigned pos = atomicAdd(&hdr->n2, 1u);
-            if ((long long)pos < cap2) list2[pos] = v;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(1024)
-k_sel_final(const float* __restrict__ d2, const float* __restrict__ ssum, long long n, long long n4, int d, const SelHdr* __restrict__ hdr,
-            const float* __restrict__ list2, long long cap2, float* __restrict__ out_h, unsigned long long* __restrict__ dbg) {
-    __shared__ unsigned sh[2048];
-    __shared__ unsigned wsum[32];
-    __shared__ int s_bin;
-    __shared__ unsigned long long s_res;
+// last stage of the select, run by ONE CTA of NT threads: radix select (11 + 11 + 10 bits) inside the short list of the hit
+// bin - or, if the bracket missed, over the whole upper triangle of d2 - and h = med^2 / ln n.  Fields that other CTAs of the
+// same launch wrote (n2, resid) are read past the L1 (__ldcg).
+template <int NT>
+__device__ __forceinline__ void sel_final_body(const float* __restrict__ d2, const float* __restrict__ ssum, long long n, long long n4, int d,
+                                               const SelHdr* hdr, const float* list2, long long cap2, float* __restrict__ out_h,
+                                               unsigned long long* __restrict__ dbg, unsigned* sh, unsigned* wsum, int* s_bin, unsigned long long* s_res) {
     const int t = threadIdx.x;
     unsigned long long rank;
-    const bool ok = sel_ok(hdr, n, &rank, hdr->ncand) && (long long)hdr->n2 <= cap2;
+    const unsigned n2 = __ldcg(&hdr->n2);
+    const bool ok = sel_ok(hdr, n, &rank, hdr->ncand) && (long long)n2 <= cap2;
     const unsigned long long pairs = (unsigned long long)n * (unsigned long long)(n - 1) / 2ull;
     float med = nanf("");                               // torch: median of an empty tensor
     if (pairs != hdr->zeros) {
         unsigned prefix = 0;
-        unsigned long long r = ok ? hdr->resid : rank;
-        const unsigned n2 = hdr->n2;
+        unsigned long long r = ok ? __ldcg(&hdr->resid) : rank;
         for (int pass = 0; pass < 3; ++pass) {
             __syncthreads();
-            for (int i = t; i < 2048; i += 1024) sh[i] = 0u;
+            for (int i = t; i < 2048; i += NT) sh[i] = 0u;
             __syncthreads();
             auto add = [&](unsigned bits) {
                 if (pass == 0) atomicAdd(&sh[bits >> 21], 1u);
@@ -587,18 +562,18 @@ k_sel_final(const float* __restrict__ d2, const float* __restrict__ ssum, long l
                 else if ((bits >> 10) == (prefix >> 10)) atomicAdd(&sh[bits & 1023u], 1u);
             };
             if (ok) {
-                for (unsigned i = t; i < n2; i += 1024) add(__float_as_uint(list2[i]));
+                for (unsigned i = t; i < n2; i += NT) add(__float_as_uint(__ldcg(list2 + i)));
             } else {
                 // fallback: radix select over the upper triangle of d2 (one CTA; never taken with a sane bracket; 32-bit bin
                 // counts, i.e. n <= 92681)
                 for (long long i = 0; i < n; ++i)
-                    for (long long j = i + 1 + t; j < n; j += 1024) {
+                    for (long long j = i + 1 + t; j < n; j += NT) {
                         const unsigned bits = __float_as_uint(pair_dist(d2, ssum, n4, d, i, j));
                         if (bits != 0u) add(bits);
                     }
             }
             __syncthreads();
-            const int b = block_find_bin<1024, 2>(sh, r, &r, wsum, &s_bin, &s_res);
+            const int b = block_find_bin<NT, 2048 / NT>(sh, r, &r, wsum, s_bin, s_res);
             prefix |= pass == 0 ? ((unsigned)b << 21) : pass == 1 ? ((unsigned)b << 10) : (unsigned)b;
         }
         med = sqrtf(__uint_as_float(prefix));           // the select ran on squared distances
@@ -608,6 +583,44 @@ k_sel_final(const float* __restrict__ d2, const float* __restrict__ ssum, long l
         if (dbg) { dbg[0] = ok ? 1ull : 0ull; dbg[1] = hdr->ncand; dbg[2] = hdr->below; dbg[3] = hdr->zeros; }
     }
 }
+
+// Single rank (multi = 0): gather + final in one launch - the last CTA to finish (ticket in hdr->done) runs the final select.
+__global__ void __launch_bounds__(256)
+k_sel_gather(long long n, SelHdr* hdr, const unsigned* __restrict__ ghist, const float* __restrict__ cand, float* list2, long long cap2, int multi,
+             const float* __restrict__ d2, const float* __restrict__ ssum, long long n4, int d, float* __restrict__ out_h,
+             unsigned long long* __restrict__ dbg) {
+    __shared__ unsigned sh[2048];
+    __shared__ unsigned wsum[8];
+    __shared__ int s_bin;
+    __shared__ unsigned long long s_res;
+    __shared__ bool s_last;
+    unsigned long long rank, resid;
+    const bool ok = sel_ok(hdr, n, &rank, multi ? hdr->ncand_tot : hdr->ncand);
+    if (multi && blockIdx.x == 0 && threadIdx.x == 0) hdr->ok = ok ? 1u : 0u;
+    if (ok) {                                           // uniform over the grid; otherwise the final stage takes the fallback
+        const int b1 = block_find_bin<256, 16>(ghist, rank - hdr->below, &resid, wsum, &s_bin, &s_res);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { hdr->bin = (unsigned)b1; hdr->resid = resid; }
+        const float lo = hdr->lo, hi = hdr->hi;
+        const float scale = hi > lo ? (float)kSelBins / (hi - lo) : 0.f;
+        const unsigned ncand = hdr->ncand;
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += gridDim.x * blockDim.x) {
+            const float v = cand[i];
+            if (sel_lbin(v, lo, scale) == b1) {
+                const unsigned pos = atomicAdd(&hdr->n2, 1u);
+                if ((long long)pos < cap2) list2[pos] = v;
+            }
+        }
+    }
+    if (multi) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&hdr->done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    sel_final_body<256>(d2, ssum, n, n4, d, hdr, list2, cap2, out_h, dbg, sh, wsum, &s_bin, &s_res);
+}
+
 
 // ---- bracket select across ranks ---------------------------------------------------------------------------------------
 // Every rank holds all particles (all-gather) and the distances of ITS rows.  The bracket is sampled from X, so every rank
@@ -1293,9 +1306,7 @@ int tc_svgd_select_fast(long long n, long long d, void* ws, float* out_h, int mo
     OCBNN_LAUNCH_CHECK();
     k_sel_count<<<(unsigned)(n < 148 * 8 ? n : 148 * 8), 256, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, 0, n, hdr, w.cand, w.cand_cap, w.ghist);
     OCBNN_LAUNCH_CHECK();
-    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap, 0);
-    OCBNN_LAUNCH_CHECK();
-    k_sel_final<<<1, 1024, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, hdr, w.list2, w.cand_cap, out_h, dbg);
+    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap, 0, w.d2, w.s, w.n4, (int)d, out_h, dbg);      // gather + final
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }
@@ -1309,9 +1320,7 @@ int tc_svgd_prepare_select(const float* x, long long n, long long d, void* ws, l
     if (rc) return rc;
     if (!sel_done) return tc_svgd_select_fast(n, d, ws, out_h, mode, dbg, st);
     SelHdr* hdr = reinterpret_cast<SelHdr*>(w.sel);
-    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap, 0);
-    OCBNN_LAUNCH_CHECK();
-    k_sel_final<<<1, 1024, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, hdr, w.list2, w.cand_cap, out_h, dbg);
+    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap, 0, w.d2, w.s, w.n4, (int)d, out_h, dbg);      // gather + final
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }
@@ -1342,7 +1351,7 @@ int tc_svgd_sel_gather(long long n, long long d, long long row_begin, long long 
     SelHdr* hdr = reinterpret_cast<SelHdr*>(w.sel);
     k_sel_unpack<<<8, 256, 0, st>>>(hdr, w.ghist, w.red64);
     OCBNN_LAUNCH_CHECK();
-    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap, 1);
+    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap, 1, w.d2, w.s, w.n4, (int)d, nullptr, nullptr);
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }
