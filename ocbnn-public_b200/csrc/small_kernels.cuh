@@ -296,6 +296,10 @@ struct SmallLaunch {
             if (mb <= 2) { if (uu <= 1) OCBNN_HMC_GO(2, 1); OCBNN_HMC_GO(2, 2); }
             if (mb == 3) { if (uu <= 1) OCBNN_HMC_GO(3, 1); if (uu <= 2) OCBNN_HMC_GO(3, 2); OCBNN_HMC_GO(3, 4); }
             if (uu >= 4) OCBNN_HMC_GO(3, 4);
+            // long point segments: four points in flight at 3 CTAs/SM are ~1 % faster than two at 4 (W2: 2.06 vs 2.04 G steps/s); short
+            // segments (W1: 6 points) lose 8 % to the partial groups
+            static const bool auto_cfg = !getenv("OCBNN_HMC_MB") && !getenv("OCBNN_HMC_U");
+            if (auto_cfg && N::NS <= 18 && a.n_cpoints >= 64) OCBNN_HMC_GO(3, 4);
             OCBNN_HMC_GO(4, 2);
 #undef OCBNN_HMC_GO
         }

@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence for the bench command: (1) launch list with device times, (2) one full capture of the dominant kernel.
 mkdir -p gpurun_out
-CMD="env OCBNN_HMC_MB=${MB:-4} OCBNN_HMC_U=${U:-2} python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-svgd --chains ${CHAINS:-262144}"
+CMD="env OCBNN_HMC_MB=${MB:-3} OCBNN_HMC_U=${U:-4} python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-svgd --chains ${CHAINS:-262144}"
 $CMD > gpurun_out/ncu_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 $CMD > gpurun_out/ncu_plain2.log 2>&1 &&
