@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--no-svgd", action="store_true", help="skip the secondary SVGD particle-iters/s measurement")
     ap.add_argument("--extras", action="store_true", help="also time SVGD/SGLD/BBB and the chain-count sweep (extra JSON keys)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-seconds", type=float, default=0.0, help="total CPU budget of --impl reference (default: max(20, 8 s per step))")
     return ap.parse_args()
 
 
@@ -192,7 +193,7 @@ def run_reference(args):
         m = workloads.build(args.workload, seed=0)
         arr = _oracle_spec_arrays(m)
         os.chdir(cwd)
-    rate, cores, M, t_step, how = cpu_hmc_rate(arr, args.leapfrog, seconds=max(20.0, 8.0 * (args.steps + args.warmup)), steps=args.steps, warmup=args.warmup)
+    rate, cores, M, t_step, how = cpu_hmc_rate(arr, args.leapfrog, seconds=args.ref_seconds or max(20.0, 8.0 * (args.steps + args.warmup)), steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "chains": M,
