@@ -349,7 +349,8 @@ __device__ __forceinline__ float head_dispatch(int sk, int kind, const float* Zl
     }
 }
 
-__global__ void __launch_bounds__(kGenThreads, 4)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 k_logpost_generic(EvalArgs a, GenLayout L, const float* __restrict__ w, long long m, float* __restrict__ out_lp, float* __restrict__ out_grad) {
     extern __shared__ __align__(16) float smem[];
     float* Ws = smem;
@@ -508,12 +509,14 @@ static int pick_tp(const Problem& p, GenLayout& L, bool with_grad) {
         const size_t need = need_for(force);
         return (long long)need <= cap ? (int)need : -1;
     }
-    for (int want : {3, 2, 1})
+    for (int want : {3, 2})
         for (int tp : {32, 16}) {
             const size_t need = need_for(tp);
             if ((long long)need <= cap && cap / (long long)(need + 1024) >= want) return (int)need;
         }
-    for (int tp : {8, 4}) {
+    // one CTA per SM (512 threads, see launch_logpost_generic): the largest tile that fits (recid, 4096 particles: 64-point tiles
+    // 1.40 ms, 32-point tiles 1.58 ms; with 256 threads 2.17 ms)
+    for (int tp : {64, 32, 16, 8, 4}) {
         const size_t need = need_for(tp);
         if ((long long)need <= cap) return (int)need;
     }
@@ -527,11 +530,22 @@ int launch_logpost_generic(const Problem& p, const EvalArgs& a, const float* w, 
     GenLayout L;
     int sm = pick_tp(p, L, true);
     OCBNN_REQUIRE(sm > 0, OCBNN_EUNSUPPORTED, "network with %d weights does not fit the shared-memory resident kernel", p.d);
-    OCBNN_CUDA(cudaFuncSetAttribute(k_logpost_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     int per_sm = (int)((long long)p.max_smem_optin / sm);
     if (per_sm < 1) per_sm = 1;
     long long grid = m < (long long)p.sm_count * per_sm * 4 ? m : (long long)p.sm_count * per_sm * 4;
-    k_logpost_generic<<<(unsigned)grid, kGenThreads, sm, st>>>(a, L, w, m, out_lp, out_grad);
+    // nets whose weights + gradient leave room for ONE CTA per SM (recid: 95 KB) run it with 512 threads: twice the warps to
+    // hide latency with, and the 650-tile weight-gradient lists take 2 rounds instead of 3.  OCBNN_GEN_THREADS overrides.
+    static const int force_nt = [] { const char* e = getenv("OCBNN_GEN_THREADS"); return e ? atoi(e) : 0; }();
+    const int nt = force_nt ? force_nt : (per_sm == 1 ? 512 : 256);
+    if (nt >= 512) {
+        auto k = k_logpost_generic<512, 1>;
+        OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        k<<<(unsigned)grid, 512, sm, st>>>(a, L, w, m, out_lp, out_grad);
+    } else {
+        auto k = k_logpost_generic<256, 4>;
+        OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        k<<<(unsigned)grid, 256, sm, st>>>(a, L, w, m, out_lp, out_grad);
+    }
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }
