@@ -494,10 +494,9 @@ k_forward_generic(GenLayout L, const float* __restrict__ w, long long m, const f
     }
 }
 
-// Points per tile vs resident CTAs per SM.  Measured on B200: on W6 (credit, D = 3202) 32-point tiles with 3 CTAs/SM beat
-// 64-point tiles with 1-2 CTAs/SM by 20 %; on W7 (recid, D = 11201, weights + gradient = 95 KB) trading the tile down to 4-8
-// points to squeeze a second CTA in halves the throughput (the 4x4 register tiles lose their reuse).  So: tiles of >= 16 points
-// first (most resident CTAs wins), smaller tiles only when nothing else fits.
+// Points per tile vs resident CTAs per SM.  On W7 (recid, D = 11201, weights + gradient = 95 KB) trading the tile down to 4-8
+// points to squeeze a second CTA in halves the throughput (the 4x4 register tiles lose their reuse).  So: the largest tile of >= 16 points
+// that still leaves two resident CTAs, smaller tiles only when nothing else fits.
 static int pick_tp(const Problem& p, GenLayout& L, bool with_grad) {
     auto need_for = [&](int tp) {
         L = make_layout(p, tp);
@@ -509,11 +508,12 @@ static int pick_tp(const Problem& p, GenLayout& L, bool with_grad) {
         const size_t need = need_for(force);
         return (long long)need <= cap ? (int)need : -1;
     }
-    for (int want : {3, 2})
-        for (int tp : {32, 16}) {
-            const size_t need = need_for(tp);
-            if ((long long)need <= cap && cap / (long long)(need + 1024) >= want) return (int)need;
-        }
+    // measured on W6 (credit, in-place dZ): 64-point tiles at 2 CTAs/SM 15.1 ms, 32-point tiles at 3 CTAs/SM 15.7 ms, 24- and 16-point
+    // tiles at 4 CTAs/SM 16.1 / 19.7 ms -> 64-point tiles as long as two CTAs fit, then 32, then 16
+    for (int tp : {64, 32, 16}) {
+        const size_t need = need_for(tp);
+        if ((long long)need <= cap && cap / (long long)(need + 1024) >= 2) return (int)need;
+    }
     // one CTA per SM (512 threads, see launch_logpost_generic): the largest tile that fits (recid, 4096 particles: 64-point tiles
     // 1.40 ms, 32-point tiles 1.58 ms; with 256 threads 2.17 ms)
     for (int tp : {64, 32, 16, 8, 4}) {
@@ -537,7 +537,11 @@ int launch_logpost_generic(const Problem& p, const EvalArgs& a, const float* w, 
     // hide latency with, and the 650-tile weight-gradient lists take 2 rounds instead of 3.  OCBNN_GEN_THREADS overrides.
     static const int force_nt = [] { const char* e = getenv("OCBNN_GEN_THREADS"); return e ? atoi(e) : 0; }();
     const int nt = force_nt ? force_nt : (per_sm == 1 ? 512 : 256);
-    if (nt >= 512) {
+    if (nt >= 512 && per_sm >= 2) {                     // experiment knob (OCBNN_GEN_THREADS=512 with a tile that leaves >= 2 CTAs/SM)
+        auto k = k_logpost_generic<512, 2>;
+        OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        k<<<(unsigned)grid, 512, sm, st>>>(a, L, w, m, out_lp, out_grad);
+    } else if (nt >= 512) {
         auto k = k_logpost_generic<512, 1>;
         OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         k<<<(unsigned)grid, 512, sm, st>>>(a, L, w, m, out_lp, out_grad);
