@@ -34,6 +34,7 @@ struct GenLayout {
     int maxw;                        // widest padded layer
     int tp, ts;                      // points per tile, row stride
     int act;
+    int sched;                       // backward schedule, see the kernel (1: weight lists fill idle slots / closing phase; 0: dW_l with dA_{l-1})
     int d;                           // compact weight count
 };
 
@@ -65,6 +66,8 @@ static GenLayout make_layout(const Problem& p, int tp) {
     L.tp = tp;
     L.ts = tp + 4;
     L.act = p.desc.activation;
+    static const int sched = [] { const char* e = getenv("OCBNN_GEN_SCHED"); return e ? atoi(e) : 1; }();
+    L.sched = sched;
     L.d = coff;
     return L;
 }
@@ -110,16 +113,36 @@ struct FastDiv {
     }
 };
 
+// Item -> register tile.  Shared-memory bandwidth, not the FMA pipe, bounds these layers (ncu: LSU wavefronts 61 % of peak at
+// 28 % FMA).  Measured rule (profiles/r01_generic_k1_w6_ncu_summary.txt): an LDS.128 is served per quarter-warp, 128 B a wavefront;
+// the two quarters of a half-warp merge only when their address sets are identical, the two halves never.  With 4 x 4 register
+// tiles one operand can have identical quarters (2 wavefronts) and the other cannot (4): 6 wavefronts per 16 FFMA, i.e. 6 LSU
+// cycles against 4 FMA cycles whatever the hand-out order - only larger register tiles (or tensor cores) change that ratio.
+// The 16 lanes of a half-warp take a 4 x 4 block of neighbouring tiles (so every operand load of a half-warp stays within 64 B
+// and bank-conflict free: 72 M conflict wavefronts instead of 153 M); lists are padded to whole blocks, lanes on a pad tile skip.
+struct TileMap {
+    int n0, n1, padded;
+    FastDiv dv;
+    __device__ __forceinline__ TileMap(int a, int b) : n0(a), n1(b), padded(((a + 3) >> 2) * ((b + 3) >> 2) * 16), dv((b + 3) >> 2) {}
+    __device__ __forceinline__ bool decode(int item, int& i0, int& i1) const {
+        int b0, b1;
+        dv.divmod(item >> 4, b0, b1);
+        i0 = 4 * b0 + ((item >> 2) & 3);
+        i1 = 4 * b1 + (item & 3);
+        return i0 < n0 && i1 < n1;
+    }
+};
+__device__ __host__ __forceinline__ int padded_items(int a, int b) { return ((a + 3) >> 2) * ((b + 3) >> 2) * 16; }
+
 // Z[o][p] = b[o] + sum_d W[d][o] A[d][p] ; Aout = act(Z) unless last.   PT points x 4 outputs per thread.
 template <int PT>
 __device__ __forceinline__ void gen_forward_tiles(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ Ain,
                                                   float* __restrict__ Z, float* __restrict__ Aout, int s_in, int ws, int tp, int ts, int act,
                                                   bool last) {
-    const int npt = tp / PT, ntile = (ws >> 2) * npt;
-    const FastDiv dv(npt);
-    for (int tile = threadIdx.x; tile < ntile; tile += blockDim.x) {
+    const TileMap tm(ws >> 2, tp / PT);
+    for (int tile = threadIdx.x; tile < tm.padded; tile += blockDim.x) {
         int ot, pt;
-        dv.divmod(tile, ot, pt);
+        if (!tm.decode(tile, ot, pt)) continue;
         const float4 bb = *reinterpret_cast<const float4*>(b + 4 * ot);
         float acc[4][PT];
 #pragma unroll
@@ -187,12 +210,12 @@ __device__ __forceinline__ void gen_forward_layer(const float* __restrict__ W, c
 // (the duplicate result is not stored), so the point loop has no guards.
 template <int OJ>
 __device__ __forceinline__ void gen_backward_weights_tiles(float* __restrict__ gW, const float* __restrict__ Ain, const float* __restrict__ dZ,
-                                                           int s_in, int s_out, int ws, int tp, int ts) {
-    const int ND = (s_in + 3) >> 2, NO = (ws + OJ - 1) / OJ, ntile = ND * NO;
-    const FastDiv dv(ND);
-    for (int tile = threadIdx.x; tile < ntile; tile += blockDim.x) {
+                                                           int s_in, int s_out, int ws, int tp, int ts, int first) {
+    const int ND = (s_in + 3) >> 2, NO = (ws + OJ - 1) / OJ;
+    const TileMap tm(NO, ND);
+    for (int tile = item_begin(first); tile < tm.padded; tile += blockDim.x) {
         int ot, dt;
-        dv.divmod(tile, ot, dt);
+        if (!tm.decode(tile, ot, dt)) continue;
         float acc[4][OJ];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -234,18 +257,17 @@ __device__ __forceinline__ void gen_backward_weights_tiles(float* __restrict__ g
         }
     }
 }
-// returns the number of list items (so that the caller can continue the hand-out with the next list)
-__device__ __forceinline__ int gen_backward_weights(float* __restrict__ gW, float* __restrict__ gb, const float* __restrict__ Ain,
-                                                    const float* __restrict__ dZ, int s_in, int s_out, int ws, int tp, int ts) {
+// number of items of a layer's weight-gradient list (so that the caller can continue the hand-out with the next list)
+__device__ __forceinline__ int gen_backward_weights_items(int s_in, int ws) {
     const int T = (int)blockDim.x, ND = (s_in + 3) >> 2;
-    int items;
-    if (!kSmallTiles || ND * (ws >> 2) * 5 >= T * 4) {
-        items = ND * ((ws + 3) / 4);
-        gen_backward_weights_tiles<4>(gW, Ain, dZ, s_in, s_out, ws, tp, ts);
-    } else {
-        items = ND * ((ws + 1) / 2);
-        gen_backward_weights_tiles<2>(gW, Ain, dZ, s_in, s_out, ws, tp, ts);
-    }
+    return (!kSmallTiles || ND * (ws >> 2) * 5 >= T * 4) ? padded_items((ws + 3) / 4, ND) : padded_items((ws + 1) / 2, ND);
+}
+__device__ __forceinline__ void gen_backward_weights(float* __restrict__ gW, float* __restrict__ gb, const float* __restrict__ Ain,
+                                                     const float* __restrict__ dZ, int s_in, int s_out, int ws, int tp, int ts, int first) {
+    const int T = (int)blockDim.x, ND = (s_in + 3) >> 2;
+    first %= T;
+    if (!kSmallTiles || ND * (ws >> 2) * 5 >= T * 4) gen_backward_weights_tiles<4>(gW, Ain, dZ, s_in, s_out, ws, tp, ts, first);
+    else gen_backward_weights_tiles<2>(gW, Ain, dZ, s_in, s_out, ws, tp, ts, first);
     // bias gradient: one thread per output, handed out from the top so that it lands on threads the tile list left idle
     for (int o = (int)blockDim.x - 1 - (int)threadIdx.x; o < s_out; o += blockDim.x) {
         float s0 = 0.f, s1 = 0.f;
@@ -257,7 +279,6 @@ __device__ __forceinline__ int gen_backward_weights(float* __restrict__ gW, floa
         }
         gb[o] += s0 + s1;
     }
-    return items;
 }
 
 // dZprev[d][p] = (sum_o W[d][o] dZ[o][p]) * act'(Zprev[d][p]).  4 rows d x PT points per thread.  Rows d >= s_in read the
@@ -267,11 +288,11 @@ __device__ __forceinline__ void gen_backward_input_tiles(const float* __restrict
                                                          const float* __restrict__ Aprev, float* dZprev, int s_in, int ws, int wsp,
                                                          int tp, int ts, int act, int first) {
     // wsp: padded width of the previous layer (rows of dZprev to produce)
-    const int ND = wsp >> 2, npt = tp / PT, ntile = ND * npt;
-    const FastDiv dv(ND);
-    for (int tile = item_begin(first); tile < ntile; tile += blockDim.x) {
+    const int ND = wsp >> 2;
+    const TileMap tm(tp / PT, ND);
+    for (int tile = item_begin(first); tile < tm.padded; tile += blockDim.x) {
         int pt, dt;
-        dv.divmod(tile, pt, dt);
+        if (!tm.decode(tile, pt, dt)) continue;
         float acc[4][PT];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -411,15 +432,38 @@ k_logpost_generic(EvalArgs a, GenLayout L, const float* __restrict__ w, long lon
                 for (int i = threadIdx.x; i < L.ws[nl] * dead; i += blockDim.x) Zl[(i / dead) * ts + count + i % dead] = 0.f;
                 __syncthreads();
             }
-            for (int l = nl; l >= 1; --l) {
-                const float* dZ = Act + (size_t)L.arow[l] * ts;
-                const float* Aprev = (l == 1) ? Act : Act + ((size_t)L.arow[l - 1] + L.ws[l - 1]) * ts;
-                const int used = gen_backward_weights(Gs + L.woff[l], Gs + L.boff[l], Aprev, dZ, L.s[l - 1], L.s[l], L.ws[l], tp, ts);
-                if (l > 1) {
-                    float* Zprev = Act + (size_t)L.arow[l - 1] * ts;
-                    gen_backward_input(Ws + L.woff[l], dZ, Zprev, Aprev, Zprev, L.s[l - 1], L.ws[l], L.ws[l - 1], tp, ts, L.act, used);
+            // Backward schedule.  The input-gradient chain dZ_l -> dZ_{l-1} is the only dependent part; a layer's weight-gradient
+            // list (needs dZ_l and A_{l-1}, both final once dZ_l is) can run in the same phase or any later one.  sched 1 (default):
+            // a chain phase takes along only the pending weight lists that fit the idle slots of its last round of threads and
+            // the rest run as one closing phase (credit shape, padded lists: [dA2 256] [dA1 256] [dW3 64 + dW2 256 + dW1 64]).
+            // sched 0 (OCBNN_GEN_SCHED=0): dW_l is handed out together with dA_{l-1}.  Measured on the credit shape 13.5 vs 14.3 ms.
+            {
+                const int T = (int)blockDim.x;
+                auto weights = [&](int l, int first) {
+                    const float* dZ = Act + (size_t)L.arow[l] * ts;
+                    const float* Aprev = (l == 1) ? Act : Act + ((size_t)L.arow[l - 1] + L.ws[l - 1]) * ts;
+                    gen_backward_weights(Gs + L.woff[l], Gs + L.boff[l], Aprev, dZ, L.s[l - 1], L.s[l], L.ws[l], tp, ts, first);
+                };
+                int hi = nl;                                          // weight lists of layers l..hi are pending in phase l
+                for (int l = nl; l >= 1; --l) {                       // l == 1: the closing phase, weight lists only
+                    const int in_items = l >= 2 ? padded_items(tp >> 2, L.ws[l - 1] >> 2) : 0;
+                    int slots = (in_items + T - 1) / T * T - in_items, used = 0;
+                    while (hi >= l) {
+                        const int items = gen_backward_weights_items(L.s[hi - 1], L.ws[hi]);
+                        if (L.sched && l >= 2 && items > slots) break;
+                        weights(hi, used);
+                        used += items;
+                        slots -= items;
+                        --hi;
+                    }
+                    if (l >= 2) {
+                        const float* dZ = Act + (size_t)L.arow[l] * ts;
+                        const float* Aprev = Act + ((size_t)L.arow[l - 1] + L.ws[l - 1]) * ts;
+                        float* Zprev = Act + (size_t)L.arow[l - 1] * ts;
+                        gen_backward_input(Ws + L.woff[l], dZ, Zprev, Aprev, Zprev, L.s[l - 1], L.ws[l], L.ws[l - 1], tp, ts, L.act, used);
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
         }
         // Gaussian prior, value reduction, compact gradient write-out
@@ -537,10 +581,11 @@ int launch_logpost_generic(const Problem& p, const EvalArgs& a, const float* w, 
     // hide latency with, and the 650-tile weight-gradient lists take 2 rounds instead of 3.  OCBNN_GEN_THREADS overrides.
     static const int force_nt = [] { const char* e = getenv("OCBNN_GEN_THREADS"); return e ? atoi(e) : 0; }();
     const int nt = force_nt ? force_nt : (per_sm == 1 ? 512 : 256);
-    if (nt >= 512 && per_sm >= 2) {                     // experiment knob (OCBNN_GEN_THREADS=512 with a tile that leaves >= 2 CTAs/SM)
-        auto k = k_logpost_generic<512, 2>;
+    static const int force_minb = [] { const char* e = getenv("OCBNN_GEN_MINB"); return e ? atoi(e) : 0; }();
+    if (nt < 512 && (force_minb ? force_minb <= 2 : per_sm <= 2)) {   // two resident CTAs: no need for the 64-register cap of <256, 4>
+        auto k = k_logpost_generic<256, 2>;
         OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        k<<<(unsigned)grid, 512, sm, st>>>(a, L, w, m, out_lp, out_grad);
+        k<<<(unsigned)grid, 256, sm, st>>>(a, L, w, m, out_lp, out_grad);
     } else if (nt >= 512) {
         auto k = k_logpost_generic<512, 1>;
         OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
