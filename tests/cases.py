@@ -106,6 +106,17 @@ CASES = {
                      overrides=dict(architecture=[8, 6], ocp_nsamples=25), constraints=[
         ("add_deterministic_constraint", dict(constrained_domain=(-0.3, 0.3), interval_func=if_f1a,
                                               prior_type="negative_exponential_cocp"))]),
+    # generic-net kernel, shapes that are not multiples of the 4 x 4 register tiles / 4 x 4 tile blocks: three hidden layers,
+    # a short list next to a long one, one wide hidden layer (several hand-out rounds)
+    "reg_odd3": dict(cls="Regressor", yaml="F1a", data="toy1", use_ocbnn=True,
+                     overrides=dict(architecture=[21, 13, 9], ocp_nsamples=40), constraints=[
+        ("add_deterministic_constraint", dict(constrained_domain=(-0.3, 0.3), interval_func=if_f1a,
+                                              prior_type="negative_exponential_cocp"))]),
+    "cls_odd2": dict(cls="Classifier", yaml="F2a", data="toy2", use_ocbnn=True,
+                     overrides=dict(architecture=[35, 18], ocp_nsamples=30), constraints=[
+        ("add_deterministic_constraint", dict(constrained_domain=(1.0, 3.0, -2.0, 0.0), forbidden_classes=[0, 2],
+                                              prior_type="positive_dirichlet_cocp"))]),
+    "bin_wide1": dict(cls="BinaryClassifier", yaml="F4", data="toy5", overrides=dict(architecture=[70])),
     "cls_vanilla": dict(cls="Classifier", yaml="cbakeoff", data="toy2"),
     "w3_cls_dir": dict(cls="Classifier", yaml="F2a", data="toy2", use_ocbnn=True, constraints=[
         ("add_deterministic_constraint", dict(constrained_domain=(1.0, 3.0, -2.0, 0.0), forbidden_classes=[0, 2],
