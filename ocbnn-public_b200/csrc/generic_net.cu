@@ -1,13 +1,14 @@
 // generic_net.cu — K1 for arbitrary MLPs (credit [10,50,50,2] D=3202, recid [9,100,100,1] D=11201, deep toys):
 // ONE CTA PER WEIGHT VECTOR.  The particle's weights and its gradient accumulator stay resident in shared
-// memory (padded row-major), points are streamed through in tiles of TP, and every layer is a small
-// register-tiled fp32 GEMM (4x4 outputs per thread, float4 shared-memory operands):
+// memory (padded row-major), points are streamed through in tiles of TP, and every layer is a small GEMM - on the
+// tensor cores (mma.sync m16n8k8 TF32, 3xTF32 split: nets that leave <= 2 CTAs per SM, i.e. the application nets) or
+// register-tiled fp32 SIMT (4x4 outputs per thread, float4 shared-memory operands: small nets, OCBNN_GEN_MMA=0):
 //     forward   Z_l[o][p]  = sum_d W_l[d][o] A_{l-1}[d][p] + b_l[o]
 //     backward  dW_l[d][o] += sum_p A_{l-1}[d][p] dZ_l[o][p] ;  dA_{l-1}[d][p] = sum_o W_l[d][o] dZ_l[o][p]
 // Activations are stored feature-major ([feature][point], row stride TP+4) so that the 4 points of a register
 // tile are one LDS.128 and consecutive feature rows fall in distinct banks.
-// Replaces forward (bnn/base.py:89-104) + autograd for the application-sized nets; fp32 SIMT on purpose:
-// the parity bar is 1e-5 and tcgen05 has no fp32 MMA.
+// Replaces forward (bnn/base.py:89-104) + autograd for the application-sized nets.  Parity bar 1e-5: the tensor variant
+// keeps it with the 3xTF32 split (~2^-21 per product), everything outside the GEMMs is fp32 / fp64 as in the SIMT variant.
 #include <cstdlib>
 #include "heads.cuh"
 #include "small_net.cuh"
@@ -257,18 +258,8 @@ __device__ __forceinline__ void gen_backward_weights_tiles(float* __restrict__ g
         }
     }
 }
-// number of items of a layer's weight-gradient list (so that the caller can continue the hand-out with the next list)
-__device__ __forceinline__ int gen_backward_weights_items(int s_in, int ws) {
-    const int T = (int)blockDim.x, ND = (s_in + 3) >> 2;
-    return (!kSmallTiles || ND * (ws >> 2) * 5 >= T * 4) ? padded_items((ws + 3) / 4, ND) : padded_items((ws + 1) / 2, ND);
-}
-__device__ __forceinline__ void gen_backward_weights(float* __restrict__ gW, float* __restrict__ gb, const float* __restrict__ Ain,
-                                                     const float* __restrict__ dZ, int s_in, int s_out, int ws, int tp, int ts, int first) {
-    const int T = (int)blockDim.x, ND = (s_in + 3) >> 2;
-    first %= T;
-    if (!kSmallTiles || ND * (ws >> 2) * 5 >= T * 4) gen_backward_weights_tiles<4>(gW, Ain, dZ, s_in, s_out, ws, tp, ts, first);
-    else gen_backward_weights_tiles<2>(gW, Ain, dZ, s_in, s_out, ws, tp, ts, first);
-    // bias gradient: one thread per output, handed out from the top so that it lands on threads the tile list left idle
+// bias gradient: one thread per output, handed out from the top so that it lands on threads the tile list left idle
+__device__ __forceinline__ void gen_bias_grad(float* __restrict__ gb, const float* __restrict__ dZ, int s_out, int tp, int ts) {
     for (int o = (int)blockDim.x - 1 - (int)threadIdx.x; o < s_out; o += blockDim.x) {
         float s0 = 0.f, s1 = 0.f;
         const float* zr = dZ + o * ts;
@@ -280,7 +271,19 @@ __device__ __forceinline__ void gen_backward_weights(float* __restrict__ gW, flo
         gb[o] += s0 + s1;
     }
 }
-
+// number of items of a layer's weight-gradient list (so that the caller can continue the hand-out with the next list)
+__device__ __forceinline__ int gen_backward_weights_items(int s_in, int ws) {
+    const int T = (int)blockDim.x, ND = (s_in + 3) >> 2;
+    return (!kSmallTiles || ND * (ws >> 2) * 5 >= T * 4) ? padded_items((ws + 3) / 4, ND) : padded_items((ws + 1) / 2, ND);
+}
+__device__ __forceinline__ void gen_backward_weights(float* __restrict__ gW, float* __restrict__ gb, const float* __restrict__ Ain,
+                                                     const float* __restrict__ dZ, int s_in, int s_out, int ws, int tp, int ts, int first) {
+    const int T = (int)blockDim.x, ND = (s_in + 3) >> 2;
+    first %= T;
+    if (!kSmallTiles || ND * (ws >> 2) * 5 >= T * 4) gen_backward_weights_tiles<4>(gW, Ain, dZ, s_in, s_out, ws, tp, ts, first);
+    else gen_backward_weights_tiles<2>(gW, Ain, dZ, s_in, s_out, ws, tp, ts, first);
+    gen_bias_grad(gb, dZ, s_out, tp, ts);
+}
 // dZprev[d][p] = (sum_o W[d][o] dZ[o][p]) * act'(Zprev[d][p]).  4 rows d x PT points per thread.  Rows d >= s_in read the
 // (finite) shared memory that follows W_l and are written as zero.
 template <int PT>
@@ -342,6 +345,152 @@ __device__ __forceinline__ void gen_backward_input(const float* __restrict__ W, 
     else gen_backward_input_tiles<2>(W, dZ, Zprev, Aprev, dZprev, s_in, ws, wsp, tp, ts, act, first);
 }
 
+// ---- 3xTF32 tensor-core path (mma.sync.m16n8k8): the same three GEMMs per layer, a warp per 16 x 32 output tile ------------------
+// The 4 x 4 register tiles above are bound by shared-memory wavefronts (6 per 16 FFMA).  A warp-level m16n8k8 MMA takes its
+// fragments with 12 LDS.32 per 16 x 32 x 8 block (4096 MAC) - a quarter of the wavefronts - and each fp32 operand is split in
+// registers into tf32 hi + lo; hi*hi + hi*lo + lo*hi accumulated in fp32 keeps ~2^-21 per product (lo*lo dropped), inside the
+// 1e-5 parity bar.  No pad rows are needed; epilogues store valid elements only.
+// cvt.rna.tf32.f32 is an ~5-instruction software sequence on sm_100a (ncu: it made the ALU pipe the limiter at 67 %).  Rounding the
+// magnitude half-up on the bit pattern is 2 integer ops and as accurate (|x - hi| <= 2^-11 |x|); lo = x - hi is exact in fp32 and
+// goes to the MMA as it is - the tensor core ignores the low 13 mantissa bits of a tf32 operand - which leaves 2^-21 |x|.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+constexpr int kMmaNT = 4;                                   // n-tiles of 8 per warp item
+// c[j][0..3] = elements (m0+g, n0+8j+2t), (m0+g, +1), (m0+g+8, n0+8j+2t), (m0+g+8, +1) with g = lane / 4, t = lane % 4.
+// A(m, k) = A[m sAm + k sAk], B(k, n) = B[k sBk + n sBn].  Rows m >= M and columns n >= N are clamped to the last valid one (their
+// results are never stored), so the main loop has no predicates; only a K tail (K % 8) loads under a mask.
+__device__ __forceinline__ void warp_gemm_3xtf32(float (&c)[kMmaNT][4], int m0, int n0, int M, int N, int K, const float* __restrict__ A,
+                                                 int sAm, int sAk, const float* __restrict__ B, int sBk, int sBn) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const float* pa0 = A + min(m0 + g, M - 1) * sAm + t * sAk;
+    const float* pa1 = A + min(m0 + g + 8, M - 1) * sAm + t * sAk;
+    const float* pb[kMmaNT];
+#pragma unroll
+    for (int j = 0; j < kMmaNT; ++j) pb[j] = B + min(n0 + 8 * j + g, N - 1) * sBn + t * sBk;
+    const int a4 = 4 * sAk, b4 = 4 * sBk;
+    auto step = [&](float x0, float x1, float x2, float x3, const float (&y0)[kMmaNT], const float (&y1)[kMmaNT]) {
+        uint32_t ah[4], al[4];
+        split_tf32(x0, ah[0], al[0]);
+        split_tf32(x1, ah[1], al[1]);
+        split_tf32(x2, ah[2], al[2]);
+        split_tf32(x3, ah[3], al[3]);
+#pragma unroll
+        for (int j = 0; j < kMmaNT; ++j) {
+            uint32_t bh[2], bl[2];
+            split_tf32(y0[j], bh[0], bl[0]);
+            split_tf32(y1[j], bh[1], bl[1]);
+            mma_tf32(c[j], al, bh);
+            mma_tf32(c[j], ah, bl);
+            mma_tf32(c[j], ah, bh);
+        }
+    };
+    int k0 = 0;
+#pragma unroll 2
+    for (; k0 + 8 <= K; k0 += 8) {
+        float y0[kMmaNT], y1[kMmaNT];
+#pragma unroll
+        for (int j = 0; j < kMmaNT; ++j) { y0[j] = pb[j][0]; y1[j] = pb[j][b4]; pb[j] += 2 * b4; }
+        step(pa0[0], pa1[0], pa0[a4], pa1[a4], y0, y1);
+        pa0 += 2 * a4;
+        pa1 += 2 * a4;
+    }
+    if (k0 < K) {
+        const bool v0 = k0 + t < K, v1 = k0 + t + 4 < K;
+        float y0[kMmaNT], y1[kMmaNT];
+#pragma unroll
+        for (int j = 0; j < kMmaNT; ++j) { y0[j] = v0 ? pb[j][0] : 0.f; y1[j] = v1 ? pb[j][b4] : 0.f; }
+        step(v0 ? pa0[0] : 0.f, v0 ? pa1[0] : 0.f, v1 ? pa0[a4] : 0.f, v1 ? pa1[a4] : 0.f, y0, y1);
+    }
+}
+__device__ __forceinline__ int mma_items(int M, int N) { return ((M + 15) >> 4) * ((N + 8 * kMmaNT - 1) / (8 * kMmaNT)); }
+// warp hand-out: warp w takes items (w - first) mod nw, + nw, ...
+#define OCBNN_MMA_ITEMS(M, N)                                                                                         \
+    const int nw_ = (int)blockDim.x >> 5, mt_ = ((M) + 15) >> 4, items_ = mma_items(M, N);                           \
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;                                                   \
+    int w0_ = ((int)threadIdx.x >> 5) - (first % nw_);                                                                \
+    if (w0_ < 0) w0_ += nw_;                                                                                          \
+    for (int item = w0_; item < items_; item += nw_)
+#define OCBNN_MMA_TILE const int ni_ = item / mt_, m0 = 16 * (item - ni_ * mt_), n0 = 8 * kMmaNT * ni_
+
+__device__ __forceinline__ void gen_forward_mma(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ Ain,
+                                                float* __restrict__ Z, float* __restrict__ Aout, int s_in, int s_out, int ws, int tp,
+                                                int ts, int act, bool last) {
+    const int first = 0;
+    OCBNN_MMA_ITEMS(s_out, tp) {
+        OCBNN_MMA_TILE;
+        const int r0 = m0 + g, r1 = r0 + 8;
+        const float b0 = r0 < s_out ? b[r0] : 0.f, b1 = r1 < s_out ? b[r1] : 0.f;
+        float c[kMmaNT][4];
+#pragma unroll
+        for (int j = 0; j < kMmaNT; ++j) { c[j][0] = c[j][1] = b0; c[j][2] = c[j][3] = b1; }
+        warp_gemm_3xtf32(c, m0, n0, s_out, tp, s_in, W, 1, ws, Ain, ts, 1);
+#pragma unroll
+        for (int j = 0; j < kMmaNT; ++j) {
+            const int n = n0 + 8 * j + 2 * t;
+            if (n >= tp) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = h ? r1 : r0;
+                if (r >= s_out) continue;
+                const float z0 = c[j][2 * h], z1 = c[j][2 * h + 1];
+                *reinterpret_cast<float2*>(Z + r * ts + n) = make_float2(z0, z1);
+                if (!last) *reinterpret_cast<float2*>(Aout + r * ts + n) = make_float2(act_rt(act, z0), act_rt(act, z1));
+            }
+        }
+    }
+}
+// gW[d][o] += sum_p A[d][p] dZ[o][p] : M = d, N = o, K = points
+__device__ __forceinline__ void gen_backward_weights_mma(float* __restrict__ gW, float* __restrict__ gb, const float* __restrict__ Ain,
+                                                         const float* __restrict__ dZ, int s_in, int s_out, int ws, int tp, int ts, int first) {
+    OCBNN_MMA_ITEMS(s_in, s_out) {
+        OCBNN_MMA_TILE;
+        float c[kMmaNT][4];
+#pragma unroll
+        for (int j = 0; j < kMmaNT; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+        warp_gemm_3xtf32(c, m0, n0, s_in, s_out, tp, Ain, ts, 1, dZ, 1, ts);
+#pragma unroll
+        for (int j = 0; j < kMmaNT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int r = m0 + g + 8 * (e >> 1), n = n0 + 8 * j + 2 * t + (e & 1);
+                if (r < s_in && n < s_out) gW[r * ws + n] += c[j][e];
+            }
+    }
+    gen_bias_grad(gb, dZ, s_out, tp, ts);
+}
+// dZprev[d][p] = (sum_o W[d][o] dZ[o][p]) * act'(Zprev[d][p]) : M = d, N = points, K = o
+__device__ __forceinline__ void gen_backward_input_mma(const float* __restrict__ W, const float* __restrict__ dZ, const float* Zprev,
+                                                       const float* __restrict__ Aprev, float* dZprev, int s_in, int s_out, int ws,
+                                                       int tp, int ts, int act, int first) {
+    OCBNN_MMA_ITEMS(s_in, tp) {
+        OCBNN_MMA_TILE;
+        float c[kMmaNT][4];
+#pragma unroll
+        for (int j = 0; j < kMmaNT; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+        warp_gemm_3xtf32(c, m0, n0, s_in, tp, s_out, W, ws, 1, dZ, ts, 1);
+#pragma unroll
+        for (int j = 0; j < kMmaNT; ++j) {
+            const int n = n0 + 8 * j + 2 * t;
+            if (n >= tp) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = m0 + g + 8 * h;
+                if (r >= s_in) continue;
+                const int off = r * ts + n;
+                const float2 zp = *reinterpret_cast<const float2*>(Zprev + off), ap = *reinterpret_cast<const float2*>(Aprev + off);
+                *reinterpret_cast<float2*>(dZprev + off) = make_float2(c[j][2 * h] * dact_rt(act, zp.x, ap.x), c[j][2 * h + 1] * dact_rt(act, zp.y, ap.y));
+            }
+        }
+    }
+}
+
 template <int SK>
 __device__ __forceinline__ float head_at_point(int kind, const float* Zlast, int ts, int p, const float* prm, const HeadConsts& hc, float wgt,
                                                float* dZ) {
@@ -370,7 +519,7 @@ __device__ __forceinline__ float head_dispatch(int sk, int kind, const float* Zl
     }
 }
 
-template <int NT, int MINB>
+template <int NT, int MINB, bool MMA>
 __global__ void __launch_bounds__(NT, MINB)
 k_logpost_generic(EvalArgs a, GenLayout L, const float* __restrict__ w, long long m, float* __restrict__ out_lp, float* __restrict__ out_grad) {
     extern __shared__ __align__(16) float smem[];
@@ -414,7 +563,8 @@ k_logpost_generic(EvalArgs a, GenLayout L, const float* __restrict__ w, long lon
             for (int l = 1; l <= nl; ++l) {
                 float* Z = Act + (size_t)L.arow[l] * ts;
                 float* Aout = Z + (size_t)L.ws[l] * ts;
-                gen_forward_layer(Ws + L.woff[l], Ws + L.boff[l], Ain, Z, Aout, L.s[l - 1], L.ws[l], tp, ts, L.act, l == nl);
+                if (MMA && L.ws[l] > 8) gen_forward_mma(Ws + L.woff[l], Ws + L.boff[l], Ain, Z, Aout, L.s[l - 1], L.s[l], L.ws[l], tp, ts, L.act, l == nl);
+                else gen_forward_layer(Ws + L.woff[l], Ws + L.boff[l], Ain, Z, Aout, L.s[l - 1], L.ws[l], tp, ts, L.act, l == nl);
                 __syncthreads();
                 Ain = Aout;
             }
@@ -438,18 +588,19 @@ k_logpost_generic(EvalArgs a, GenLayout L, const float* __restrict__ w, long lon
             // the rest run as one closing phase (credit shape, padded lists: [dA2 256] [dA1 256] [dW3 64 + dW2 256 + dW1 64]).
             // sched 0 (OCBNN_GEN_SCHED=0): dW_l is handed out together with dA_{l-1}.  Measured on the credit shape 13.5 vs 14.3 ms.
             {
-                const int T = (int)blockDim.x;
+                const int T = MMA ? (int)blockDim.x >> 5 : (int)blockDim.x;      // hand-out unit: warps on the tensor path, threads otherwise
                 auto weights = [&](int l, int first) {
                     const float* dZ = Act + (size_t)L.arow[l] * ts;
                     const float* Aprev = (l == 1) ? Act : Act + ((size_t)L.arow[l - 1] + L.ws[l - 1]) * ts;
-                    gen_backward_weights(Gs + L.woff[l], Gs + L.boff[l], Aprev, dZ, L.s[l - 1], L.s[l], L.ws[l], tp, ts, first);
+                    if (MMA) gen_backward_weights_mma(Gs + L.woff[l], Gs + L.boff[l], Aprev, dZ, L.s[l - 1], L.s[l], L.ws[l], tp, ts, first);
+                    else gen_backward_weights(Gs + L.woff[l], Gs + L.boff[l], Aprev, dZ, L.s[l - 1], L.s[l], L.ws[l], tp, ts, first);
                 };
                 int hi = nl;                                          // weight lists of layers l..hi are pending in phase l
                 for (int l = nl; l >= 1; --l) {                       // l == 1: the closing phase, weight lists only
-                    const int in_items = l >= 2 ? padded_items(tp >> 2, L.ws[l - 1] >> 2) : 0;
+                    const int in_items = l < 2 ? 0 : MMA ? mma_items(L.s[l - 1], tp) : padded_items(tp >> 2, L.ws[l - 1] >> 2);
                     int slots = (in_items + T - 1) / T * T - in_items, used = 0;
                     while (hi >= l) {
-                        const int items = gen_backward_weights_items(L.s[hi - 1], L.ws[hi]);
+                        const int items = MMA ? mma_items(L.s[hi - 1], L.s[hi]) : gen_backward_weights_items(L.s[hi - 1], L.ws[hi]);
                         if (L.sched && l >= 2 && items > slots) break;
                         weights(hi, used);
                         used += items;
@@ -460,7 +611,8 @@ k_logpost_generic(EvalArgs a, GenLayout L, const float* __restrict__ w, long lon
                         const float* dZ = Act + (size_t)L.arow[l] * ts;
                         const float* Aprev = Act + ((size_t)L.arow[l - 1] + L.ws[l - 1]) * ts;
                         float* Zprev = Act + (size_t)L.arow[l - 1] * ts;
-                        gen_backward_input(Ws + L.woff[l], dZ, Zprev, Aprev, Zprev, L.s[l - 1], L.ws[l], L.ws[l - 1], tp, ts, L.act, used);
+                        if (MMA) gen_backward_input_mma(Ws + L.woff[l], dZ, Zprev, Aprev, Zprev, L.s[l - 1], L.s[l], L.ws[l], tp, ts, L.act, used);
+                        else gen_backward_input(Ws + L.woff[l], dZ, Zprev, Aprev, Zprev, L.s[l - 1], L.ws[l], L.ws[l - 1], tp, ts, L.act, used);
                     }
                     __syncthreads();
                 }
@@ -581,17 +733,18 @@ int launch_logpost_generic(const Problem& p, const EvalArgs& a, const float* w, 
     // hide latency with, and the 650-tile weight-gradient lists take 2 rounds instead of 3.  OCBNN_GEN_THREADS overrides.
     static const int force_nt = [] { const char* e = getenv("OCBNN_GEN_THREADS"); return e ? atoi(e) : 0; }();
     const int nt = force_nt ? force_nt : (per_sm == 1 ? 512 : 256);
+    static const bool use_mma = [] { const char* e = getenv("OCBNN_GEN_MMA"); return e ? atoi(e) != 0 : true; }();
     static const int force_minb = [] { const char* e = getenv("OCBNN_GEN_MINB"); return e ? atoi(e) : 0; }();
     if (nt < 512 && (force_minb ? force_minb <= 2 : per_sm <= 2)) {   // two resident CTAs: no need for the 64-register cap of <256, 4>
-        auto k = k_logpost_generic<256, 2>;
+        auto k = use_mma ? k_logpost_generic<256, 2, true> : k_logpost_generic<256, 2, false>;
         OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         k<<<(unsigned)grid, 256, sm, st>>>(a, L, w, m, out_lp, out_grad);
     } else if (nt >= 512) {
-        auto k = k_logpost_generic<512, 1>;
+        auto k = use_mma ? k_logpost_generic<512, 1, true> : k_logpost_generic<512, 1, false>;
         OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         k<<<(unsigned)grid, 512, sm, st>>>(a, L, w, m, out_lp, out_grad);
     } else {
-        auto k = k_logpost_generic<256, 4>;
+        auto k = k_logpost_generic<256, 4, false>;
         OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         k<<<(unsigned)grid, 256, sm, st>>>(a, L, w, m, out_lp, out_grad);
     }

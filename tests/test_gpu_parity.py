@@ -428,3 +428,24 @@ def test_full_size_properties_hmc_262144_chains_and_svgd_4096_particles():
     assert abs(out[0][0] - out[1][0]) <= 2e-6 * out[0][0]
     rel = (out[0][1][pm] - out[1][1]).norm(dim=1) / out[0][1][pm].norm(dim=1)
     assert float(rel.max()) < 1e-5, float(rel.max())
+
+
+@pytest.mark.parametrize("env, select", [
+    # small generic nets run the SIMT variant by default: force the 3xTF32 tensor variant on them
+    (dict(OCBNN_GEN_MMA="1", OCBNN_GEN_MINB="2"), "test_k1_logpost_and_grad and (odd or wide1 or deep)"),
+    # credit / recid run the tensor variant by default: force the SIMT register-tile variant, both backward schedules
+    (dict(OCBNN_GEN_MMA="0", OCBNN_GEN_SCHED="1"), "test_k1_logpost_and_grad and (credit or recid)"),
+    (dict(OCBNN_GEN_MMA="0", OCBNN_GEN_SCHED="0", OCBNN_GEN_TP="16"), "test_k1_logpost_and_grad and (credit or odd)"),
+], ids=["tensor_path_forced", "simt_path_forced", "simt_16_point_tiles"])
+def test_generic_net_kernel_variants(env, select):
+    """The generic-net K1 picks its variant (tile size, threads, SIMT / tensor path) from the net's shared-memory footprint; the
+    variant knobs are read once per process, so each combination runs the K1 parity test in a child process."""
+    import os
+    import subprocess
+    import sys
+    e = dict(os.environ, **env)
+    select += " and not kernel_variants"                     # never this test itself (-k also matches parameter ids)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k", select,
+                        "-p", "no:cacheprovider"], env=e, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "no tests ran" not in r.stdout, r.stdout[-500:]
