@@ -296,7 +296,7 @@ def main():
         m.update_config(lanes=args.lanes, hmc_l=L)
         os.chdir(scratch)
         m.hmc_run(qd, min(K, 3), True, collect_every=1, chunk=1, samples_host=samples_h[:min(K, 3)])   # warm the streams / allocator / pinned pages (untimed)
-        best = None
+        best, reps_ms = None, []
         for rep in range(2):                      # the K-step run is repeated once and the faster repetition reported: a one-off host
             pos[0] = 0                            # stall on a rank (seen twice at N = 2: +170 ms in a 37 ms region) is not the path's speed
             barrier()
@@ -309,11 +309,28 @@ def main():
             ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
             if world > 1:
                 torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
+            reps_ms.append(round(float(ms2.item()), 3))
             best = ms2 if best is None or float(ms2.item()) < float(best.item()) else best
         ms2 = best
         os.chdir(cwd)
+        # context for the number above: this box's pinned-memory copy bandwidth (64 MiB each way, untimed region)
+        pin = torch.empty(16 << 20, dtype=torch.float32).pin_memory()
+        dbuf = torch.empty_like(pin, device=dev)
+        link = {}
+        for name, (src_, dst_) in (("h2d", (pin, dbuf)), ("d2h", (dbuf, pin))):
+            dst_.copy_(src_, non_blocking=True)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(4):
+                dst_.copy_(src_, non_blocking=True)
+            c1.record()
+            torch.cuda.synchronize()
+            link[name] = round(4 * pin.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9, 1)
+        del pin, dbuf
         e2e = {"value": world * M * L * K / (float(ms2.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(M * D * 4 + M * 8), "d2h_bytes_per_step": int(M * D * 4 + M * 8 // K),
+               "reps_ms": reps_ms, "pinned_copy_gbs": link,
                "path": "HMCMixin.hmc_run(collect_every=1, chunk=1, samples_host=pinned): momenta+uniforms H2D per step on a side stream, that step's samples D2H on a copy stream, accept counts D2H at the end; faster of two repetitions of the K-step run (max over ranks each)"}
 
     # ---- second headline metric of BASELINE.json: SVGD particle-iters/s (W4 = repro/F3b.yaml, 4096 particles per GPU) --------
