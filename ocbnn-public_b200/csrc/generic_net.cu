@@ -704,8 +704,9 @@ static int pick_tp(const Problem& p, GenLayout& L, bool with_grad) {
         const size_t need = need_for(force);
         return (long long)need <= cap ? (int)need : -1;
     }
-    // measured on W6 (credit, in-place dZ): 64-point tiles at 2 CTAs/SM 15.1 ms, 32-point tiles at 3 CTAs/SM 15.7 ms, 24- and 16-point
-    // tiles at 4 CTAs/SM 16.1 / 19.7 ms -> 64-point tiles as long as two CTAs fit, then 32, then 16
+    // measured on W6 (credit, in-place dZ, SIMT variant): 64-point tiles at 2 CTAs/SM 15.1 ms, 32-point tiles at 3 CTAs/SM 15.7 ms, 24- and
+    // 16-point tiles at 4 CTAs/SM 16.1 / 19.7 ms -> 64-point tiles as long as two CTAs fit, then 32, then 16 (the tensor variant wants
+    // the 64-point tile too: its warp items are 16 x 32 outputs)
     for (int tp : {64, 32, 16}) {
         const size_t need = need_for(tp);
         if ((long long)need <= cap && cap / (long long)(need + 1024) >= 2) return (int)need;
