@@ -354,7 +354,11 @@ __device__ __forceinline__ void gen_backward_input(const float* __restrict__ W, 
 // magnitude half-up on the bit pattern is 2 integer ops and as accurate (|x - hi| <= 2^-11 |x|); lo = x - hi is exact in fp32 and
 // goes to the MMA as it is - the tensor core ignores the low 13 mantissa bits of a tf32 operand - which leaves 2^-21 |x|.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+#ifdef OCBNN_GEN_SPLIT_TRUNC                                 // experiment: truncate instead of rounding (one integer op less per element)
+    hi = __float_as_uint(x) & 0xffffe000u;
+#else
     hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+#endif
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
