@@ -1,7 +1,7 @@
 """Relative error of the generic-net K1 (value, gradient) against the float64 oracle on the credit / recid parity cases."""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # test infrastructure: the only place besides tests that may import oracle/
 for p in (ROOT, os.path.join(ROOT, "ocbnn-public_b200"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
     sys.path.insert(0, p)
 import tempfile
