@@ -303,6 +303,13 @@ struct SmallLaunch {
             OCBNN_HMC_GO(4, 2);
 #undef OCBNN_HMC_GO
         }
+        if constexpr (G > 1 && G <= 8 && N::NS <= 18) {
+            // few chains, 2-8 lanes per chain: four points in flight per lane at 3 CTAs/SM, as on the one-lane path (4096 chains x 8 lanes on
+            // W2: 0.915 vs 0.872 G steps/s; at 16 lanes the segments are too short: 0.62 vs 0.74, so G >= 16 keeps two).  OCBNN_HMC_GU=2 | 4 forces.
+            static const int gu = [] { const char* e = getenv("OCBNN_HMC_GU"); return e ? atoi(e) : 0; }();
+            if (gu == 4 || (gu == 0 && a.n_cpoints >= 64))
+                return hmc_mb<G, 3, 4>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
+        }
         return hmc_mb<G, (N::NS > 24 ? 2 : N::NS > 18 ? 3 : 4), 2>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
     }
     template <int G>
