@@ -288,7 +288,7 @@ def main():
         qd = q.clone()
         pos = [0]
 
-        def draw_from_host(n, m_, device):
+        def draw_from_host(n, m_, device, lo=0, hi=None):
             i = pos[0]
             pos[0] += n
             return p0h[i:i + n].to(device, non_blocking=True), uh[i:i + n].to(device, non_blocking=True)

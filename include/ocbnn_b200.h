@@ -38,7 +38,7 @@ extern "C" {
 #define OCBNN_API
 #endif
 
-#define OCBNN_ABI_VERSION 1
+#define OCBNN_ABI_VERSION 2
 #define OCBNN_MAX_LAYERS 8
 
 /* error codes */
@@ -145,54 +145,62 @@ OCBNN_API int ocbnn_sgld_iterate(ocbnn_problem *p, float *w, const float *noise,
                        int32_t batch_stride, int64_t m, int32_t t_steps, int32_t with_data, float *out_samples,
                        int32_t thin, int32_t lanes, void *stream);
 
+/* Communicator for the two samplers with an exchange step (SVGD, BBB): one per process (= per GPU), NCCL underneath (the library
+ * binds libnccl.so.2 at run time - the copy already loaded in the process if there is one).  Rank 0 obtains an id, the host
+ * program hands it to the other ranks by whatever means it has (torch.distributed / MPI / a file), every rank calls
+ * ocbnn_comm_create (collective).  ocbnn_comm_wrap adopts a communicator the caller already owns (nccl_comm = ncclComm_t).
+ * NULL stands for "one rank" wherever a communicator is taken. */
+typedef struct ocbnn_comm ocbnn_comm;
+#define OCBNN_COMM_ID_BYTES 128
+OCBNN_API int ocbnn_comm_unique_id(uint8_t id[OCBNN_COMM_ID_BYTES]);
+OCBNN_API int ocbnn_comm_create(const uint8_t id[OCBNN_COMM_ID_BYTES], int32_t rank, int32_t world, ocbnn_comm **out);
+OCBNN_API int ocbnn_comm_wrap(void *nccl_comm, int32_t rank, int32_t world, ocbnn_comm **out);
+OCBNN_API int ocbnn_comm_destroy(ocbnn_comm *comm);
+/* rows [*row_begin, *row_begin + *n_rows) of n units that rank `rank` of `world` owns: contiguous shares, the first n % world
+ * ranks hold one more.  The layout every sharded entry point below assumes. */
+OCBNN_API int ocbnn_comm_shard(int64_t n, int32_t rank, int32_t world, int64_t *row_begin, int64_t *n_rows);
+
 /* K3 — SVGD (inference.py:208-292).  Two implementations behind one interface, selected by use_tensor:
  *   0  exact fp32 SIMT kernels (distances recomputed from x on every pass);
- *   1  tcgen05 path: x is centred and split into tf32 hi/lo parts, squared distances of this rank's rows are formed once
- *      (exact differences for D <= 64, 3xTF32 Gram GEMM on the tensor cores above that) and kept in the workspace, the
- *      kernel matrix K = exp(-d2/h) and O = K [G | Xc] run as a TMA-fed tcgen05 GEMM in 3xTF32 precision;
+ *   1  tcgen05 path: x is centred and split into tf32 hi/lo parts.  D <= 64: neither the distances nor the kernel matrix are
+ *      ever written to memory - the median select classifies 128 x 128 Gram tiles recomputed on the tensor cores (pairs near
+ *      the bracket are re-evaluated with exact differences) and phi is a flash-attention shaped kernel, S = Xc Xc^T -> TMEM ->
+ *      K = exp(..) -> TMEM -> O += K [G | Xc].  D > 64: distances of this rank's rows by a 3xTF32 Gram GEMM, K materialised as
+ *      tf32 hi/lo, O by a TMA-fed tcgen05 GEMM;
  *  -1  choose (tensor path from 1024 particles up).
- * workspace >= ocbnn_svgd_workspace_bytes(n, d, n_rows, use_tensor) device bytes, 256-byte aligned; it starts with the
- * select histogram (3 x 2048 u32) and the select state (4 x u64), which a multi-GPU caller all-reduces between passes.
+ * workspace >= ocbnn_svgd_workspace_bytes(n, d, n_rows, use_tensor) device bytes, 256-byte aligned.
  *
- * K3a — bandwidth h = med^2 / ln n: exact LOWER median of ||x_i - x_j + 1e-6|| over i<j, zeros dropped, by a 3-pass radix
- * select (11+11+10 bits of the fp32 pattern).  out_h: device scalar.  A SIMT pass histograms rows i = row_start + t*row_step,
- * t < n_rows, against all j > i; a "prepared" pass reads the distances ocbnn_svgd_prepare left in the workspace for rows
- * [row_begin, row_begin + n_rows). */
+ * ocbnn_svgd_step — ONE SVGD iteration (SVGDMixin.single + the Adagrad step of SVGDMixin.infer, inference.py:225-259,272-283)
+ * for particles sharded over the ranks of `comm`, everything enqueued on `stream` (and on an internal side stream forked from /
+ * joined to it by events), no host synchronisation, capturable in a CUDA graph:
+ *   gradients of this rank's rows (K1)  ->  all-gather G  ->  exact median bandwidth over ALL pairs (K3a; counters and radix
+ *   histograms all-reduced)  ->  phi of this rank's rows (K3b)  ->  Adagrad on this rank's rows (K3c)  ->  all-gather X.
+ * x_all (n x D, in/out): ALL particles, identical on every rank at entry and at exit; this rank owns the rows ocbnn_comm_shard
+ * gives it (row_begin / n_rows are passed for checking).  g_all (n x D, out): gradients of all particles.  acc, phi
+ * (n_rows x D): Adagrad accumulator (in/out) and update direction (out) of the owned rows.  h: device scalar (out).
+ * batch_offset / batch_stride / with_data as in ocbnn_logpost_grad. */
 OCBNN_API int64_t ocbnn_svgd_workspace_bytes(int64_t n, int64_t d, int64_t n_rows, int32_t use_tensor);
-OCBNN_API int ocbnn_svgd_prepare(const float *x, int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t use_tensor,
-                                 void *workspace, int64_t workspace_bytes, void *stream);
-OCBNN_API int ocbnn_svgd_hist_pass(const float *x, int64_t n, int64_t d, int64_t row_start, int64_t row_step, int64_t n_rows,
-                                   int32_t pass, uint32_t *hist, uint64_t *select_state, void *stream);
-OCBNN_API int ocbnn_svgd_hist_pass_prepared(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t pass, uint32_t *hist,
-                                            uint64_t *select_state, void *workspace, void *stream);
-OCBNN_API int ocbnn_svgd_select_update(int32_t pass, uint32_t *hist, uint64_t *select_state, int64_t n, float *out_h, void *stream);
-/* single-GPU convenience: prepare (tensor path) + the select.  With all rows on one GPU the tensor path finds the same exact
- * median in three launches (sampled bracket, one counting/compaction pass over the distances, one-CTA select among the ~2.5 %
- * candidates; in-kernel fallback to the radix select if the bracket misses).  On return the first 4 x u64 of the select state
- * hold (bracket hit, candidates, values below the bracket, exact zeros). */
+OCBNN_API int ocbnn_svgd_step(ocbnn_problem *p, float *x_all, float *g_all, float *acc, float *phi, float *h, int64_t n,
+                              int64_t row_begin, int64_t n_rows, float lr, int32_t batch_offset, int32_t batch_stride,
+                              int32_t with_data, int32_t use_tensor, void *workspace, int64_t workspace_bytes, ocbnn_comm *comm,
+                              void *stream);
+
+/* Building blocks of the step on one GPU (tests, profiling).
+ * K3a — bandwidth h = med^2 / ln n: exact LOWER median of ||x_i - x_j + 1e-6|| over i<j, zeros dropped (inference.py:208-217).
+ * SIMT arm: 3-pass radix select (11+11+10 bits of the fp32 pattern).  Tensor path: sampled bracket, one counting/compaction pass
+ * over the pairs, select among the ~3 % candidates; in-kernel fallback to the radix select if the bracket misses.  On return
+ * the first 4 x u64 after the 3 x 2048 u32 at the start of the workspace hold (bracket hit, candidates, values below the
+ * bracket, exact zeros).  out_h: device scalar. */
 OCBNN_API int ocbnn_svgd_bandwidth(const float *x, int64_t n, int64_t d, float *out_h, int32_t use_tensor, void *workspace,
                                    int64_t workspace_bytes, void *stream);
-/* Bracket select across ranks (tensor path; every rank holds all particles and the distances of rows [row_begin, row_begin + n_rows),
- * left in `workspace` by ocbnn_svgd_prepare).  Stage 1 samples the bracket from X (identical on every rank), counts this rank's pairs
- * and returns the device reduce buffer (reduce_words u64: counters + linear histogram) which the caller all-reduces as int64 sums;
- * stage 2 gathers this rank's candidates of the hit bin; stage 3 is a 3-pass radix select over those short lists: _sel_hist fills
- * hist[pass] (2048 u32, all-reduced by the caller), _sel_update advances the select state and, after pass 2, writes h.  If the bracket
- * missed, stage 3 runs over the distance rows instead (same result).  Replaces inference.py:208-217 for sharded particles. */
-OCBNN_API int ocbnn_svgd_sel_count(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, void *workspace, uint64_t **reduce_buf,
-                                   int64_t *reduce_words, void *stream);
-OCBNN_API int ocbnn_svgd_sel_gather(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, void *workspace, void *stream);
-OCBNN_API int ocbnn_svgd_sel_hist(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t pass, uint32_t *hist, uint64_t *select_state,
-                                  void *workspace, void *stream);
-OCBNN_API int ocbnn_svgd_sel_update(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t pass, const uint32_t *hist,
-                                    uint64_t *select_state, void *workspace, float *out_h, void *stream);
-/* median-select algorithm of ocbnn_svgd_bandwidth's tensor path: 1 bracket select (default), 0 the 3-pass radix select,
- * 2 bracket select with a sabotaged bracket (exercises the fallback; tests).  mode < 0 queries.  Returns the previous mode. */
+/* median-select algorithm of the tensor path: 1 bracket select (default), 0 the plain radix select, 2 bracket select with a
+ * sabotaged bracket (exercises the fallback; tests).  mode < 0 queries.  Returns the previous mode. */
 OCBNN_API int ocbnn_svgd_select_mode(int32_t mode);
 
 /* K3b — SVGD update direction phi_i = (1/n) sum_j [K_ji g_j + grad_{x_j} K_ji] (inference.py:219-259) for rows
- * [row_begin, row_begin + n_rows) of the (gathered) particle matrix x (n x D) with gradients g (n x D).
- * use_tensor = 2: tensor path, and the workspace was already prepared for this x and these rows (by ocbnn_svgd_prepare
- * or ocbnn_svgd_bandwidth); 1 prepares it itself. */
+ * [row_begin, row_begin + n_rows) of the particle matrix x (n x D) with gradients g (n x D).
+ * use_tensor = 2: tensor path, and the workspace was already prepared for this x and these rows by ocbnn_svgd_bandwidth;
+ * 1 prepares it itself. */
 OCBNN_API int ocbnn_svgd_phi(const float *x, const float *g, int64_t n, int64_t d, int64_t row_begin, int64_t n_rows,
                              const float *h, float *out_phi, int32_t use_tensor, void *workspace, int64_t workspace_bytes, void *stream);
 
@@ -215,6 +223,16 @@ OCBNN_API int ocbnn_bbb_sample(const float *q_params, const float *eps, int64_t 
  * colstat (device, D floats) is scratch.  Partial results of several ranks add up (all-reduce sum). */
 OCBNN_API int ocbnn_bbb_reduce(const float *q_params, const float *eps, const float *lp, const float *grad, int64_t k, int64_t d,
                      int64_t k_total, int32_t add_entropy, float *out_grad_q, float *out_elbo, float *colstat, void *stream);
+
+/* ocbnn_bbb_step — ONE Bayes-by-Backprop epoch (BBBMixin.compute_elbo + backward + the Adagrad step, inference.py:142-187) with
+ * the Monte-Carlo samples sharded over the ranks of `comm`: w_j = mu + eps_j softplus(rho) for this rank's k_local draws
+ * eps (k_local x D), K1 on them, the closed-form (D x 2) ELBO gradient, ONE all-reduce of gradient + ELBO, Adagrad on q_params
+ * (D x 2, in/out, identical on every rank) with accumulator acc (D x 2, in/out).  out_elbo: device scalar.
+ * workspace >= ocbnn_bbb_workspace_bytes(k_local, d) device bytes.  Enqueued on `stream`, no host synchronisation. */
+OCBNN_API int64_t ocbnn_bbb_workspace_bytes(int64_t k_local, int64_t d);
+OCBNN_API int ocbnn_bbb_step(ocbnn_problem *p, float *q_params, float *acc, const float *eps, int64_t k_local, int64_t k_total,
+                             float lr, int32_t batch_offset, int32_t batch_stride, int32_t with_data, float *out_elbo,
+                             void *workspace, int64_t workspace_bytes, ocbnn_comm *comm, void *stream);
 
 /* K6 — Gaussian AOCP objective and its gradient w.r.t. params (D x 2 = mean, rho; std = softplus(rho)).
  * Replaces gaussian_aocp_objective + autograd (base.py:390-419 regression, :624-672 binary) for C constraint points cx (C x s_0):

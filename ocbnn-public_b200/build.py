@@ -33,7 +33,7 @@ def _newer(src, dst, deps):
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
-    deps = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
+    deps = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
     jobs = []
     for s in srcs:
         o = os.path.join(OBJ, os.path.basename(s)[:-3] + ".o")

@@ -116,7 +116,7 @@ static unsigned ew_blocks(long long n) {
     return (unsigned)(b > 148 * 32 ? 148 * 32 : (b < 1 ? 1 : b));
 }
 
-static EvalArgs eval_args(const Problem& p, int offset, int stride, int with_data) {
+EvalArgs eval_args(const Problem& p, int offset, int stride, int with_data) {
     EvalArgs a = p.base;
     a.batch_offset = stride > 1 ? offset : 0;
     a.batch_stride = stride > 1 ? stride : 1;
@@ -124,7 +124,7 @@ static EvalArgs eval_args(const Problem& p, int offset, int stride, int with_dat
     return a;
 }
 
-static int logpost_any(const Problem& p, const EvalArgs& a, const float* w, long long m, float* lp, float* grad, int lanes, cudaStream_t st) {
+int logpost_any(const Problem& p, const EvalArgs& a, const float* w, long long m, float* lp, float* grad, int lanes, cudaStream_t st) {
     if (small_net_supported(p)) {
         int pts = (a.with_data ? batch_count(a.n_train, 0, a.batch_stride) : 0) + a.n_cpoints;
         if (lanes <= 0) lanes = choose_lanes(p, m, pts);
@@ -132,6 +132,8 @@ static int logpost_any(const Problem& p, const EvalArgs& a, const float* w, long
     }
     return launch_logpost_generic(p, a, w, m, lp, grad, st);
 }
+
+const Problem* problem_of(const ocbnn_problem* h) { return reinterpret_cast<const ProblemImpl*>(h); }
 
 }  // namespace ocbnn
 

@@ -104,4 +104,9 @@ int launch_forward_generic(const Problem& p, const float* w, long long m, const 
 
 int choose_lanes(const Problem& p, long long m, int points);
 
+// abi.cu: evaluation arguments of a (minibatch, with_data) pair and K1 on whichever kernel family serves the net
+EvalArgs eval_args(const Problem& p, int offset, int stride, int with_data);
+int logpost_any(const Problem& p, const EvalArgs& a, const float* w, long long m, float* lp, float* grad, int lanes, cudaStream_t st);
+const Problem* problem_of(const ocbnn_problem* h);
+
 }  // namespace ocbnn

@@ -329,17 +329,40 @@ k_adagrad(float* __restrict__ x, float* __restrict__ acc, const float* __restric
 
 using namespace ocbnn;
 
-extern "C" OCBNN_API int ocbnn_svgd_hist_pass(const float* x, int64_t n, int64_t d, int64_t row_start, int64_t row_step, int64_t n_rows, int32_t pass,
-                                    uint32_t* hist, uint64_t* select_state, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    OCBNN_REQUIRE(x && hist && select_state && n >= 2 && d >= 1 && pass >= 0 && pass < 3 && row_step >= 1, OCBNN_EINVAL,
-                  "ocbnn_svgd_hist_pass: bad argument");
+// tensor path (svgd_tc.cu), collectives (comm.cu)
+#include "svgd_tc.h"
+#include "comm.h"
+
+// use_tensor: 0 exact fp32 SIMT kernels ; 1 tcgen05 path ; -1 choose (tensor path from 1024 particles up)
+static bool want_tensor(int32_t use_tensor, int64_t n) { return use_tensor > 0 || (use_tensor < 0 && n >= 1024); }
+static const int64_t kHdrBytes = 3 * kBins * sizeof(uint32_t) + 256;     // select histogram + select state at the start of every workspace
+
+extern "C" OCBNN_API int64_t ocbnn_svgd_workspace_bytes(int64_t n, int64_t d, int64_t n_rows, int32_t use_tensor) {
+    int64_t b = kHdrBytes;
+    if (want_tensor(use_tensor, n)) return b + tc::tc_workspace_bytes(n, d, n_rows);
+    if (d > 64) b += (n_rows * n + n_rows) * (int64_t)sizeof(float);      // kernel matrix + row sums (exact wide path)
+    return b;
+}
+
+// 1 bracket select (default), 0 full radix select, 2 bracket select with a sabotaged bracket (takes the in-kernel fallback);
+// initial value from OCBNN_SVGD_SELECT = fast | legacy | fallback
+static std::atomic<int> g_select_mode{[] { const char* e = getenv("OCBNN_SVGD_SELECT"); return !e ? 1 : e[0] == 'l' ? 0 : (e[0] == 'f' && e[1] == 'a' && e[2] == 'l') ? 2 : 1; }()};
+namespace ocbnn { int svgd_select_mode_value() { return g_select_mode.load(); } }
+extern "C" OCBNN_API int ocbnn_svgd_select_mode(int32_t mode) {
+    const int prev = g_select_mode.load();
+    if (mode >= 0 && mode <= 2) g_select_mode.store(mode);
+    return prev;
+}
+
+namespace ocbnn {
+// SIMT arm: one radix-select histogram pass over rows row_start + t row_step (pairs i < j), and the rank bookkeeping after it
+int simt_hist_pass(const float* x, long long n, long long d, long long row_start, long long row_step, long long n_rows, int pass, uint32_t* hist,
+                   const unsigned long long* state, cudaStream_t st) {
     if (pass == 0) {
         k_zero_u32<<<(3 * kBins + 255) / 256, 256, 0, st>>>(hist, 3 * kBins);
         OCBNN_LAUNCH_CHECK();
     }
     if (n_rows <= 0) return OCBNN_OK;
-    auto* state = reinterpret_cast<const unsigned long long*>(select_state);
     if (d <= 64) {
         unsigned blocks = (unsigned)((n_rows + kRowsPerCta - 1) / kRowsPerCta);
         if (d <= 32) k_dist_hist<8><<<blocks, kRowsPerCta * kLpr, 0, st>>>(x, n, (int)d, row_start, row_step, n_rows, pass, hist, state);
@@ -350,142 +373,76 @@ extern "C" OCBNN_API int ocbnn_svgd_hist_pass(const float* x, int64_t n, int64_t
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }
-
-extern "C" OCBNN_API int ocbnn_svgd_select_update(int32_t pass, uint32_t* hist, uint64_t* select_state, int64_t n, float* out_h, void* stream) {
-    OCBNN_REQUIRE(hist && select_state && pass >= 0 && pass < 3, OCBNN_EINVAL, "ocbnn_svgd_select_update: bad argument");
-    k_select_update<<<1, 256, 0, (cudaStream_t)stream>>>(pass, hist, reinterpret_cast<unsigned long long*>(select_state), n, out_h);
+int simt_select_update(int pass, uint32_t* hist, unsigned long long* state, long long n, float* out_h, cudaStream_t st) {
+    k_select_update<<<1, 256, 0, st>>>(pass, hist, state, n, out_h);
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }
-
-// tensor path (svgd_tc.cu)
-namespace ocbnn { namespace tc {
-long long tc_workspace_bytes(long long n, long long d, long long n_rows);
-int tc_svgd_prepare(const float* x, long long n, long long d, long long row_begin, long long n_rows, void* ws, long long ws_bytes, unsigned* hist0,
-                    bool* hist0_done, cudaStream_t st);
-int tc_svgd_hist(long long n, long long d, long long row_begin, long long n_rows, int pass, unsigned* hist, const unsigned long long* state, void* ws,
-                 cudaStream_t st);
-int tc_svgd_phi(const float* g, const float* h, long long n, long long d, long long row_begin, long long n_rows, float* phi, void* ws, cudaStream_t st);
-int tc_svgd_select_fast(long long n, long long d, void* ws, float* out_h, int mode, unsigned long long* dbg, cudaStream_t st);
-int tc_svgd_prepare_select(const float* x, long long n, long long d, void* ws, long long ws_bytes, float* out_h, int mode, unsigned long long* dbg,
-                           cudaStream_t st);
-int tc_svgd_sel_count(long long n, long long d, long long row_begin, long long n_rows, void* ws, unsigned long long** red64_out, int mode, cudaStream_t st);
-int tc_svgd_sel_gather(long long n, long long d, long long row_begin, long long n_rows, void* ws, cudaStream_t st);
-int tc_svgd_sel_hist(long long n, long long d, long long row_begin, long long n_rows, int pass, unsigned* hist, const unsigned long long* state, void* ws,
-                     cudaStream_t st);
-int tc_svgd_sel_update(long long n, long long d, long long row_begin, long long n_rows, int pass, const unsigned* hist, unsigned long long* state, void* ws,
-                       float* out_h, cudaStream_t st);
-} }
-
-// use_tensor: 0 exact fp32 SIMT kernels ; 1 tcgen05 path ; -1 choose (tensor path from 1024 particles up)
-static bool want_tensor(int32_t use_tensor, int64_t n) { return use_tensor > 0 || (use_tensor < 0 && n >= 1024); }
-
-extern "C" OCBNN_API int64_t ocbnn_svgd_workspace_bytes(int64_t n, int64_t d, int64_t n_rows, int32_t use_tensor) {
-    int64_t b = 3 * kBins * sizeof(uint32_t) + 256;                       // histogram + select state
-    if (want_tensor(use_tensor, n)) return b + tc::tc_workspace_bytes(n, d, n_rows);
-    if (d > 64) b += (n_rows * n + n_rows) * (int64_t)sizeof(float);      // kernel matrix + row sums (exact wide path)
-    return b;
-}
-
-extern "C" OCBNN_API int ocbnn_svgd_prepare(const float* x, int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t use_tensor,
-                                            void* workspace, int64_t workspace_bytes, void* stream) {
-    OCBNN_REQUIRE(x && n >= 2 && d >= 1 && row_begin >= 0 && row_begin + n_rows <= n, OCBNN_EINVAL, "ocbnn_svgd_prepare: bad argument");
-    if (!want_tensor(use_tensor, n) || n_rows == 0) return OCBNN_OK;
-    return tc::tc_svgd_prepare(x, n, d, row_begin, n_rows, workspace, workspace_bytes, nullptr, nullptr, (cudaStream_t)stream);
-}
-
-extern "C" OCBNN_API int ocbnn_svgd_hist_pass_prepared(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t pass, uint32_t* hist,
-                                                       uint64_t* select_state, void* workspace, void* stream) {
-    OCBNN_REQUIRE(hist && select_state && workspace && pass >= 0 && pass < 3, OCBNN_EINVAL, "ocbnn_svgd_hist_pass_prepared: bad argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    if (pass == 0) {
-        k_zero_u32<<<(3 * kBins + 255) / 256, 256, 0, st>>>(hist, 3 * kBins);
+// SIMT arm of phi for rows [row_begin, row_begin + n_rows); `wide` (D > 64): n_rows x n kernel matrix + n_rows row sums
+int simt_phi(const float* x, const float* g, long long n, long long d, long long row_begin, long long n_rows, const float* h, float* out_phi, float* wide,
+             cudaStream_t st) {
+    if (d <= 64) {
+        unsigned blocks = (unsigned)((n_rows + kRowsPerCta - 1) / kRowsPerCta);
+        if (d <= 32) k_svgd_phi_small<8><<<blocks, kRowsPerCta * kLpr, 0, st>>>(x, g, n, (int)d, row_begin, n_rows, h, out_phi);
+        else k_svgd_phi_small<16><<<blocks, kRowsPerCta * kLpr, 0, st>>>(x, g, n, (int)d, row_begin, n_rows, h, out_phi);
         OCBNN_LAUNCH_CHECK();
+        return OCBNN_OK;
     }
-    if (n_rows <= 0) return OCBNN_OK;
-    return tc::tc_svgd_hist(n, d, row_begin, n_rows, pass, hist, reinterpret_cast<const unsigned long long*>(select_state), workspace, st);
+    float* kmat = wide;
+    float* rowsum = kmat + n_rows * n;
+    k_kernel_matrix_wide<<<(unsigned)n_rows, 256, 0, st>>>(x, n, (int)d, row_begin, n_rows, h, kmat, rowsum);
+    OCBNN_LAUNCH_CHECK();
+    dim3 grid((unsigned)((d + 63) / 64), (unsigned)((n_rows + 63) / 64));
+    k_phi_gemm_wide<<<grid, 256, 0, st>>>(kmat, rowsum, x, g, n, (int)d, row_begin, n_rows, h, out_phi);
+    OCBNN_LAUNCH_CHECK();
+    return OCBNN_OK;
 }
+int adagrad_launch(float* x, float* acc, const float* dir, long long n_elem, float lr, float grad_sign, cudaStream_t st) {
+    if (n_elem == 0) return OCBNN_OK;
+    long long blocks = (n_elem + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_adagrad<<<(unsigned)blocks, 256, 0, st>>>(x, acc, dir, n_elem, lr, grad_sign);
+    OCBNN_LAUNCH_CHECK();
+    return OCBNN_OK;
+}
+}  // namespace ocbnn
 
-// 1 fast (default), 0 legacy, 2 fast with a sabotaged bracket; initial value from OCBNN_SVGD_SELECT = fast | legacy | fallback
-static std::atomic<int> g_select_mode{[] { const char* e = getenv("OCBNN_SVGD_SELECT"); return !e ? 1 : e[0] == 'l' ? 0 : (e[0] == 'f' && e[1] == 'a' && e[2] == 'l') ? 2 : 1; }()};
-// sets the median-select algorithm of ocbnn_svgd_bandwidth's single-rank tensor path (mode < 0: query only); returns the previous mode
-static int g_select_mode_value() { return g_select_mode.load(); }
-extern "C" OCBNN_API int ocbnn_svgd_select_mode(int32_t mode) {
-    const int prev = g_select_mode.load();
-    if (mode >= 0 && mode <= 2) g_select_mode.store(mode);
-    return prev;
-}
-
-// ---- bracket select across ranks (tensor path; see svgd_tc.cu).  stage 1 .. 3; the caller all-reduces (int64 sums) the reduce
-// buffer after stage 1 and hist[pass] after every stage-3 histogram.  workspace = the tensor workspace (after the 3*2048*4+256 B header).
-extern "C" OCBNN_API int ocbnn_svgd_sel_count(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, void* workspace, uint64_t** reduce_buf,
-                                              int64_t* reduce_words, void* stream) {
-    OCBNN_REQUIRE(workspace && n >= 2 && row_begin >= 0 && row_begin + n_rows <= n, OCBNN_EINVAL, "ocbnn_svgd_sel_count: bad argument");
-    unsigned long long* rb = nullptr;
-    int rc = tc::tc_svgd_sel_count(n, d, row_begin, n_rows, workspace, &rb, g_select_mode_value(), (cudaStream_t)stream);
-    if (reduce_buf) *reduce_buf = reinterpret_cast<uint64_t*>(rb);
-    if (reduce_words) *reduce_words = 4 + 2048;
-    return rc;
-}
-extern "C" OCBNN_API int ocbnn_svgd_sel_gather(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, void* workspace, void* stream) {
-    OCBNN_REQUIRE(workspace, OCBNN_EINVAL, "ocbnn_svgd_sel_gather: bad argument");
-    return tc::tc_svgd_sel_gather(n, d, row_begin, n_rows, workspace, (cudaStream_t)stream);
-}
-extern "C" OCBNN_API int ocbnn_svgd_sel_hist(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t pass, uint32_t* hist, uint64_t* select_state,
-                                             void* workspace, void* stream) {
-    OCBNN_REQUIRE(workspace && hist && select_state && pass >= 0 && pass < 3, OCBNN_EINVAL, "ocbnn_svgd_sel_hist: bad argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    if (pass == 0) {
-        k_zero_u32<<<(3 * kBins + 255) / 256, 256, 0, st>>>(hist, 3 * kBins);
-        OCBNN_LAUNCH_CHECK();
-    }
-    return tc::tc_svgd_sel_hist(n, d, row_begin, n_rows, pass, hist, reinterpret_cast<const unsigned long long*>(select_state), workspace, st);
-}
-extern "C" OCBNN_API int ocbnn_svgd_sel_update(int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, int32_t pass, const uint32_t* hist,
-                                               uint64_t* select_state, void* workspace, float* out_h, void* stream) {
-    OCBNN_REQUIRE(workspace && hist && select_state && pass >= 0 && pass < 3, OCBNN_EINVAL, "ocbnn_svgd_sel_update: bad argument");
-    return tc::tc_svgd_sel_update(n, d, row_begin, n_rows, pass, hist, reinterpret_cast<unsigned long long*>(select_state), workspace, out_h,
-                                  (cudaStream_t)stream);
-}
-
+// K3a, all particles on this GPU
 extern "C" OCBNN_API int ocbnn_svgd_bandwidth(const float* x, int64_t n, int64_t d, float* out_h, int32_t use_tensor, void* workspace,
                                               int64_t workspace_bytes, void* stream) {
+    OCBNN_REQUIRE(x && out_h && n >= 2 && d >= 1, OCBNN_EINVAL, "ocbnn_svgd_bandwidth: bad argument");
     OCBNN_REQUIRE(workspace && workspace_bytes >= ocbnn_svgd_workspace_bytes(n, d, n, use_tensor), OCBNN_EINVAL,
                   "ocbnn_svgd_bandwidth: workspace too small (see ocbnn_svgd_workspace_bytes)");
+    cudaStream_t st = (cudaStream_t)stream;
     uint32_t* hist = reinterpret_cast<uint32_t*>(workspace);
-    uint64_t* state = reinterpret_cast<uint64_t*>(hist + 3 * kBins);
-    void* tcws = reinterpret_cast<char*>(workspace) + 3 * kBins * sizeof(uint32_t) + 256;
-    const bool tensor = want_tensor(use_tensor, n);
+    unsigned long long* state = reinterpret_cast<unsigned long long*>(hist + 3 * kBins);
+    void* tcws = reinterpret_cast<char*>(workspace) + kHdrBytes;
     int rc;
-    bool hist0_done = false;
-    // OCBNN_SVGD_SELECT: fast (default; bracket + count + compact, all rows are on this rank) | legacy (3 radix-select histogram
-    // passes, the algorithm the multi-GPU path all-reduces) | fallback (fast path with a sabotaged bracket: tests the in-kernel fallback)
-    const int sel_mode = g_select_mode.load();
-    if (tensor && sel_mode != 0 && n <= 2000000000ll) {
-        return tc::tc_svgd_prepare_select(x, n, d, tcws, workspace_bytes - (3 * kBins * sizeof(uint32_t) + 256), out_h, sel_mode,
-                                          reinterpret_cast<unsigned long long*>(state), (cudaStream_t)stream);
-    }
-    if (tensor) {                       // the pass-0 histogram rides on the distance pass when the direct kernel forms the distances
-        k_zero_u32<<<(3 * kBins + 255) / 256, 256, 0, (cudaStream_t)stream>>>(hist, 3 * kBins);
-        OCBNN_LAUNCH_CHECK();
-        if ((rc = tc::tc_svgd_prepare(x, n, d, 0, n, tcws, workspace_bytes - (3 * kBins * sizeof(uint32_t) + 256), hist, &hist0_done,
-                                      (cudaStream_t)stream)))
-            return rc;
+    if (want_tensor(use_tensor, n)) {
+        if ((rc = tc::tc_svgd_prepare(x, n, d, 0, n, tcws, workspace_bytes - kHdrBytes, st))) return rc;
+        const int mode = g_select_mode.load();
+        if (mode == 0 && !tc::tc_is_flash(n, d)) {          // 3-pass radix select over the materialised distances (D > 64)
+            for (int pass = 0; pass < 3; ++pass) {
+                if (pass == 0) {
+                    k_zero_u32<<<(3 * kBins + 255) / 256, 256, 0, st>>>(hist, 3 * kBins);
+                    OCBNN_LAUNCH_CHECK();
+                }
+                if ((rc = tc::tc_svgd_hist(n, d, 0, n, pass, hist, state, tcws, st))) return rc;
+                if ((rc = simt_select_update(pass, hist, state, n, pass == 2 ? out_h : nullptr, st))) return rc;
+            }
+            return OCBNN_OK;
+        }
+        return tc::tc_svgd_select_local(n, d, tcws, out_h, mode, state, st);
     }
     for (int pass = 0; pass < 3; ++pass) {
-        if (pass == 0 && hist0_done) rc = OCBNN_OK;
-        else if (tensor && pass == 0) rc = tc::tc_svgd_hist(n, d, 0, n, 0, hist, reinterpret_cast<const unsigned long long*>(state), tcws, (cudaStream_t)stream);
-        else rc = tensor ? ocbnn_svgd_hist_pass_prepared(n, d, 0, n, pass, hist, state, tcws, stream)
-                         : ocbnn_svgd_hist_pass(x, n, d, 0, 1, n, pass, hist, state, stream);
-        if (rc) return rc;
-        rc = ocbnn_svgd_select_update(pass, hist, state, n, pass == 2 ? out_h : nullptr, stream);
-        if (rc) return rc;
+        if ((rc = simt_hist_pass(x, n, d, 0, 1, n, pass, hist, state, st))) return rc;
+        if ((rc = simt_select_update(pass, hist, state, n, pass == 2 ? out_h : nullptr, st))) return rc;
     }
     return OCBNN_OK;
 }
 
-// use_tensor: 0 SIMT ; 1 tensor path (centres/splits X and forms the distances itself) ; 2 tensor path, the workspace was prepared
-// for this X and these rows by ocbnn_svgd_prepare / ocbnn_svgd_bandwidth ; -1 choose between 0 and 1
+// use_tensor: 0 SIMT ; 1 tensor path (centres/splits X itself) ; 2 tensor path, the workspace was prepared for this X and these
+// rows by ocbnn_svgd_bandwidth ; -1 choose between 0 and 1
 extern "C" OCBNN_API int ocbnn_svgd_phi(const float* x, const float* g, int64_t n, int64_t d, int64_t row_begin, int64_t n_rows, const float* h,
                               float* out_phi, int32_t use_tensor, void* workspace, int64_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -495,39 +452,109 @@ extern "C" OCBNN_API int ocbnn_svgd_phi(const float* x, const float* g, int64_t 
     if (want_tensor(use_tensor, n)) {
         OCBNN_REQUIRE(workspace && workspace_bytes >= ocbnn_svgd_workspace_bytes(n, d, n_rows, 1), OCBNN_EINVAL,
                       "ocbnn_svgd_phi: workspace too small for the tensor path (see ocbnn_svgd_workspace_bytes)");
-        void* tcws = reinterpret_cast<char*>(workspace) + 3 * kBins * sizeof(uint32_t) + 256;
+        void* tcws = reinterpret_cast<char*>(workspace) + kHdrBytes;
         if (use_tensor != 2) {
-            int rc = tc::tc_svgd_prepare(x, n, d, row_begin, n_rows, tcws, workspace_bytes - (3 * kBins * sizeof(uint32_t) + 256), nullptr, nullptr, st);
+            int rc = tc::tc_svgd_prepare(x, n, d, row_begin, n_rows, tcws, workspace_bytes - kHdrBytes, st);
             if (rc) return rc;
         }
         return tc::tc_svgd_phi(g, h, n, d, row_begin, n_rows, out_phi, tcws, st);
     }
-    if (d <= 64) {
-        unsigned blocks = (unsigned)((n_rows + kRowsPerCta - 1) / kRowsPerCta);
-        if (d <= 32) k_svgd_phi_small<8><<<blocks, kRowsPerCta * kLpr, 0, st>>>(x, g, n, (int)d, row_begin, n_rows, h, out_phi);
-        else k_svgd_phi_small<16><<<blocks, kRowsPerCta * kLpr, 0, st>>>(x, g, n, (int)d, row_begin, n_rows, h, out_phi);
-        OCBNN_LAUNCH_CHECK();
-        return OCBNN_OK;
-    }
-    const int64_t off = 3 * kBins * sizeof(uint32_t) + 256;
-    OCBNN_REQUIRE(workspace && workspace_bytes >= off + (n_rows * n + n_rows) * (int64_t)sizeof(float), OCBNN_EINVAL,
+    OCBNN_REQUIRE(d <= 64 || (workspace && workspace_bytes >= kHdrBytes + (n_rows * n + n_rows) * (int64_t)sizeof(float)), OCBNN_EINVAL,
                   "ocbnn_svgd_phi: workspace too small for the wide exact path (see ocbnn_svgd_workspace_bytes)");
-    float* kmat = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + off);
-    float* rowsum = kmat + n_rows * n;
-    k_kernel_matrix_wide<<<(unsigned)n_rows, 256, 0, st>>>(x, n, (int)d, row_begin, n_rows, h, kmat, rowsum);
-    OCBNN_LAUNCH_CHECK();
-    dim3 grid((unsigned)((d + 63) / 64), (unsigned)((n_rows + 63) / 64));
-    k_phi_gemm_wide<<<grid, 256, 0, st>>>(kmat, rowsum, x, g, n, (int)d, row_begin, n_rows, h, out_phi);
-    OCBNN_LAUNCH_CHECK();
-    return OCBNN_OK;
+    return simt_phi(x, g, n, d, row_begin, n_rows, h, out_phi, d > 64 ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kHdrBytes) : nullptr, st);
+}
+
+// One SVGD iteration, particles sharded over the ranks of `comm` (NULL: one rank).  See include/ocbnn_b200.h.
+// Stream plan: K1 of the owned rows runs on the side stream while the main stream centres X and does the (compute-heavy, X-only)
+// first stage of the select; every collective is issued on the main stream after the join, in the same order on every rank.
+extern "C" OCBNN_API int ocbnn_svgd_step(ocbnn_problem* ph, float* x_all, float* g_all, float* acc, float* phi, float* h, int64_t n, int64_t row_begin,
+                                         int64_t n_rows, float lr, int32_t batch_offset, int32_t batch_stride, int32_t with_data, int32_t use_tensor,
+                                         void* workspace, int64_t workspace_bytes, ocbnn_comm* comm_h, void* stream) {
+    OCBNN_REQUIRE(ph && x_all && g_all && acc && phi && h && n >= 2, OCBNN_EINVAL, "ocbnn_svgd_step: bad argument");
+    Comm* comm = reinterpret_cast<Comm*>(comm_h);
+    const int rank = comm_rank(comm), world = comm_world(comm);
+    long long lo, cnt;
+    shard_of(n, rank, world, &lo, &cnt);
+    OCBNN_REQUIRE(row_begin == lo && n_rows == cnt, OCBNN_EINVAL, "ocbnn_svgd_step: rank %d of %d owns rows [%lld, %lld) of %lld, not [%lld, %lld)", rank, world,
+                  lo, lo + cnt, (long long)n, (long long)row_begin, (long long)(row_begin + n_rows));
+    OCBNN_REQUIRE(batch_stride <= 1 || (batch_offset >= 0 && batch_offset < batch_stride), OCBNN_EINVAL, "batch_offset must be in [0, stride)");
+    const Problem& p = *problem_of(ph);
+    const long long d = p.d;
+    const bool tensor = want_tensor(use_tensor, n);
+    OCBNN_REQUIRE(workspace && workspace_bytes >= ocbnn_svgd_workspace_bytes(n, d, n_rows, tensor ? 1 : 0), OCBNN_EINVAL,
+                  "ocbnn_svgd_step: workspace too small (see ocbnn_svgd_workspace_bytes)");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(workspace);
+    unsigned long long* state = reinterpret_cast<unsigned long long*>(hist + 3 * kBins);
+    void* tcws = reinterpret_cast<char*>(workspace) + kHdrBytes;
+    const long long tcws_bytes = workspace_bytes - kHdrBytes;
+    int rc;
+
+    // ---- fork: gradients of the owned rows (K1) on the side stream ----
+    SideStream* side;
+    if ((rc = side_stream(&side))) return rc;
+    OCBNN_CUDA(cudaEventRecord(side->fork, st));
+    OCBNN_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    if (n_rows > 0) {
+        const EvalArgs a = eval_args(p, batch_offset, batch_stride, with_data);
+        if ((rc = logpost_any(p, a, x_all + row_begin * d, n_rows, nullptr, g_all + row_begin * d, 0, side->stream))) return rc;
+    }
+    OCBNN_CUDA(cudaEventRecord(side->join, side->stream));
+
+    // ---- main: bandwidth (K3a) ----
+    const int mode = g_select_mode.load();
+    const bool legacy = tensor && mode == 0 && !tc::tc_is_flash(n, d);       // plain radix select over materialised distances
+    unsigned long long* red64 = nullptr;
+    if (tensor) {
+        if ((rc = tc::tc_svgd_prepare(x_all, n, d, row_begin, n_rows, tcws, tcws_bytes, st))) return rc;
+        if (world == 1 && !legacy) {
+            if ((rc = tc::tc_svgd_select_local(n, d, tcws, h, mode, state, st))) return rc;
+        } else if (!legacy) {
+            if ((rc = tc::tc_svgd_sel_stage1(n, d, row_begin, n_rows, rank, world, tcws, mode, &red64, st))) return rc;
+        }
+    }
+    OCBNN_CUDA(cudaStreamWaitEvent(st, side->join, 0));                       // join
+    if ((rc = comm_all_gather_rows(comm, g_all, n, d, st))) return rc;
+    if (tensor && legacy) {
+        for (int pass = 0; pass < 3; ++pass) {
+            if (pass == 0) {
+                k_zero_u32<<<(3 * kBins + 255) / 256, 256, 0, st>>>(hist, 3 * kBins);
+                OCBNN_LAUNCH_CHECK();
+            }
+            if (n_rows > 0 && (rc = tc::tc_svgd_hist(n, d, row_begin, n_rows, pass, hist, state, tcws, st))) return rc;
+            if ((rc = comm_all_sum(comm, hist + pass * kBins, kBins, kCommU32, st))) return rc;
+            if ((rc = simt_select_update(pass, hist, state, n, pass == 2 ? h : nullptr, st))) return rc;
+        }
+    } else if (tensor && world > 1) {
+        if ((rc = comm_all_sum(comm, red64, 4 + 2048, kCommU64, st))) return rc;
+        if ((rc = tc::tc_svgd_sel_stage2(n, d, row_begin, n_rows, tcws, st))) return rc;
+        for (int pass = 0; pass < 3; ++pass) {
+            unsigned* hp = nullptr;
+            if ((rc = tc::tc_svgd_sel_hist(n, d, row_begin, n_rows, rank, world, pass, tcws, &hp, st))) return rc;
+            if ((rc = comm_all_sum(comm, hp, 2048, kCommU32, st))) return rc;
+            if ((rc = tc::tc_svgd_sel_update(n, d, row_begin, n_rows, pass, tcws, h, st))) return rc;
+        }
+    } else if (!tensor) {
+        // exact SIMT arm: rows dealt out cyclically (balances the i < j triangle), histograms summed over the ranks
+        const long long my_rows = n > rank ? (n - rank + world - 1) / world : 0;
+        for (int pass = 0; pass < 3; ++pass) {
+            if ((rc = simt_hist_pass(x_all, n, d, rank, world, my_rows, pass, hist, state, st))) return rc;
+            if ((rc = comm_all_sum(comm, hist + pass * kBins, kBins, kCommU32, st))) return rc;
+            if ((rc = simt_select_update(pass, hist, state, n, pass == 2 ? h : nullptr, st))) return rc;
+        }
+    }
+
+    // ---- phi (K3b) and Adagrad (K3c) on the owned rows, then the particles go round ----
+    if (n_rows > 0) {
+        if (tensor) rc = tc::tc_svgd_phi(g_all, h, n, d, row_begin, n_rows, phi, tcws, st);
+        else rc = simt_phi(x_all, g_all, n, d, row_begin, n_rows, h, phi, d > 64 ? reinterpret_cast<float*>(tcws) : nullptr, st);
+        if (rc) return rc;
+        if ((rc = adagrad_launch(x_all + row_begin * d, acc, phi, n_rows * d, lr, -1.f, st))) return rc;      // particles.grad = -phi (inference.py:280)
+    }
+    return comm_all_gather_rows(comm, x_all, n, d, st);
 }
 
 extern "C" OCBNN_API int ocbnn_adagrad_step(float* x, float* acc, const float* dir, int64_t n_elem, float lr, float grad_sign, void* stream) {
     OCBNN_REQUIRE(x && acc && dir && n_elem >= 0, OCBNN_EINVAL, "ocbnn_adagrad_step: bad argument");
-    if (n_elem == 0) return OCBNN_OK;
-    long long blocks = (n_elem + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    k_adagrad<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, acc, dir, n_elem, lr, grad_sign);
-    OCBNN_LAUNCH_CHECK();
-    return OCBNN_OK;
+    return adagrad_launch(x, acc, dir, n_elem, lr, grad_sign, (cudaStream_t)stream);
 }

@@ -125,6 +125,9 @@ struct TcWs {
     unsigned long long* red64;        // multi-rank bracket select: [zeros, below, candidates, overflow | ghist as 2048 u64] summed over ranks
     unsigned long long* sel; // bracket-select header: see SelHdr
     long long cand_cap;
+    bool flash;                       // D <= 64: svgd_flash.cuh kernels, no d2 / K in the workspace
+    int fl_tiles, fl_splits, fl_per, fl_nj;   // flash phi: row tiles per CTA, column splits, column blocks per split / in total
+    float* ncr;                       // flash phi: -r_j log2(e) / h per column (-inf beyond n)
     unsigned* hist;
     unsigned long long* state;
     long long bytes;
@@ -139,15 +142,25 @@ static int pick_splits(long long n_rows, long long n4, int two_dp, int bn) {
     return (int)(s < 1 ? 1 : s);
 }
 
-static int fused_splits(long long n_rows, long long n4);
 long long tc_workspace_bytes(long long n, long long d, long long n_rows);      // K splits of the fused phi kernel (defined with it)
 
-static bool fused_enabled() {          // OCBNN_SVGD_FUSED=0 forces the unfused phi pipeline (K materialised as hi/lo matrices, TMA-fed GEMM)
-    static const bool on = [] { const char* e = getenv("OCBNN_SVGD_FUSED"); return !(e && e[0] == '0'); }();
-    return on;
-}
-constexpr int kFusedMaxSplitsHost = 16; // = kFusedMaxSplits
 constexpr int kSelSamplesHost = 32768;      // = kSelSamples (pair sample of the bracket select, defined with its kernels)
+constexpr int kSelSamplesMaxHost = 1 << 20;
+// work split of the flash phi kernel: `tiles` 128-row tiles per CTA (2 when D <= 32 and there are enough rows to fill the
+// SMs that way), column blocks of 64 particles, at most 8 of them (512 columns) accumulated into one TMEM accumulator
+static void flash_plan(long long n, long long n_rows, int dp, int* tiles, int* splits, int* per, int* nj_total) {
+    const int nj = (int)((n + 63) / 64);
+    const int t = (dp == 32 && n_rows >= 3072) ? 2 : 1;
+    const long long row_blocks = (n_rows + 128 * t - 1) / (128 * t);
+    int p = 8;                                                   // column blocks per split (accumulation chain limit)
+    const long long want = (148 + row_blocks - 1) / row_blocks;  // splits needed to put a CTA on every SM
+    if (want > (nj + p - 1) / p) p = (int)((nj + want - 1) / want);
+    if (p < 1) p = 1;
+    *tiles = t;
+    *per = p;
+    *splits = (nj + p - 1) / p;
+    *nj_total = nj;
+}
 
 static TcWs carve(void* workspace, long long n, long long d, long long row_begin, long long n_rows) {
     TcWs w{};
@@ -164,22 +177,32 @@ static TcWs carve(void* workspace, long long n, long long d, long long row_begin
     w.xc = take(n * w.dp);
     w.xc_hi = take(n * w.dp);
     w.xc_lo = take(n * w.dp);
-    w.d2 = take(n_rows * w.n4);
-    // the K matrices (hi / lo, n_rows x n4 each) exist only on the unfused path; the fused phi kernel (one N tile) keeps K on
-    // chip and needs only the per-split row sums there (2/3 of the workspace at large n)
-    const bool fused = fused_enabled() && 2 * w.dp <= w.bn;
-    w.k_hi = take(fused ? (long long)kFusedMaxSplitsHost * n_rows : n_rows * w.n4);
-    w.k_lo = take(fused ? 0 : n_rows * w.n4);
+    w.flash = w.dp <= 64;
+    if (w.flash) {
+        // D <= 64: neither the distances nor K are ever materialised (svgd_flash.cuh); what is left are the per-split partial
+        // outputs of the flash kernel
+        flash_plan(n, n_rows, (int)w.dp, &w.fl_tiles, &w.fl_splits, &w.fl_per, &w.fl_nj);
+        w.d2 = nullptr;
+        w.k_lo = nullptr;
+        w.k_hi = take((long long)w.fl_splits * 2 * n_rows);                        // partial row sums (rs_part)
+        w.ncr = take((long long)w.fl_nj * 64);
+    } else {
+        w.fl_tiles = w.fl_splits = w.fl_per = w.fl_nj = 0;
+        w.d2 = take(n_rows * w.n4);                                                // distance rows of this rank (Gram GEMM)
+        w.k_hi = take(n_rows * w.n4);                                              // K = exp(-d2/h) as tf32 hi / lo matrices
+        w.k_lo = take(n_rows * w.n4);
+        w.ncr = nullptr;
+    }
     w.vt_hi = take(2 * w.dp * w.n4);
     w.vt_lo = take(2 * w.dp * w.n4);
     w.rowsum = take(n_rows);
-    const int fs = fused_splits(n_rows, w.n4);
-    w.o = take((long long)(w.splits > fs ? w.splits : fs) * n_rows * 2 * w.dp);
+    w.o = take((long long)(w.flash ? w.fl_splits : w.splits) * n_rows * 2 * w.dp);
     w.sel = reinterpret_cast<unsigned long long*>(take(64));
-    w.cand_cap = n_rows * n / 16 > (1 << 16) ? n_rows * n / 16 : (1 << 16);      // ~2x the pairs a 3.3 % bracket keeps of this rank's rows
+    // candidates: ~2x the pairs the bracket keeps (3.3 % of the pairs up to n = 4096, narrower above: see sel_samples)
+    w.cand_cap = n_rows * n / 16 > (1 << 16) ? n_rows * n / 16 : (1 << 16);
     w.cand = take(w.cand_cap);
     w.list2 = take(w.cand_cap);
-    w.samples = take(kSelSamplesHost);
+    w.samples = take(kSelSamplesMaxHost);
     w.ghist = reinterpret_cast<unsigned*>(take(4096));
     w.red64 = reinterpret_cast<unsigned long long*>(take(2 * (4 + 2048)));
     w.bytes = p - reinterpret_cast<char*>(workspace);
@@ -232,71 +255,6 @@ k_center_split(const float* __restrict__ x, const float* __restrict__ mean, long
 __device__ __forceinline__ void hist_add_warp(unsigned* sh, unsigned bin) {
     const unsigned peers = __match_any_sync(0xffffffffu, bin);
     if (bin != 0xFFFFFFFFu && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[bin], (unsigned)__popc(peers));
-}
-
-// exact squared distances for small D (dp <= 64): d2[t][j] = ||xc_i - xc_j||^2 by direct differences.
-// 64 x 64 tile per CTA, 4 x 4 per thread, float4 shared-memory operands.  When hist0 != NULL the first radix-select
-// histogram (top 11 bits of the eps-perturbed distance, pairs i < j) is accumulated in the same pass.
-template <int DP>
-__global__ void __launch_bounds__(256)
-k_d2_direct(const float* __restrict__ hi, const float* __restrict__ lo, const float* __restrict__ ssum, long long n, long long n4, int d,
-            long long row_begin, long long n_rows, float* __restrict__ d2, unsigned* __restrict__ hist0) {
-    __shared__ __align__(16) float xi[64][DP + 4];
-    __shared__ __align__(16) float xj[64][DP + 4];
-    __shared__ unsigned sh[2048];
-    const long long t0 = (long long)blockIdx.y * 64, j0 = (long long)blockIdx.x * 64;
-    if (hist0) for (int i = threadIdx.x; i < 2048; i += 256) sh[i] = 0u;
-    for (int idx = threadIdx.x; idx < 64 * DP; idx += 256) {
-        const int rr = idx / DP, c = idx % DP;
-        const long long i = row_begin + t0 + rr, j = j0 + rr;
-        xi[rr][c] = (t0 + rr < n_rows) ? hi[i * DP + c] + lo[i * DP + c] : 0.f;
-        xj[rr][c] = j < n ? hi[j * DP + c] + lo[j * DP + c] : 0.f;
-    }
-    __syncthreads();
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // columns tx + 16 q, rows ty + 16 p (interleaved: conflict-free rows)
-    float acc[4][4] = {};
-#pragma unroll
-    for (int c = 0; c < DP; c += 4) {
-        float4 a[4], b[4];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) a[p] = *reinterpret_cast<const float4*>(&xi[ty + 16 * p][c]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4*>(&xj[tx + 16 * q][c]);
-#pragma unroll
-        for (int p = 0; p < 4; ++p)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float e;
-                e = a[p].x - b[q].x; acc[p][q] = fmaf(e, e, acc[p][q]);
-                e = a[p].y - b[q].y; acc[p][q] = fmaf(e, e, acc[p][q]);
-                e = a[p].z - b[q].z; acc[p][q] = fmaf(e, e, acc[p][q]);
-                e = a[p].w - b[q].w; acc[p][q] = fmaf(e, e, acc[p][q]);
-            }
-    }
-    const float eps = 1e-6f, deps2 = (float)d * 1e-12f;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const long long t = t0 + ty + 16 * p, i = row_begin + t;
-        const float si = (hist0 && t < n_rows) ? ssum[i] : 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const long long j = j0 + tx + 16 * q;
-            if (t < n_rows && j < n4) d2[t * n4 + j] = j < n ? acc[p][q] : 0.f;
-            if (hist0) {
-                unsigned bin = 0xFFFFFFFFu;
-                if (t < n_rows && j > i && j < n) {
-                    const unsigned bits = __float_as_uint(sqrtf(fmaxf(acc[p][q] + 2.f * eps * (si - ssum[j]) + deps2, 0.f)));
-                    if (bits != 0u) bin = bits >> 21;
-                }
-                hist_add_warp(sh, bin);
-            }
-        }
-    }
-    if (hist0) {
-        __syncthreads();
-        for (int b = threadIdx.x; b < 2048; b += 256)
-            if (sh[b]) atomicAdd(&hist0[b], sh[b]);
-    }
 }
 
 // radix-select histogram pass over the eps-perturbed distances reconstructed from d2:
@@ -367,23 +325,35 @@ __device__ __forceinline__ float pair_w(float d2v, float si, float sj, int d) { 
 __device__ __forceinline__ float pair_dist(const float* __restrict__ d2, const float* __restrict__ ssum, long long n4, int d, long long i, long long j) {
     return pair_w(d2[i * n4 + j], ssum[i], ssum[j], d);
 }
+// distance source of the select's fallback: the materialised matrix (D > 64) or, on the flash path, the centred particles
+// themselves (exact fp32 differences, the arithmetic of exact_d2 in svgd_flash.cuh)
+struct DistSrc {
+    const float* d2;       // rows [row_off, ...) x n4, or NULL
+    const float* xc;       // n x dp (used when d2 == NULL)
+    long long n4, row_off;
+    int dp;
+    __device__ __forceinline__ float operator()(const float* __restrict__ ssum, int d, long long i, long long j) const {
+        if (d2) return pair_w(d2[(i - row_off) * n4 + j], ssum[i], ssum[j], d);
+        const float4* a4 = reinterpret_cast<const float4*>(xc + i * dp);
+        const float4* b4 = reinterpret_cast<const float4*>(xc + j * dp);
+        float acc = 0.f;
+        for (int c = 0; c < dp / 4; ++c) {
+            const float4 a = __ldg(a4 + c), b = __ldg(b4 + c);
+            float e;
+            e = a.x - b.x; acc = fmaf(e, e, acc);
+            e = a.y - b.y; acc = fmaf(e, e, acc);
+            e = a.z - b.z; acc = fmaf(e, e, acc);
+            e = a.w - b.w; acc = fmaf(e, e, acc);
+        }
+        return pair_w(acc, ssum[i], ssum[j], d);
+    }
+};
 __device__ __forceinline__ unsigned mix32(unsigned x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
 }
 
 constexpr int kSelSamples = kSelSamplesHost, kSelBins = 4096;
-
-__global__ void __launch_bounds__(256)
-k_sel_sample(const float* __restrict__ d2, const float* __restrict__ ssum, long long n, long long n4, int d, float* __restrict__ samples) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= kSelSamples) return;
-    const unsigned a = mix32((unsigned)idx * 2u + 0x9e3779b9u), b = mix32(a ^ 0x85ebca6bu);
-    long long i = (long long)(a % (unsigned)n), j = (long long)(b % (unsigned)n);
-    if (i == j) j = (j + 1) % n;
-    if (i > j) { const long long tmp = i; i = j; j = tmp; }
-    samples[idx] = pair_dist(d2, ssum, n4, d, i, j);
-}
 
 // block-wide: index of the bin holding 0-based rank `rank` in bins[0..NT*BPT) (shared or global), residual rank out.
 // NT threads, BPT consecutive bins per thread.  Contains __syncthreads.
@@ -418,23 +388,19 @@ __device__ __forceinline__ int block_find_bin(const unsigned* bins, unsigned lon
 }
 
 __global__ void __launch_bounds__(1024)
-k_sel_bracket(const float* __restrict__ samples, SelHdr* __restrict__ hdr, unsigned* __restrict__ ghist, int sabotage) {
+k_sel_bracket(const float* __restrict__ samples, int ns, SelHdr* __restrict__ hdr, unsigned* __restrict__ ghist, int sabotage) {
     __shared__ unsigned sh[kSelBins];
     __shared__ float red_min[32], red_max[32];
     __shared__ unsigned red_cnt[32];
     __shared__ unsigned wsum[32];
     __shared__ int s_bin;
     __shared__ unsigned long long s_res;
-    constexpr int PT = kSelSamples / 1024;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int i = t; i < kSelBins; i += 1024) { sh[i] = 0u; ghist[i] = 0u; }
-    float v[PT];
     float mn = INFINITY, mx = 0.f;
     unsigned cnt = 0;
-#pragma unroll
-    for (int k = 0; k < PT; ++k) {
-        const float x = samples[k * 1024 + t];
-        v[k] = x;
+    for (int k = t; k < ns; k += 1024) {
+        const float x = samples[k];
         if (x != 0.f) { mn = fminf(mn, x); mx = fmaxf(mx, x); ++cnt; }
     }
 #pragma unroll
@@ -448,11 +414,13 @@ k_sel_bracket(const float* __restrict__ samples, SelHdr* __restrict__ hdr, unsig
     mn = INFINITY; mx = 0.f; cnt = 0;
     for (int w = 0; w < 32; ++w) { mn = fminf(mn, red_min[w]); mx = fmaxf(mx, red_max[w]); cnt += red_cnt[w]; }
     const float scale = mx > mn ? (float)kSelBins / (mx - mn) : 0.f;
-#pragma unroll
-    for (int k = 0; k < PT; ++k)
-        if (v[k] != 0.f) atomicAdd(&sh[min(kSelBins - 1, (int)((v[k] - mn) * scale))], 1u);
+    for (int k = t; k < ns; k += 1024) {
+        const float x = samples[k];
+        if (x != 0.f) atomicAdd(&sh[min(kSelBins - 1, (int)((x - mn) * scale))], 1u);
+    }
     __syncthreads();
-    const float delta = 0.0155f, width = scale > 0.f ? 1.f / scale : 0.f;      // 5.6 sigma of the sample-rank error at 32768 samples
+    // half-width of the quantile bracket: 5.6 sigma of the sample-rank error (0.0155 at 32768 samples)
+    const float delta = 2.8f * rsqrtf((float)ns), width = scale > 0.f ? 1.f / scale : 0.f;
     const unsigned r_lo = (unsigned)fmaxf(0.f, floorf((0.5f - delta) * (float)cnt)), r_hi = min(cnt ? cnt - 1 : 0u, (unsigned)ceilf((0.5f + delta) * (float)cnt));
     unsigned long long dummy;
     const int b_lo = block_find_bin<1024, 4>(sh, r_lo, &dummy, wsum, &s_bin, &s_res);
@@ -540,7 +508,7 @@ __device__ __forceinline__ bool sel_ok(const SelHdr* hdr, long long n, unsigned 
 // bin - or, if the bracket missed, over the whole upper triangle of d2 - and h = med^2 / ln n.  Fields that other CTAs of the
 // same launch wrote (n2, resid) are read past the L1 (__ldcg).
 template <int NT>
-__device__ __forceinline__ void sel_final_body(const float* __restrict__ d2, const float* __restrict__ ssum, long long n, long long n4, int d,
+__device__ __forceinline__ void sel_final_body(const DistSrc dist, const float* __restrict__ ssum, long long n, int d,
                                                const SelHdr* hdr, const float* list2, long long cap2, float* __restrict__ out_h,
                                                unsigned long long* __restrict__ dbg, unsigned* sh, unsigned* wsum, int* s_bin, unsigned long long* s_res) {
     const int t = threadIdx.x;
@@ -568,7 +536,7 @@ __device__ __forceinline__ void sel_final_body(const float* __restrict__ d2, con
                 // counts, i.e. n <= 92681)
                 for (long long i = 0; i < n; ++i)
                     for (long long j = i + 1 + t; j < n; j += NT) {
-                        const unsigned bits = __float_as_uint(pair_dist(d2, ssum, n4, d, i, j));
+                        const unsigned bits = __float_as_uint(dist(ssum, d, i, j));
                         if (bits != 0u) add(bits);
                     }
             }
@@ -587,7 +555,7 @@ __device__ __forceinline__ void sel_final_body(const float* __restrict__ d2, con
 // Single rank (multi = 0): gather + final in one launch - the last CTA to finish (ticket in hdr->done) runs the final select.
 __global__ void __launch_bounds__(256)
 k_sel_gather(long long n, SelHdr* hdr, const unsigned* __restrict__ ghist, const float* __restrict__ cand, float* list2, long long cap2, int multi,
-             const float* __restrict__ d2, const float* __restrict__ ssum, long long n4, int d, float* __restrict__ out_h,
+             const DistSrc dist, const float* __restrict__ ssum, int d, float* __restrict__ out_h,
              unsigned long long* __restrict__ dbg) {
     __shared__ unsigned sh[2048];
     __shared__ unsigned wsum[8];
@@ -618,7 +586,7 @@ k_sel_gather(long long n, SelHdr* hdr, const unsigned* __restrict__ ghist, const
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    sel_final_body<256>(d2, ssum, n, n4, d, hdr, list2, cap2, out_h, dbg, sh, wsum, &s_bin, &s_res);
+    sel_final_body<256>(dist, ssum, n, d, hdr, list2, cap2, out_h, dbg, sh, wsum, &s_bin, &s_res);
 }
 
 
@@ -643,7 +611,7 @@ k_sel_unpack(SelHdr* __restrict__ hdr, unsigned* __restrict__ ghist, const unsig
 }
 // radix-select histogram pass of the final stage: over this rank's short list (bracket hit) or over its distance rows (miss)
 __global__ void __launch_bounds__(256)
-k_hist_sel(const float* __restrict__ d2, const float* __restrict__ ssum, long long n, long long n4, int d, long long row_begin, long long n_rows,
+k_hist_sel(const DistSrc dist, const float* __restrict__ ssum, long long n, int d, long long row_start, long long row_step, long long n_rows,
            const SelHdr* __restrict__ hdr, const float* __restrict__ list2, long long cap2, int pass, unsigned* __restrict__ hist,
            const unsigned long long* __restrict__ state) {
     __shared__ unsigned sh[2048];
@@ -666,12 +634,11 @@ k_hist_sel(const float* __restrict__ d2, const float* __restrict__ ssum, long lo
             add(i < n2 ? __float_as_uint(list2[i]) : 0u);
         }
     } else {
-        for (long long t = blockIdx.x; t < n_rows; t += gridDim.x) {
-            const long long i = row_begin + t;
-            const float si = ssum[i];
+        for (long long t = blockIdx.x; t < n_rows; t += gridDim.x) {       // bracket missed: this rank's rows, every pair i < j
+            const long long i = row_start + t * row_step;
             for (long long j0 = (i + 1) / 256 * 256; j0 < n; j0 += 256) {
                 const long long j = j0 + threadIdx.x;
-                add((j > i && j < n) ? __float_as_uint(pair_w(d2[t * n4 + j], si, ssum[j], d)) : 0u);
+                add((j > i && j < n) ? __float_as_uint(dist(ssum, d, i, j)) : 0u);
             }
         }
     }
@@ -705,17 +672,12 @@ k_select_update_sel(int pass, const unsigned* __restrict__ hist, unsigned long l
     }
 }
 
-// ---- single-rank, D <= 64: distances and the select's counting pass in ONE symmetric kernel -------------------------------
-// k_sel_sample_x draws the pair sample straight from the centred particles (the bracket is needed before d2 exists);
-// k_d2_sym computes only the tiles on and above the diagonal of d2 (half the FMA work of k_d2_direct), writes each tile and,
-// through a shared-memory transpose, its mirror image, and classifies the pairs i < j of the tile against the bracket on the
-// way (zeros / below in registers, candidates compacted through warp-private staging + the linear histogram): no second
-// pass over d2 for the median.
+// ---- pair sample of the bracket select, drawn straight from the centred particles ---------------------------------------
 template <int DP>
 __global__ void __launch_bounds__(256)
-k_sel_sample_x(const float* __restrict__ xc, const float* __restrict__ ssum, long long n, int d, float* __restrict__ samples) {
+k_sel_sample_x(const float* __restrict__ xc, const float* __restrict__ ssum, long long n, int d, float* __restrict__ samples, int ns) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= kSelSamples) return;
+    if (idx >= ns) return;
     const unsigned a = mix32((unsigned)idx * 2u + 0x9e3779b9u), b = mix32(a ^ 0x85ebca6bu);
     long long i = (long long)(a % (unsigned)n), j = (long long)(b % (unsigned)n);
     if (i == j) j = (j + 1) % n;
@@ -736,9 +698,9 @@ k_sel_sample_x(const float* __restrict__ xc, const float* __restrict__ ssum, lon
 
 // pair sample for D > 64 (one warp per pair; the distance is only a bracket estimate)
 __global__ void __launch_bounds__(256)
-k_sel_sample_wide(const float* __restrict__ xc, const float* __restrict__ ssum, long long n, int d, int dp, float* __restrict__ samples) {
+k_sel_sample_wide(const float* __restrict__ xc, const float* __restrict__ ssum, long long n, int d, int dp, float* __restrict__ samples, int ns) {
     const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (idx >= kSelSamples) return;
+    if (idx >= ns) return;
     const unsigned a = mix32((unsigned)idx * 2u + 0x9e3779b9u), b = mix32(a ^ 0x85ebca6bu);
     long long i = (long long)(a % (unsigned)n), j = (long long)(b % (unsigned)n);
     if (i == j) j = (j + 1) % n;
@@ -751,151 +713,6 @@ k_sel_sample_wide(const float* __restrict__ xc, const float* __restrict__ ssum, 
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (lane == 0) samples[idx] = pair_w(acc, ssum[i], ssum[j], d);
-}
-
-template <int DP>
-__global__ void __launch_bounds__(256)
-k_d2_sym(const float* __restrict__ xc, const float* __restrict__ ssum, long long n, long long n4, int d,
-         float* __restrict__ d2, SelHdr* __restrict__ hdr, float* __restrict__ cand, long long cand_cap, unsigned* __restrict__ ghist) {
-    if (blockIdx.x < blockIdx.y) return;                        // tiles below the diagonal are the mirror images
-    // operands transposed in shared memory, [dim][row'] with row' = 4 (row % 16) + row / 16, so that the 4 rows (4 columns) of a
-    // thread's register tile are ONE LDS.128 per dimension and the difference / square-accumulate run as packed FADD2 / FFMA2
-    constexpr int RS = 64 + 4;
-    __shared__ __align__(16) float sm_x[(2 * DP * RS > 64 * 65) ? 2 * DP * RS : 64 * 65];     // xiT | xjT, later the 64 x 65 tile of the mirror
-    constexpr unsigned kStageCap = 2048;
-    __shared__ float stage[kStageCap];
-    __shared__ unsigned long long red[2][8];
-    __shared__ unsigned s_cnt, s_base;
-    if (threadIdx.x == 0) s_cnt = 0u;
-    float (*xiT)[RS] = reinterpret_cast<float (*)[RS]>(sm_x);
-    float (*xjT)[RS] = reinterpret_cast<float (*)[RS]>(sm_x + DP * RS);
-    const long long t0 = (long long)blockIdx.y * 64, j0 = (long long)blockIdx.x * 64;
-    const bool diag = blockIdx.x == blockIdx.y;
-    for (int idx = threadIdx.x; idx < 64 * (DP / 4); idx += 256) {
-        // a warp takes rows {0-7, 16-23, 32-39, 48-55} (+8 on odd turns) of one 4-dimension chunk: their transposed positions
-        // rp are 32 different banks, so the scalar transposed stores below are conflict free
-        const int g = idx & 31, blk = idx >> 5;
-        const int rr = (g & 7) + 16 * (g >> 3) + 8 * (blk & 1), c = blk >> 1;
-        const int rp = 4 * (rr & 15) + (rr >> 4);
-        const long long i = t0 + rr, j = j0 + rr;
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 a = i < n ? __ldg(reinterpret_cast<const float4*>(xc + i * DP) + c) : z4;
-        const float4 b = j < n ? __ldg(reinterpret_cast<const float4*>(xc + j * DP) + c) : z4;
-        xiT[4 * c + 0][rp] = a.x; xiT[4 * c + 1][rp] = a.y; xiT[4 * c + 2][rp] = a.z; xiT[4 * c + 3][rp] = a.w;
-        xjT[4 * c + 0][rp] = b.x; xjT[4 * c + 1][rp] = b.y; xjT[4 * c + 2][rp] = b.z; xjT[4 * c + 3][rp] = b.w;
-    }
-    __syncthreads();
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // columns tx + 16 q, rows ty + 16 p
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2 acc2[4][2];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) acc2[p][0] = acc2[p][1] = make_float2(0.f, 0.f);
-#pragma unroll 8
-    for (int c = 0; c < DP; ++c) {
-        const float4 a = *reinterpret_cast<const float4*>(&xiT[c][4 * ty]);
-        const float4 b = *reinterpret_cast<const float4*>(&xjT[c][4 * tx]);
-        const float2 b01 = make_float2(b.x, b.y), b23 = make_float2(b.z, b.w);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const float2 na = make_float2(-av[p], -av[p]);
-            const float2 e0 = __fadd2_rn(b01, na), e1 = __fadd2_rn(b23, na);
-            acc2[p][0] = __ffma2_rn(e0, e0, acc2[p][0]);
-            acc2[p][1] = __ffma2_rn(e1, e1, acc2[p][1]);
-        }
-    }
-    float acc[4][4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) { acc[p][0] = acc2[p][0].x; acc[p][1] = acc2[p][0].y; acc[p][2] = acc2[p][1].x; acc[p][3] = acc2[p][1].y; }
-    // ---- the tile itself, and the classification of its pairs i < j (on squared distances; branch-free counting, one
-    //      staging flush per warp: at most 16 x 32 candidates) ----
-    const float lo_b = hdr->lo, hi_b = hdr->hi;
-    const float scale = hi_b > lo_b ? (float)kSelBins / (hi_b - lo_b) : 0.f;
-    float si[4], sj[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) si[p] = t0 + ty + 16 * p < n ? ssum[t0 + ty + 16 * p] : 0.f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) sj[q] = j0 + tx + 16 * q < n ? ssum[j0 + tx + 16 * q] : 0.f;
-    // candidates are staged per CTA (shared-memory counter) and appended with ONE global atomic per CTA: per-warp appends put
-    // ~16 K atomics on the same address at n = 4096 (2 M at n = 32768) and serialised in the L2
-    unsigned zeros = 0, below = 0;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    // interior tiles strictly above the diagonal (all but O(n/64) of them) need no bounds or j > i tests
-    const bool interior = !diag && t0 + 64 <= n && j0 + 64 <= n;
-    auto classify = [&](auto interior_tag) {
-        constexpr bool IN = decltype(interior_tag)::value;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const long long t = t0 + ty + 16 * p;
-            float* drow = d2 + t * n4 + j0 + tx;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const long long j = j0 + tx + 16 * q;
-                if (IN) drow[16 * q] = acc[p][q];
-                else if (t < n && j < n4) drow[16 * q] = j < n ? acc[p][q] : 0.f;
-                const float v = pair_w(acc[p][q], si[p], sj[q], d);
-                const bool valid = IN || (t < n && j < n && j > t);
-                zeros += (valid && v == 0.f) ? 1u : 0u;
-                below += (valid && v > 0.f && v < lo_b) ? 1u : 0u;
-                const bool is_c = valid && v >= lo_b && v <= hi_b && v > 0.f;
-                const unsigned m = __ballot_sync(0xffffffffu, is_c);
-                if (m) {
-                    unsigned wb = 0;
-                    if (lane == 0) wb = atomicAdd(&s_cnt, (unsigned)__popc(m));
-                    wb = __shfl_sync(0xffffffffu, wb, 0);
-                    if (is_c) {
-                        const unsigned pos = wb + __popc(m & lt_mask);
-                        if (pos < kStageCap) stage[pos] = v;
-                        atomicAdd(&ghist[sel_lbin(v, lo_b, scale)], 1u);
-                    }
-                }
-            }
-        }
-    };
-    if (interior) classify(std::true_type{}); else classify(std::false_type{});
-    unsigned long long z = zeros, b = below;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        z += __shfl_xor_sync(0xffffffffu, z, off);
-        b += __shfl_xor_sync(0xffffffffu, b, off);
-    }
-    if (lane == 0) { red[0][warp] = z; red[1][warp] = b; }
-    __syncthreads();                                             // also: everybody is done with xiT / xjT, staging complete
-    const unsigned cnt = s_cnt;
-    if (threadIdx.x == 0) {
-        z = 0; b = 0;
-        for (int w = 0; w < 8; ++w) { z += red[0][w]; b += red[1][w]; }
-        if (z) atomicAdd(&hdr->zeros, z);
-        if (b) atomicAdd(&hdr->below, b);
-        unsigned base = 0;
-        if (cnt) base = atomicAdd(&hdr->ncand, cnt);
-        if (cnt > kStageCap || (long long)base + cnt > cand_cap) { hdr->overflow = 1u; base = 0xFFFFFFFFu; }
-        s_base = base;
-    }
-    __syncthreads();
-    if (cnt && s_base != 0xFFFFFFFFu)
-        for (unsigned k = threadIdx.x; k < cnt; k += 256) cand[s_base + k] = stage[k];
-    __syncthreads();                                             // stage / sm_x are reused below
-    if (diag) return;
-    // ---- mirror image: d2[j][t] = d2[t][j], transposed through shared memory so that both writes are coalesced ----
-    float (*tile)[65] = reinterpret_cast<float (*)[65]>(sm_x);
-#pragma unroll
-    for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) tile[ty + 16 * p][tx + 16 * q] = acc[p][q];
-    __syncthreads();
-    const int col = threadIdx.x & 63;
-    float* mrow = d2 + (j0 + (threadIdx.x >> 6)) * n4 + t0 + col;
-#pragma unroll 4
-    for (int rr = 0; rr < 16; ++rr) {
-        const int row = (threadIdx.x >> 6) + 4 * rr;
-        if (interior) {
-            mrow[(long long)(4 * rr) * n4] = tile[col][row];
-        } else {
-            const long long jg = j0 + row, tg = t0 + col;       // row jg of d2, column tg
-            if (jg < n && tg < n4) d2[jg * n4 + tg] = tg < n ? tile[col][row] : 0.f;
-        }
-    }
 }
 
 // K = exp(-d2/h) split into tf32 hi/lo, row sums; one block per row
@@ -936,11 +753,18 @@ k_kmat_split(const float* __restrict__ d2, const float* __restrict__ hptr, long 
 // Vt[c][j] : c < dp -> g[j][c] ; c >= dp -> xc[j][c - dp] ; split hi/lo, zero padded.  32x32 shared-memory transpose.
 __global__ void __launch_bounds__(256)
 k_vt_split(const float* __restrict__ g, const float* __restrict__ xc_hi, const float* __restrict__ xc_lo, long long n, long long n4, int d, int dp,
-           float* __restrict__ vt_hi, float* __restrict__ vt_lo) {
+           float* __restrict__ vt_hi, float* __restrict__ vt_lo, const float* __restrict__ r, const float* __restrict__ hptr, float* __restrict__ ncr,
+           long long ncr_len) {
     __shared__ float tile[32][33];
     const long long j0 = (long long)blockIdx.x * 32;
     const int c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 8 rows per pass
+    if (ncr && blockIdx.y == 0 && ty == 0) {
+        // flash phi: exponent offset of column j, -r_j log2(e) / h; -inf beyond n switches the padding columns off (K = 0)
+        const float c = 1.4426950408889634f / __ldg(hptr);
+        const long long end = blockIdx.x == gridDim.x - 1 ? ncr_len : j0 + 32;
+        for (long long j = j0 + tx; j < end; j += 32) ncr[j] = j < n ? -c * r[j] : -INFINITY;
+    }
     for (int rr = ty; rr < 32; rr += 8) {
         const long long j = j0 + rr;
         const int c = c0 + tx;
@@ -989,239 +813,39 @@ k_phi_finalize(const float* __restrict__ o, int splits, const float* __restrict_
     }
 }
 
-// ---- K3b fused: K tiles generated on the fly -----------------------------------------------------------------------------
-// O[rows x BN] = K[rows x n] * Vt[BN x n]^T with K_tj = exp(-d2_tj / h) NEVER written to HBM: eight SIMT warps (the four epilogue
-// warps of tc_gemm.cuh's layout plus four more) produce the A operand.  Per 32-column K block they read the 128 x 32 tile of d2
-// (coalesced 128-byte rows), evaluate the exponentials (MUFU.EX2), split them into tf32 hi / lo and store both tiles
-// straight into the 128-byte-swizzled K-major shared-memory layout the UMMA descriptor expects (16-byte chunk c of row r
-// at chunk position c ^ (r & 7)), fence the generic-proxy writes towards the async proxy and arrive on the stage's full
-// barrier next to the TMA transaction of the B tiles (Vt hi / lo).  Row sums of K ride along in registers.  Used when
-// [G | X] fits one N tile (2 dp <= 128, i.e. D <= 64): with more N tiles every one of them would regenerate K.
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ float ex2_fast(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 
-// Two CTAs per SM (2 smem stages of 48 / 64 KB, 168 registers): the producers wait on d2 loads, a second CTA fills the gaps.
-template <int BN>
-struct FusedCfg {
-    static constexpr int kStages = 2;
-    static constexpr int kTileA = kBM * kBK * 4;
-    static constexpr int kTileB = BN * kBK * 4;
-    static constexpr int kStageBytes = 2 * kTileA + 2 * kTileB;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
-    static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-};
-constexpr int kFusedCtasPerSm = 2, kFusedMaxSplits = kFusedMaxSplitsHost;
-constexpr int kFusedProducers = 8;                       // producer warps (warps 2..9; warps 2..5 are also the epilogue warps)
-constexpr int kFusedThreads = 32 * (2 + kFusedProducers);
-static int fused_splits(long long n_rows, long long n4) {
-    const long long tiles = (n_rows + kBM - 1) / kBM, num_kb = (n4 + kBK - 1) / kBK;
-    long long sp = (148 * kFusedCtasPerSm) / tiles;
-    if (sp > kFusedMaxSplits) sp = kFusedMaxSplits;
-    if (sp > num_kb) sp = num_kb;
-    return (int)(sp < 1 ? 1 : sp);
+}  // namespace tc
+}  // namespace ocbnn
+#include "svgd_flash.cuh"
+namespace ocbnn {
+namespace tc {
+
+// pairs sampled for the bracket of the median select: 32768 up to n = 4096, then proportional to the pair count (the
+// bracket holds 5.6 sigma of the sample-rank error = 2.8 / sqrt(samples) of all pairs on each side, and every pair inside it
+// is re-evaluated exactly), capped at 2^20
+static int sel_samples(long long n) {
+    long long s = n * n / 512;
+    if (s < kSelSamplesHost) s = kSelSamplesHost;
+    if (s > kSelSamplesMaxHost) s = kSelSamplesMaxHost;
+    return (int)(s / 1024 * 1024);
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kFusedThreads, 2)
-k_phi_fused(const float* __restrict__ d2, const float* __restrict__ hptr, long long n, long long n4, long long n_rows,
-            const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, float* __restrict__ o, long long ldo,
-            long long split_stride, float* __restrict__ rs_part, int num_kb, int kb_per_split) {
-    using Cfg = FusedCfg<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t bars = base + Cfg::kStages * Cfg::kStageBytes;          // full[stages], empty[stages], tmem_full, tmem_slot
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 1));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kBM;
-    const int kb_begin = blockIdx.z * kb_per_split;
-    const int kb_end = min(num_kb, kb_begin + kb_per_split);
-    const int nkb = kb_end - kb_begin;
+static DistSrc dist_src(const TcWs& w) { return DistSrc{w.d2, w.xc, w.n4, w.row_begin, (int)w.dp}; }
 
-    auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (Cfg::kStages + s); };
-    const uint32_t tmem_full_bar = bars + 8u * (2 * Cfg::kStages);
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < Cfg::kStages; ++s) {
-            mbar_init(full_bar(s), 1 + kFusedProducers);          // the TMA thread (B tiles) + one arrival per producer warp (A tiles)
-            mbar_init(empty_bar(s), 1);
-        }
-        mbar_init(tmem_full_bar, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_d = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % Cfg::kStages;
-                const uint32_t ph = (i / Cfg::kStages) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1);
-                const uint32_t st = base + s * Cfg::kStageBytes;
-                mbar_expect_tx(full_bar(s), 2 * Cfg::kTileB);
-                const int kx = (kb_begin + i) * kBK;
-                tma_load_2d(st + 2 * Cfg::kTileA, &tm_b_hi, full_bar(s), kx, 0);
-                tma_load_2d(st + 2 * Cfg::kTileA + Cfg::kTileB, &tm_b_lo, full_bar(s), kx, 0);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(kBM, BN);
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % Cfg::kStages;
-                const uint32_t ph = (i / Cfg::kStages) & 1;
-                mbar_wait(full_bar(s), ph);
-                tc_fence_after();
-                const uint32_t st = base + s * Cfg::kStageBytes;
-                const uint64_t a_hi = make_kmajor_sw128_desc(st), a_lo = make_kmajor_sw128_desc(st + Cfg::kTileA);
-                const uint64_t b_hi = make_kmajor_sw128_desc(st + 2 * Cfg::kTileA), b_lo = make_kmajor_sw128_desc(st + 2 * Cfg::kTileA + Cfg::kTileB);
-#pragma unroll
-                for (int k = 0; k < kBK / kUmmaK; ++k) {
-                    const uint64_t adv = (uint64_t)((k * kUmmaK * 4) >> 4);
-                    umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, (i | k) != 0);
-                    umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
-                    umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, 1);
-                }
-                umma_commit(empty_bar(s));
-            }
-            umma_commit(tmem_full_bar);
-        }
-    } else {
-        // ---- A producers: 8 warps, warp wp owns rows [16 wp, 16 wp + 16) of the tile; per pass 4 rows x 8 chunks of 16 bytes ----
-        constexpr int NP = 128 / kFusedProducers / 4;           // passes per warp and K block
-        const int wp = warp - 2, rr = lane >> 3, c = lane & 7;
-        const float sc = -1.4426950408889634f / __ldg(hptr);
-        float rs[NP];
-#pragma unroll
-        for (int ps = 0; ps < NP; ++ps) rs[ps] = 0.f;
-        // the d2 tile of K block i + 1 is in flight (registers) while block i is evaluated: the loads do not touch the stage,
-        // so they are issued ahead of the empty-barrier wait and hide the L2/HBM latency behind a whole block of work
-        auto load_tile = [&](float4 (&dst)[NP], int i) {
-            const long long jj = (long long)(kb_begin + i) * kBK + 4 * c;
-#pragma unroll
-            for (int ps = 0; ps < NP; ++ps) {
-                const long long t = m0 + 4 * NP * wp + 4 * ps + rr;
-                dst[ps] = (i < nkb && t < n_rows && jj < n4) ? __ldg(reinterpret_cast<const float4*>(d2 + t * n4 + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-        float4 v[NP], nx[NP];
-        load_tile(v, 0);
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % Cfg::kStages;
-            const uint32_t ph = (i / Cfg::kStages) & 1;
-            const long long j = (long long)(kb_begin + i) * kBK + 4 * c;
-            load_tile(nx, i + 1);
-            mbar_wait(empty_bar(s), ph ^ 1);
-            uint8_t* stp = gen_base + s * Cfg::kStageBytes;
-#pragma unroll
-            for (int ps = 0; ps < NP; ++ps) {
-                const int r = 4 * NP * wp + 4 * ps + rr;
-                const bool row_ok = m0 + r < n_rows;
-                float k[4] = {ex2_fast(v[ps].x * sc), ex2_fast(v[ps].y * sc), ex2_fast(v[ps].z * sc), ex2_fast(v[ps].w * sc)};
-                float hi[4], lo[4], sum = 0.f;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (!row_ok || j + e >= n) k[e] = 0.f;
-                    hi[e] = __uint_as_float(__float_as_uint(k[e]) & 0xFFFFE000u);
-                    lo[e] = k[e] - hi[e];
-                    sum += k[e];
-                }
-                const int off = r * 128 + ((c ^ (r & 7)) << 4);
-                *reinterpret_cast<float4*>(stp + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(stp + Cfg::kTileA + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-                rs[ps] += sum;
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(s));
-#pragma unroll
-            for (int ps = 0; ps < NP; ++ps) v[ps] = nx[ps];
-        }
-        if (c == 0) {
-#pragma unroll
-            for (int ps = 0; ps < NP; ++ps) {
-                const long long t = m0 + 4 * NP * wp + 4 * ps + rr;
-                if (t < n_rows) rs_part[(long long)blockIdx.z * n_rows + t] = rs[ps];
-            }
-        }
-        if (warp >= 6) goto done;                               // warps 6..9 only produce
-        // ---- epilogue: TMEM lane quarter = warp % 4 ----
-        const int q = warp & 3;
-        if (nkb > 0) {
-            mbar_wait(tmem_full_bar, 0);
-            tc_fence_after();
-        }
-        const long long row = m0 + q * 32 + lane;
-#pragma unroll 1
-        for (int cc = 0; cc < BN; cc += 32) {
-            float acc[32];
-            if (nkb > 0) {
-                tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, acc);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-            }
-            if (row < n_rows) {
-                float* dst = o + (long long)blockIdx.z * split_stride + row * ldo + cc;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
-            }
-        }
-    }
-done:
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_d, Cfg::kTmemCols);
-}
-
-// centre + split X, squared distances of rows [row_begin, row_begin + n_rows) into the workspace
-// hist0: when non-NULL (and the distances are formed by the direct kernel) the pass-0 select histogram is fused into the pass
-// sel_mode > 0 (single rank, all rows, D <= 64): the bracket is sampled from X and k_d2_sym forms the distances AND does the
-// median select's counting pass; *sel_done tells the caller that only gather + final are left.
-static int tc_prepare(const TcWs& w, const float* x, unsigned* hist0, bool* hist0_done, cudaStream_t st, int sel_mode = 0, bool* sel_done = nullptr) {
-    if (hist0_done) *hist0_done = false;
-    if (sel_done) *sel_done = false;
+// centre + split X (every rank holds all particles); D > 64: also the squared distances of rows [row_begin, row_begin + n_rows)
+// by the Gram GEMM on the tensor cores.  D <= 64: nothing else - the select and phi recompute their tiles (svgd_flash.cuh).
+static int tc_prepare(const TcWs& w, const float* x, cudaStream_t st) {
     k_colmean<<<(unsigned)w.dp, 256, 0, st>>>(x, w.n, (int)w.d, (int)w.dp, w.mean);
     OCBNN_LAUNCH_CHECK();
     k_center_split<<<(unsigned)((w.n * 32 + 255) / 256), 256, 0, st>>>(x, w.mean, w.n, (int)w.d, (int)w.dp, w.xc, w.xc_hi, w.xc_lo, w.r, w.s);
     OCBNN_LAUNCH_CHECK();
-    static const bool gram_small = [] { const char* e = getenv("OCBNN_SVGD_GRAM"); return e && e[0] == 't'; }();   // experiment: tensor Gram for small D too
-    if (w.dp <= 64 && !gram_small && sel_mode > 0 && w.n_rows == w.n && w.row_begin == 0) {
-        SelHdr* hdr = reinterpret_cast<SelHdr*>(w.sel);
-        if (w.dp == 32) k_sel_sample_x<32><<<kSelSamples / 256, 256, 0, st>>>(w.xc, w.s, w.n, (int)w.d, w.samples);
-        else k_sel_sample_x<64><<<kSelSamples / 256, 256, 0, st>>>(w.xc, w.s, w.n, (int)w.d, w.samples);
-        OCBNN_LAUNCH_CHECK();
-        k_sel_bracket<<<1, 1024, 0, st>>>(w.samples, hdr, w.ghist, sel_mode == 2 ? 1 : 0);
-        OCBNN_LAUNCH_CHECK();
-        dim3 grid((unsigned)((w.n + 63) / 64), (unsigned)((w.n + 63) / 64));
-        if (w.dp == 32) k_d2_sym<32><<<grid, 256, 0, st>>>(w.xc, w.s, w.n, w.n4, (int)w.d, w.d2, hdr, w.cand, w.cand_cap, w.ghist);
-        else k_d2_sym<64><<<grid, 256, 0, st>>>(w.xc, w.s, w.n, w.n4, (int)w.d, w.d2, hdr, w.cand, w.cand_cap, w.ghist);
-        OCBNN_LAUNCH_CHECK();
-        if (sel_done) *sel_done = true;
-        return OCBNN_OK;
-    }
-    if (w.dp <= 64 && !gram_small) {
-        dim3 grid((unsigned)((w.n4 + 63) / 64), (unsigned)((w.n_rows + 63) / 64));
-        if (w.dp == 32) k_d2_direct<32><<<grid, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.s, w.n, w.n4, (int)w.d, w.row_begin, w.n_rows, w.d2, hist0);
-        else k_d2_direct<64><<<grid, 256, 0, st>>>(w.xc_hi, w.xc_lo, w.s, w.n, w.n4, (int)w.d, w.row_begin, w.n_rows, w.d2, hist0);
-        OCBNN_LAUNCH_CHECK();
-        if (hist0_done) *hist0_done = hist0 != nullptr;
-        return OCBNN_OK;
-    }
-    // Gram on tensor cores: A = rows of this rank, B = all rows
+    if (w.flash || w.n_rows == 0) return OCBNN_OK;
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     int rc;
     if ((rc = make_tmap(&ta_hi, w.xc_hi + w.row_begin * w.dp, w.n_rows, w.dp, kBM))) return rc;
@@ -1232,40 +856,89 @@ static int tc_prepare(const TcWs& w, const float* x, unsigned* hist0, bool* hist
     return launch_gemm<128>(ta_hi, ta_lo, tb_hi, tb_lo, epi, w.n_rows, w.n, w.dp, 1, st);
 }
 
-static int tc_phi(const TcWs& w, const float* g, const float* h, float* phi, cudaStream_t st) {
-    const bool fused_ok = fused_enabled();
-    dim3 gv((unsigned)((w.n4 + 31) / 32), (unsigned)(2 * w.dp / 32));
-    k_vt_split<<<gv, 256, 0, st>>>(g, w.xc_hi, w.xc_lo, w.n, w.n4, (int)w.d, (int)w.dp, w.vt_hi, w.vt_lo);
+// bracket of the median select, sampled from the centred particles (identical on every rank: no communication)
+static int sel_bracket(const TcWs& w, int mode, cudaStream_t st) {
+    const int ns = sel_samples(w.n);
+    SelHdr* hdr = reinterpret_cast<SelHdr*>(w.sel);
+    if (w.dp == 32) k_sel_sample_x<32><<<ns / 256, 256, 0, st>>>(w.xc, w.s, w.n, (int)w.d, w.samples, ns);
+    else if (w.dp == 64) k_sel_sample_x<64><<<ns / 256, 256, 0, st>>>(w.xc, w.s, w.n, (int)w.d, w.samples, ns);
+    else k_sel_sample_wide<<<ns / 8, 256, 0, st>>>(w.xc, w.s, w.n, (int)w.d, (int)w.dp, w.samples, ns);
     OCBNN_LAUNCH_CHECK();
-    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-    int rc;
-    if ((rc = make_tmap(&tb_hi, w.vt_hi, 2 * w.dp, w.n4, w.bn))) return rc;
-    if ((rc = make_tmap(&tb_lo, w.vt_lo, 2 * w.dp, w.n4, w.bn))) return rc;
-    if (fused_ok && 2 * w.dp <= w.bn) {
-        // one N tile: K tiles are generated inside the GEMM (k_phi_fused); K splits sized to ONE wave of CTAs
-        const long long tiles = (w.n_rows + kBM - 1) / kBM;
-        const int num_kb = (int)((w.n4 + kBK - 1) / kBK);
-        const int splits = fused_splits(w.n_rows, w.n4);    // o[] is sized for it (carve)
-        const int per = (num_kb + splits - 1) / splits;
-        float* rs_part = w.k_hi;                            // the K matrices are not materialised on this path: reuse their space
-        dim3 grid((unsigned)tiles, 1, (unsigned)splits);
-        if (w.bn == 64) {
-            auto kern = k_phi_fused<64>;
-            OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<64>::kSmemBytes));
-            kern<<<grid, kFusedThreads, FusedCfg<64>::kSmemBytes, st>>>(w.d2, h, w.n, w.n4, w.n_rows, tb_hi, tb_lo, w.o, 2 * w.dp, w.n_rows * 2 * w.dp, rs_part,
-                                                                  num_kb, per);
-        } else {
-            auto kern = k_phi_fused<128>;
-            OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg<128>::kSmemBytes));
-            kern<<<grid, kFusedThreads, FusedCfg<128>::kSmemBytes, st>>>(w.d2, h, w.n, w.n4, w.n_rows, tb_hi, tb_lo, w.o, 2 * w.dp, w.n_rows * 2 * w.dp, rs_part,
-                                                                   num_kb, per);
+    k_sel_bracket<<<1, 1024, 0, st>>>(w.samples, ns, hdr, w.ghist, mode == 1 ? 0 : 1);      // modes 0 / 2: sabotaged -> full select
+    OCBNN_LAUNCH_CHECK();
+    return OCBNN_OK;
+}
+
+// counting pass of this rank's share of the pairs.  Flash path: the 128 x 128 tiles on or above the diagonal, dealt out
+// cyclically (tile index % world == rank); D > 64: the rows [row_begin, row_begin + n_rows) of the materialised distances.
+static int sel_count(const TcWs& w, int rank, int world, cudaStream_t st) {
+    SelHdr* hdr = reinterpret_cast<SelHdr*>(w.sel);
+    if (!w.flash) {
+        if (w.n_rows > 0) {
+            k_sel_count<<<(unsigned)(w.n_rows < 148 * 8 ? w.n_rows : 148 * 8), 256, 0, st>>>(w.d2, w.s, w.n, w.n4, (int)w.d, w.row_begin, w.n_rows, hdr,
+                                                                                         w.cand, w.cand_cap, w.ghist);
+            OCBNN_LAUNCH_CHECK();
         }
-        OCBNN_LAUNCH_CHECK();
-        k_phi_finalize<<<grid_for_ll(w.n_rows * w.d), 256, 0, st>>>(w.o, splits, rs_part, splits, w.xc_hi, w.xc_lo, h, w.n, (int)w.d, (int)w.dp,
-                                                                  w.row_begin, w.n_rows, phi);
+        return OCBNN_OK;
+    }
+    const int T = (int)((w.n + 127) / 128);
+    const long long tiles = (long long)T * (T + 1) / 2;
+    const long long mine = tiles > rank ? (tiles - rank + world - 1) / world : 0;
+    if (mine == 0) return OCBNN_OK;
+    CUtensorMap tm_hi, tm_lo;
+    int rc;
+    if ((rc = make_tmap(&tm_hi, w.xc_hi, w.n, w.dp, 128))) return rc;
+    if ((rc = make_tmap(&tm_lo, w.xc_lo, w.n, w.dp, 128))) return rc;
+    if (w.dp == 32) {
+        auto kern = k_count_tc<32>;
+        OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CountCfg<32>::kSmemBytes));
+        kern<<<(unsigned)mine, kCntThreads, CountCfg<32>::kSmemBytes, st>>>(tm_hi, tm_lo, w.xc, w.r, w.s, w.n, (int)w.d, T, rank, world, hdr, w.cand,
+                                                                          w.cand_cap, w.ghist);
+    } else {
+        auto kern = k_count_tc<64>;
+        OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CountCfg<64>::kSmemBytes));
+        kern<<<(unsigned)mine, kCntThreads, CountCfg<64>::kSmemBytes, st>>>(tm_hi, tm_lo, w.xc, w.r, w.s, w.n, (int)w.d, T, rank, world, hdr, w.cand,
+                                                                          w.cand_cap, w.ghist);
+    }
+    OCBNN_LAUNCH_CHECK();
+    return OCBNN_OK;
+}
+
+template <int DP, int TILES>
+static int launch_flash(const TcWs& w, const float* h, cudaStream_t st) {
+    using Cfg = FlashCfg<DP, TILES>;
+    CUtensorMap xj_hi, xj_lo, vt_hi, vt_lo;
+    int rc;
+    if ((rc = make_tmap(&xj_hi, w.xc_hi, w.n, w.dp, kFlashBJ))) return rc;
+    if ((rc = make_tmap(&xj_lo, w.xc_lo, w.n, w.dp, kFlashBJ))) return rc;
+    if ((rc = make_tmap(&vt_hi, w.vt_hi, 2 * w.dp, w.n4, Cfg::NV))) return rc;
+    if ((rc = make_tmap(&vt_lo, w.vt_lo, 2 * w.dp, w.n4, Cfg::NV))) return rc;
+    auto kern = k_phi_flash<DP, TILES>;
+    OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    dim3 grid((unsigned)((w.n_rows + 128 * TILES - 1) / (128 * TILES)), (unsigned)w.fl_splits);
+    kern<<<grid, kFlashThreads, Cfg::kSmemBytes, st>>>(xj_hi, xj_lo, vt_hi, vt_lo, w.xc_hi, w.xc_lo, w.r, w.ncr, h, w.n, w.row_begin, w.n_rows, w.o,
+                                                     w.k_hi, w.fl_nj, w.fl_per);
+    OCBNN_LAUNCH_CHECK();
+    return OCBNN_OK;
+}
+
+static int tc_phi(const TcWs& w, const float* g, const float* h, float* phi, cudaStream_t st) {
+    dim3 gv((unsigned)((w.n4 + 31) / 32), (unsigned)(2 * w.dp / 32));
+    k_vt_split<<<gv, 256, 0, st>>>(g, w.xc_hi, w.xc_lo, w.n, w.n4, (int)w.d, (int)w.dp, w.vt_hi, w.vt_lo, w.r, h, w.ncr, (long long)w.fl_nj * 64);
+    OCBNN_LAUNCH_CHECK();
+    int rc;
+    if (w.flash) {
+        if (w.dp == 32) rc = w.fl_tiles == 2 ? launch_flash<32, 2>(w, h, st) : launch_flash<32, 1>(w, h, st);
+        else rc = launch_flash<64, 1>(w, h, st);
+        if (rc) return rc;
+        k_phi_finalize<<<grid_for_ll(w.n_rows * w.d), 256, 0, st>>>(w.o, w.fl_splits, w.k_hi, w.fl_splits * (w.fl_tiles == 2 ? 1 : 2), w.xc_hi, w.xc_lo, h,
+                                                                  w.n, (int)w.d, (int)w.dp, w.row_begin, w.n_rows, phi);
         OCBNN_LAUNCH_CHECK();
         return OCBNN_OK;
     }
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    if ((rc = make_tmap(&tb_hi, w.vt_hi, 2 * w.dp, w.n4, w.bn))) return rc;
+    if ((rc = make_tmap(&tb_lo, w.vt_lo, 2 * w.dp, w.n4, w.bn))) return rc;
     k_kmat_split<<<(unsigned)(w.n_rows < 148 * 8 ? w.n_rows : 148 * 8), 256, 0, st>>>(w.d2, h, w.n, w.n4, w.n_rows, w.k_hi, w.k_lo, w.rowsum);
     OCBNN_LAUNCH_CHECK();
     if ((rc = make_tmap(&ta_hi, w.k_hi, w.n_rows, w.n4, kBM))) return rc;
@@ -1282,103 +955,90 @@ static int tc_phi(const TcWs& w, const float* g, const float* h, float* phi, cud
 
 long long tc_workspace_bytes(long long n, long long d, long long n_rows) { return carve(nullptr, n, d, 0, n_rows).bytes + 512; }
 
-int tc_svgd_prepare(const float* x, long long n, long long d, long long row_begin, long long n_rows, void* ws, long long ws_bytes, unsigned* hist0,
-                    bool* hist0_done, cudaStream_t st) {
+int tc_svgd_prepare(const float* x, long long n, long long d, long long row_begin, long long n_rows, void* ws, long long ws_bytes, cudaStream_t st) {
     OCBNN_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(n, d, n_rows), OCBNN_EINVAL, "SVGD tensor path: workspace too small");
-    return tc_prepare(carve(ws, n, d, row_begin, n_rows), x, hist0, hist0_done, st);
+    return tc_prepare(carve(ws, n, d, row_begin, n_rows), x, st);
 }
+// legacy 3-pass radix select over the materialised distance rows (D > 64 only)
 int tc_svgd_hist(long long n, long long d, long long row_begin, long long n_rows, int pass, unsigned* hist, const unsigned long long* state, void* ws,
                  cudaStream_t st) {
     TcWs w = carve(ws, n, d, row_begin, n_rows);
+    OCBNN_REQUIRE(!w.flash, OCBNN_EUNSUPPORTED, "tc_svgd_hist: D <= 64 keeps no distance matrix");
     k_hist_d2<<<(unsigned)(n_rows < 148 * 8 ? n_rows : 148 * 8), 256, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, row_begin, n_rows, pass, hist, state);
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }
-// exact lower median of the perturbed pair distances of the prepared workspace (all rows on this rank) -> h = med^2 / ln n.
-// mode 1: normal ; mode 2: sabotage the bracket (exercises the in-kernel fallback; tests only).  dbg: optional 4 x u64
-// (bracket hit, candidates, below, zeros).
-int tc_svgd_select_fast(long long n, long long d, void* ws, float* out_h, int mode, unsigned long long* dbg, cudaStream_t st) {
+bool tc_is_flash(long long n, long long d) { return carve(nullptr, n, d, 0, n).flash; }
+
+// Exact lower median of the perturbed pair distances -> h = med^2 / ln n, all pairs on this rank (after tc_svgd_prepare with
+// all rows).  mode 1: bracket select; 0 / 2: the full radix select (one CTA, exact distances recomputed on the flash path) -
+// the fallback the bracket select takes in-kernel when the bracket misses.  dbg: optional 4 x u64 (bracket hit, candidates,
+// below, zeros).
+int tc_svgd_select_local(long long n, long long d, void* ws, float* out_h, int mode, unsigned long long* dbg, cudaStream_t st) {
     TcWs w = carve(ws, n, d, 0, n);
     SelHdr* hdr = reinterpret_cast<SelHdr*>(w.sel);
-    k_sel_sample<<<kSelSamples / 256, 256, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, w.samples);
-    OCBNN_LAUNCH_CHECK();
-    k_sel_bracket<<<1, 1024, 0, st>>>(w.samples, hdr, w.ghist, mode == 2 ? 1 : 0);
-    OCBNN_LAUNCH_CHECK();
-    k_sel_count<<<(unsigned)(n < 148 * 8 ? n : 148 * 8), 256, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, 0, n, hdr, w.cand, w.cand_cap, w.ghist);
-    OCBNN_LAUNCH_CHECK();
-    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap, 0, w.d2, w.s, w.n4, (int)d, out_h, dbg);      // gather + final
+    int rc;
+    if ((rc = sel_bracket(w, mode, st))) return rc;
+    if (mode == 1 && (rc = sel_count(w, 0, 1, st))) return rc;
+    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap, 0, dist_src(w), w.s, (int)d, out_h, dbg);      // gather + final
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }
-// prepare (centre, split, distances) + exact median in one go; for D <= 64 the counting pass rides on the distance kernel
-int tc_svgd_prepare_select(const float* x, long long n, long long d, void* ws, long long ws_bytes, float* out_h, int mode, unsigned long long* dbg,
-                           cudaStream_t st) {
-    OCBNN_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(n, d, n), OCBNN_EINVAL, "SVGD tensor path: workspace too small");
-    TcWs w = carve(ws, n, d, 0, n);
-    bool sel_done = false;
-    int rc = tc_prepare(w, x, nullptr, nullptr, st, mode, &sel_done);
-    if (rc) return rc;
-    if (!sel_done) return tc_svgd_select_fast(n, d, ws, out_h, mode, dbg, st);
-    SelHdr* hdr = reinterpret_cast<SelHdr*>(w.sel);
-    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap, 0, w.d2, w.s, w.n4, (int)d, out_h, dbg);      // gather + final
-    OCBNN_LAUNCH_CHECK();
-    return OCBNN_OK;
-}
-// multi-rank bracket select, stage 1 (after tc_svgd_prepare): bracket from X, counting pass over this rank's rows, counters packed
-// into the reduce buffer (*red64_out, 4 + 2048 u64: the caller all-reduces it as int64 sums)
-int tc_svgd_sel_count(long long n, long long d, long long row_begin, long long n_rows, void* ws, unsigned long long** red64_out, int mode, cudaStream_t st) {
+// ---- the same select across ranks --------------------------------------------------------------------------------------
+// stage 1: bracket from X, counting pass over this rank's share of the pairs, counters packed into the reduce buffer
+// (*red64_out, 4 + 2048 u64: the caller all-reduces it as int64 sums)
+int tc_svgd_sel_stage1(long long n, long long d, long long row_begin, long long n_rows, int rank, int world, void* ws, int mode,
+                       unsigned long long** red64_out, cudaStream_t st) {
     TcWs w = carve(ws, n, d, row_begin, n_rows);
     SelHdr* hdr = reinterpret_cast<SelHdr*>(w.sel);
     if (red64_out) *red64_out = w.red64;
-    if (w.dp == 32) k_sel_sample_x<32><<<kSelSamples / 256, 256, 0, st>>>(w.xc, w.s, w.n, (int)w.d, w.samples);
-    else if (w.dp == 64) k_sel_sample_x<64><<<kSelSamples / 256, 256, 0, st>>>(w.xc, w.s, w.n, (int)w.d, w.samples);
-    else k_sel_sample_wide<<<kSelSamples / 8, 256, 0, st>>>(w.xc, w.s, w.n, (int)w.d, (int)w.dp, w.samples);
-    OCBNN_LAUNCH_CHECK();
-    k_sel_bracket<<<1, 1024, 0, st>>>(w.samples, hdr, w.ghist, mode == 2 ? 1 : 0);
-    OCBNN_LAUNCH_CHECK();
-    if (n_rows > 0) {
-        k_sel_count<<<(unsigned)(n_rows < 148 * 8 ? n_rows : 148 * 8), 256, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, row_begin, n_rows, hdr, w.cand, w.cand_cap,
-                                                                                   w.ghist);
-        OCBNN_LAUNCH_CHECK();
-    }
+    int rc;
+    if ((rc = sel_bracket(w, mode, st))) return rc;
+    if (mode == 1 && (rc = sel_count(w, rank, world, st))) return rc;
     k_sel_pack<<<8, 256, 0, st>>>(hdr, w.ghist, w.red64);
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }
 // stage 2 (after the all-reduce of the reduce buffer): global counters in, this rank's candidates of the hit bin gathered
-int tc_svgd_sel_gather(long long n, long long d, long long row_begin, long long n_rows, void* ws, cudaStream_t st) {
+int tc_svgd_sel_stage2(long long n, long long d, long long row_begin, long long n_rows, void* ws, cudaStream_t st) {
     TcWs w = carve(ws, n, d, row_begin, n_rows);
     SelHdr* hdr = reinterpret_cast<SelHdr*>(w.sel);
     k_sel_unpack<<<8, 256, 0, st>>>(hdr, w.ghist, w.red64);
     OCBNN_LAUNCH_CHECK();
-    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap, 1, w.d2, w.s, w.n4, (int)d, nullptr, nullptr);
+    k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap, 1, dist_src(w), w.s, (int)d, nullptr, nullptr);
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }
-// stage 3, per radix pass: local histogram (the caller all-reduces hist[pass]) ...
-int tc_svgd_sel_hist(long long n, long long d, long long row_begin, long long n_rows, int pass, unsigned* hist, const unsigned long long* state, void* ws,
+__global__ void k_zero_words(unsigned* p, int nwords) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nwords) p[i] = 0u;
+}
+// stage 3, per radix pass: local histogram over this rank's short list - or, if the bracket missed, over its share of ALL pairs
+// (flash: rows rank, rank + world, ...; D > 64: its distance rows).  *hist_out = the 2048 u32 the caller all-reduces.
+int tc_svgd_sel_hist(long long n, long long d, long long row_begin, long long n_rows, int rank, int world, int pass, void* ws, unsigned** hist_out,
                      cudaStream_t st) {
     TcWs w = carve(ws, n, d, row_begin, n_rows);
-    k_hist_sel<<<148, 256, 0, st>>>(w.d2, w.s, n, w.n4, (int)d, row_begin, n_rows, reinterpret_cast<const SelHdr*>(w.sel), w.list2, w.cand_cap, pass, hist,
-                                    state);
+    if (pass == 0) {
+        k_zero_words<<<(3 * 2048 + 255) / 256, 256, 0, st>>>(w.hist, 3 * 2048);
+        OCBNN_LAUNCH_CHECK();
+    }
+    const long long rs = w.flash ? rank : row_begin, rstep = w.flash ? world : 1;
+    const long long rows = w.flash ? (n > rank ? (n - rank + world - 1) / world : 0) : n_rows;
+    k_hist_sel<<<148, 256, 0, st>>>(dist_src(w), w.s, n, (int)d, rs, rstep, rows, reinterpret_cast<const SelHdr*>(w.sel), w.list2, w.cand_cap, pass, w.hist,
+                                    w.state);
     OCBNN_LAUNCH_CHECK();
+    if (hist_out) *hist_out = w.hist + pass * 2048;
     return OCBNN_OK;
 }
 // ... and the rank bookkeeping / final h
-int tc_svgd_sel_update(long long n, long long d, long long row_begin, long long n_rows, int pass, const unsigned* hist, unsigned long long* state, void* ws,
-                       float* out_h, cudaStream_t st) {
+int tc_svgd_sel_update(long long n, long long d, long long row_begin, long long n_rows, int pass, void* ws, float* out_h, cudaStream_t st) {
     TcWs w = carve(ws, n, d, row_begin, n_rows);
-    k_select_update_sel<<<1, 1024, 0, st>>>(pass, hist, state, n, reinterpret_cast<const SelHdr*>(w.sel), out_h);
+    k_select_update_sel<<<1, 1024, 0, st>>>(pass, w.hist, w.state, n, reinterpret_cast<const SelHdr*>(w.sel), out_h);
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }
 int tc_svgd_phi(const float* g, const float* h, long long n, long long d, long long row_begin, long long n_rows, float* phi, void* ws, cudaStream_t st) {
     return tc_phi(carve(ws, n, d, row_begin, n_rows), g, h, phi, st);
-}
-void tc_ws_hist(void* ws, long long n, long long d, long long n_rows, unsigned** hist, unsigned long long** state) {
-    TcWs w = carve(ws, n, d, 0, n_rows);
-    *hist = w.hist;
-    *state = w.state;
 }
 
 }  // namespace tc

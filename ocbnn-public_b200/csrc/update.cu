@@ -2,7 +2,8 @@
 //   w_j = mu + eps_j * softplus(rho)                                                    (inference.py:132-140)
 //   dELBO/dmu = mean_j g_j ; dELBO/drho = sigmoid(rho) (mean_j g_j*eps_j + 1/sigma)      (autograd of :142-153)
 //   ELBO = mean_j [ log post(w_j) - sum_i log N(w_ji; mu_i, sigma_i) ]
-#include "common.cuh"
+#include "comm.h"
+#include "svgd_tc.h"
 
 namespace ocbnn {
 
@@ -96,6 +97,44 @@ extern "C" OCBNN_API int ocbnn_bbb_reduce(const float* q_params, const float* ep
     k_bbb_reduce_cols<<<(unsigned)d, 256, 0, st>>>(q_params, eps, grad, k, d, inv, add_entropy, out_grad_q, colstat);
     OCBNN_LAUNCH_CHECK();
     k_bbb_elbo<<<1, 256, 0, st>>>(lp, k, colstat, d, inv, out_elbo);
+    OCBNN_LAUNCH_CHECK();
+    return OCBNN_OK;
+}
+
+// ---- one BBB epoch in one call ---------------------------------------------------------------------------------------------
+// workspace: W[k x D] | G[k x D] | lp[k] | colstat[D] | red[2 D + 1] (gradient and ELBO, summed over the ranks in ONE all-reduce)
+static long long up256(long long floats) { return (floats * 4 + 255) / 256 * 256; }
+extern "C" OCBNN_API int64_t ocbnn_bbb_workspace_bytes(int64_t k_local, int64_t d) {
+    return 2 * up256(k_local * d) + up256(k_local) + up256(d) + up256(2 * d + 1) + 256;
+}
+
+__global__ void k_copy_scalar(const float* __restrict__ src, float* __restrict__ dst) { *dst = *src; }
+
+extern "C" OCBNN_API int ocbnn_bbb_step(ocbnn_problem* ph, float* q_params, float* acc, const float* eps, int64_t k_local, int64_t k_total, float lr,
+                                        int32_t batch_offset, int32_t batch_stride, int32_t with_data, float* out_elbo, void* workspace,
+                                        int64_t workspace_bytes, ocbnn_comm* comm_h, void* stream) {
+    OCBNN_REQUIRE(ph && q_params && acc && eps && out_elbo && k_local >= 1 && k_total >= k_local, OCBNN_EINVAL, "ocbnn_bbb_step: bad argument");
+    OCBNN_REQUIRE(batch_stride <= 1 || (batch_offset >= 0 && batch_offset < batch_stride), OCBNN_EINVAL, "batch_offset must be in [0, stride)");
+    const Problem& p = *problem_of(ph);
+    const long long d = p.d;
+    OCBNN_REQUIRE(workspace && workspace_bytes >= ocbnn_bbb_workspace_bytes(k_local, d), OCBNN_EINVAL, "ocbnn_bbb_step: workspace too small");
+    Comm* comm = reinterpret_cast<Comm*>(comm_h);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = reinterpret_cast<char*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    float* w = reinterpret_cast<float*>(base);        base += up256(k_local * d);
+    float* g = reinterpret_cast<float*>(base);        base += up256(k_local * d);
+    float* lp = reinterpret_cast<float*>(base);       base += up256(k_local);
+    float* colstat = reinterpret_cast<float*>(base);  base += up256(d);
+    float* red = reinterpret_cast<float*>(base);
+    int rc;
+    if ((rc = ocbnn_bbb_sample(q_params, eps, k_local, d, w, stream))) return rc;
+    const EvalArgs a = eval_args(p, batch_offset, batch_stride, with_data);
+    if ((rc = logpost_any(p, a, w, k_local, lp, g, 0, st))) return rc;
+    // the entropy term of the gradient is added once: on rank 0
+    if ((rc = ocbnn_bbb_reduce(q_params, eps, lp, g, k_local, d, k_total, comm_rank(comm) == 0 ? 1 : 0, red, red + 2 * d, colstat, stream))) return rc;
+    if ((rc = comm_all_sum(comm, red, 2 * d + 1, kCommF32, st))) return rc;
+    if ((rc = adagrad_launch(q_params, acc, red, 2 * d, lr, -1.f, st))) return rc;              // loss = -ELBO
+    k_copy_scalar<<<1, 1, 0, st>>>(red + 2 * d, out_elbo);
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }

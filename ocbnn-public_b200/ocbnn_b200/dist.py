@@ -31,6 +31,38 @@ def shard(n, r=None, w=None):
     return lo, lo + base + (1 if r < rem else 0)
 
 
+def broadcast_(t, src=0):
+    """Rank `src`'s copy of `t` on every rank (replicated state must not depend on how the user seeded the ranks)."""
+    if active():
+        if not t.is_cuda and dist.get_backend() == "nccl":      # NCCL moves device memory only
+            d = t.cuda()
+            dist.broadcast(d, src=src)
+            t.copy_(d)
+        else:
+            dist.broadcast(t, src=src)
+    return t
+
+
+_COMM = None
+
+
+def comm():
+    """The library's own communicator (ocbnn_comm, NCCL inside libocbnn_b200.so) for the one-call SVGD / BBB steps; None on one
+    rank.  torch.distributed only carries the 128-byte id from rank 0 to the others."""
+    global _COMM
+    if not active():
+        return None
+    if _COMM is None or _COMM.world != world() or _COMM.rank != rank():
+        from . import engine as E
+
+        def exchange(ident):
+            box = [ident]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        _COMM = E.Comm(rank(), world(), exchange)
+    return _COMM
+
+
 def all_sum_(t):
     if active():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)

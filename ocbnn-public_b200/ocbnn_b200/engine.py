@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libocbnn_b200.so")
 
-OCBNN_ABI_VERSION = 1
+OCBNN_ABI_VERSION = 2
 OCBNN_MAX_LAYERS = 8
 ACT_IDENTITY, ACT_RBF, ACT_RELU = 0, 1, 2
 HEAD_LIK_GAUSS, HEAD_NEG_EXP, HEAD_POS_GAUSS, HEAD_DIRICHLET, HEAD_LIK_SOFTMAX, HEAD_LIK_BERNOULLI = range(6)
@@ -76,22 +76,21 @@ _SIGS = {
                                     C.c_void_p]),
     "ocbnn_sgld_iterate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _fp, _ip, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
-    "ocbnn_svgd_hist_pass": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
-                                       C.c_void_p, C.c_void_p]),
-    "ocbnn_svgd_select_update": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ocbnn_svgd_bandwidth": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "ocbnn_svgd_select_mode": (C.c_int, [C.c_int32]),
-    "ocbnn_svgd_sel_count": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p]),
-    "ocbnn_svgd_sel_gather": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
-    "ocbnn_svgd_sel_hist": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "ocbnn_svgd_sel_update": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                        C.c_void_p]),
-    "ocbnn_svgd_prepare": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
-    "ocbnn_svgd_hist_pass_prepared": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
-                                                C.c_void_p]),
     "ocbnn_svgd_phi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                  C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "ocbnn_svgd_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64, C.c_int32]),
+    "ocbnn_svgd_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                  C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ocbnn_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "ocbnn_comm_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "ocbnn_comm_wrap": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "ocbnn_comm_destroy": (C.c_int, [C.c_void_p]),
+    "ocbnn_comm_shard": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ocbnn_bbb_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
+    "ocbnn_bbb_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ocbnn_gemm_tf32x3_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64]),
     "ocbnn_gemm_tf32x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "ocbnn_adagrad_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p]),
@@ -303,59 +302,61 @@ def svgd_select_mode(mode=-1):
     return int(lib().ocbnn_svgd_select_mode(int(mode)))
 
 
-def svgd_sel_count(n, d, row_begin, n_rows, workspace):
-    """Stage 1 of the bracket select across ranks.  Returns the reduce buffer as an int64 view INTO the workspace (all-reduce it
-    in place with SUM before svgd_sel_gather)."""
-    ws = workspace[SVGD_HDR_BYTES // 8:]
-    ptr, words = C.c_void_p(), C.c_int64()
-    check(lib().ocbnn_svgd_sel_count(int(n), int(d), int(row_begin), int(n_rows), _ptr(ws), C.byref(ptr), C.byref(words), _stream()))
-    off = (ptr.value - workspace.data_ptr()) // 8
-    return workspace[off:off + words.value]
-
-
-def svgd_sel_gather(n, d, row_begin, n_rows, workspace):
-    ws = workspace[SVGD_HDR_BYTES // 8:]
-    check(lib().ocbnn_svgd_sel_gather(int(n), int(d), int(row_begin), int(n_rows), _ptr(ws), _stream()))
-
-
-def svgd_sel_hist(n, d, row_begin, n_rows, pass_, hist, state, workspace):
-    ws = workspace[SVGD_HDR_BYTES // 8:]
-    check(lib().ocbnn_svgd_sel_hist(int(n), int(d), int(row_begin), int(n_rows), int(pass_), _ptr(hist), _ptr(state), _ptr(ws), _stream()))
-
-
-def svgd_sel_update(n, d, row_begin, n_rows, pass_, hist, state, workspace, out_h):
-    ws = workspace[SVGD_HDR_BYTES // 8:]
-    check(lib().ocbnn_svgd_sel_update(int(n), int(d), int(row_begin), int(n_rows), int(pass_), _ptr(hist), _ptr(state), _ptr(ws), _ptr(out_h),
-                                      _stream()))
-
-
-def svgd_prepare(X, row_begin, n_rows, workspace, use_tensor=1):
-    X = _f32(X, "X")
-    ws = workspace[SVGD_HDR_BYTES // 8:]
-    check(lib().ocbnn_svgd_prepare(_ptr(X), X.shape[0], X.shape[1], int(row_begin), int(n_rows), int(use_tensor), _ptr(ws), ws.numel() * 8,
-                                   _stream()))
-
-
-def svgd_hist_pass(X, row_start, row_step, n_rows, pass_, hist, state):
-    check(lib().ocbnn_svgd_hist_pass(_ptr(X), X.shape[0], X.shape[1], int(row_start), int(row_step), int(n_rows), int(pass_), _ptr(hist),
-                                     _ptr(state), _stream()))
-
-
-def svgd_hist_pass_prepared(n, d, row_begin, n_rows, pass_, hist, state, workspace):
-    ws = workspace[SVGD_HDR_BYTES // 8:]
-    check(lib().ocbnn_svgd_hist_pass_prepared(int(n), int(d), int(row_begin), int(n_rows), int(pass_), _ptr(hist), _ptr(state), _ptr(ws), _stream()))
-
-
-def svgd_select_update(pass_, hist, state, n, out_h):
-    check(lib().ocbnn_svgd_select_update(int(pass_), _ptr(hist), _ptr(state), int(n), _ptr(out_h), _stream()))
-
-
 def svgd_phi(X, G, h, row_begin, n_rows, workspace, use_tensor=0, out=None):
     X, G = _f32(X, "X"), _f32(G, "G")
     phi = out if out is not None else torch.empty(n_rows, X.shape[1], device=X.device)
     check(lib().ocbnn_svgd_phi(_ptr(X), _ptr(G), X.shape[0], X.shape[1], int(row_begin), int(n_rows), _ptr(h), _ptr(phi), int(use_tensor),
                                _ptr(workspace), workspace.numel() * 8 if workspace is not None else 0, _stream()))
     return phi
+
+
+def svgd_step(problem, X_all, G_all, acc, phi, h, row_begin, n_rows, lr, batch, with_data, use_tensor, workspace, comm=None):
+    """One SVGD iteration in one library call (K1 -> all-gather G -> K3a -> K3b -> K3c -> all-gather X), on the current stream.
+    X_all / G_all: (n, D) device buffers replicated on every rank; acc / phi: (n_rows, D) of the owned rows; comm: Comm or None."""
+    off, stride = batch
+    check(lib().ocbnn_svgd_step(problem._h, _ptr(X_all), _ptr(G_all), _ptr(acc), _ptr(phi), _ptr(h), X_all.shape[0], int(row_begin), int(n_rows),
+                                float(lr), int(off), int(stride), int(bool(with_data)), int(use_tensor), _ptr(workspace), workspace.numel() * 8,
+                                comm.handle if comm is not None else None, _stream()))
+
+
+def bbb_workspace(k_local, d, device):
+    nbytes = int(lib().ocbnn_bbb_workspace_bytes(int(k_local), int(d)))
+    return torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=device)
+
+
+def bbb_step(problem, q_params, acc, eps, k_total, lr, batch, with_data, out_elbo, workspace, comm=None):
+    """One BBB epoch in one library call (sample -> K1 -> closed-form ELBO gradient -> one all-reduce -> Adagrad)."""
+    off, stride = batch
+    check(lib().ocbnn_bbb_step(problem._h, _ptr(q_params), _ptr(acc), _ptr(_f32(eps, "eps")), eps.shape[0], int(k_total), float(lr), int(off),
+                               int(stride), int(bool(with_data)), _ptr(out_elbo), _ptr(workspace), workspace.numel() * 8,
+                               comm.handle if comm is not None else None, _stream()))
+
+
+class Comm:
+    """ocbnn_comm: the library's own NCCL communicator (one per process).  The id is created on rank 0 and handed to the other
+    ranks by `exchange` (a callable: bytes-or-None -> bytes, e.g. a torch.distributed broadcast) - host plumbing only."""
+
+    def __init__(self, rank, world, exchange):
+        require_cuda()
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            check(lib().ocbnn_comm_unique_id(buf))
+        ident = exchange(bytes(buf) if rank == 0 else None)
+        buf = (C.c_uint8 * 128).from_buffer_copy(ident)
+        h = C.c_void_p()
+        check(lib().ocbnn_comm_create(buf, int(rank), int(world), C.byref(h)))
+        self.handle, self.rank, self.world = h, int(rank), int(world)
+
+    def close(self):
+        if self.handle:
+            lib().ocbnn_comm_destroy(self.handle)
+            self.handle = None
+
+
+def comm_shard(n, rank, world):
+    lo, cnt = C.c_int64(), C.c_int64()
+    check(lib().ocbnn_comm_shard(int(n), int(rank), int(world), C.byref(lo), C.byref(cnt)))
+    return lo.value, lo.value + cnt.value
 
 
 def gemm_tf32x3(A, B):

@@ -39,6 +39,18 @@ def _batch_for(self, t):
     return (t % nb, nb)
 
 
+def _device_generator(self, dev):
+    """rng='device': one CUDA generator per model and rank, seeded from rank 0's torch seed + the rank."""
+    gen = getattr(self, "_dev_gen", None)
+    if gen is None or gen.device != dev:
+        seed = torch.tensor([int(torch.initial_seed()) & 0x7FFFFFFFFFFF], dtype=torch.int64)
+        D.broadcast_(seed)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(int(seed) + 7919 * D.rank())
+        self._dev_gen = gen
+    return gen
+
+
 def _raise_nan(self):
     logging.error(f"[{self.uid}] NaNs encountered in current set of weights.")
     raise Exception
@@ -52,21 +64,31 @@ class HMCMixin:
         M = max(1, int(getattr(self, "nchains", 1) or 1))
         return max(1, min(512, (64 << 20) // max(1, M * self.nweights)))
 
-    def _hmc_draw(self, n_it, M, dev):
-        """Momenta (n_it,M,D) ~ N(0,1) and uniforms (n_it,M) float64.  rng='host' reproduces the reference's streams:
-        one torch Normal(0,1).sample([D]) and one numpy uniform per iteration (inference.py:45,74)."""
+    def _hmc_draw(self, n_it, M, dev, lo=0, hi=None):
+        """Momenta (n_it, hi-lo, D) ~ N(0,1) and uniforms (n_it, hi-lo) float64 for chains [lo, hi) of M.
+
+        rng='host', one chain: the reference's streams exactly - one torch Normal(0,1).sample([D]) and one numpy uniform per
+        iteration (inference.py:45,74).  rng='host', M > 1 (no reference stream exists): ONE torch.randn / numpy call for all
+        chains of the chunk; every rank draws the full (n_it, M, D) block and keeps its slice, so N ranks seeded alike reproduce
+        one rank bit for bit and ranks seeded differently still run independent chains.  rng='device': a generator per rank
+        (rank 0's seed + rank), so equal user seeds on all ranks do not couple the chains."""
         Dw = self.nweights
+        hi = M if hi is None else hi
         if getattr(self, "rng", "host") == "device":
-            p0 = torch.randn(n_it, M, Dw, device=dev)
-            u = torch.rand(n_it, M, device=dev, dtype=torch.float64)
+            gen = _device_generator(self, dev)
+            p0 = torch.randn(n_it, hi - lo, Dw, device=dev, generator=gen)
+            u = torch.rand(n_it, hi - lo, device=dev, dtype=torch.float64, generator=gen)
             return p0, u
-        p0 = torch.empty(n_it, M, Dw)
-        u = np.empty((n_it, M))
-        for it in range(n_it):
-            for c in range(M):
-                p0[it, c] = Normal(0, 1).sample(torch.Size([Dw]))
-                u[it, c] = np.random.uniform()
-        return p0.to(dev), torch.from_numpy(u).to(dev)
+        if M == 1:
+            p0 = torch.empty(n_it, 1, Dw)
+            u = np.empty((n_it, 1))
+            for it in range(n_it):
+                p0[it, 0] = Normal(0, 1).sample(torch.Size([Dw]))
+                u[it, 0] = np.random.uniform()
+            return p0[:, lo:hi].to(dev), torch.from_numpy(u[:, lo:hi]).to(dev)
+        p0 = torch.randn(n_it, M, Dw)
+        u = np.random.uniform(size=(n_it, M))
+        return p0[:, lo:hi].contiguous().to(dev), torch.from_numpy(np.ascontiguousarray(u[:, lo:hi])).to(dev)
 
     def _hmc_state(self, M, dev):
         """Chain 0 continues from self.weights (like the reference); further chains continue from the previous
@@ -78,8 +100,10 @@ class HMCMixin:
             q[c] = prev[c] if prev is not None and prev.shape[0] > c else Normal(0, self.sigma_w).sample(torch.Size([self.nweights]))
         return q.to(dev).contiguous()
 
-    def hmc_run(self, q, n_it, with_data, collect_every=0, chunk=None, samples_host=None):
+    def hmc_run(self, q, n_it, with_data, collect_every=0, chunk=None, samples_host=None, chains=None):
         """n_it iterations from state q (M,D, device; updated in place).  Returns (accepts (M,), samples or None).
+        chains = (lo, M_total): q holds chains [lo, lo + M) of M_total (a rank's share; the random streams are defined over
+        all M_total chains, see _hmc_draw).
 
         The iterations run in chunks (one kernel launch each).  The momenta / uniforms of chunk k+1 are drawn and uploaded
         on a side stream while the kernel of chunk k runs, so host RNG and H2D copies overlap the compute.  With
@@ -87,9 +111,12 @@ class HMCMixin:
         a third stream while the next chunk runs; the copies are complete when this method returns."""
         prob = self.engine_problem()
         M = q.shape[0]
+        c_lo, M_total = (0, M) if chains is None else chains
         acc_total = torch.zeros(M, dtype=torch.int64, device=q.device)
         nsamp = n_it // collect_every if collect_every else 0
         samples = torch.empty(nsamp, M, self.nweights, device=q.device) if nsamp else None
+        if M == 0:                                       # a rank without chains (nchains < world size) only joins the collectives
+            return acc_total, samples
         chunk = self._hmc_chunk() if chunk is None else int(chunk)
         if collect_every:
             chunk = max(collect_every, chunk - chunk % collect_every)
@@ -107,7 +134,7 @@ class HMCMixin:
 
         def draw(n):
             with torch.cuda.stream(side):
-                p0, u = self._hmc_draw(n, M, q.device)
+                p0, u = self._hmc_draw(n, M_total, q.device, c_lo, c_lo + M)
                 ev = torch.cuda.Event()
                 ev.record(side)
             return p0, u, ev
@@ -154,7 +181,7 @@ class HMCMixin:
         q = self._hmc_state(M_total, dev)[lo:hi].contiguous()
         M = hi - lo
 
-        acc, _ = self.hmc_run(q, self.hmc_nburnin, with_data)
+        acc, _ = self.hmc_run(q, self.hmc_nburnin, with_data, chains=(lo, M_total))
         self.accepts = int(D.all_sum(acc.sum()))
         self.rejects = self.hmc_nburnin * M_total - self.accepts
         if self.hmc_nburnin:
@@ -163,7 +190,7 @@ class HMCMixin:
         logging.info("  Collecting samples now...")
         rounds = -(-self.infer_nsamples // M_total)
         n_it = rounds * self.hmc_ninterval
-        acc, samples = self.hmc_run(q, n_it, with_data, collect_every=self.hmc_ninterval)
+        acc, samples = self.hmc_run(q, n_it, with_data, collect_every=self.hmc_ninterval, chains=(lo, M_total))
         self.accepts = int(D.all_sum(acc.sum()))
         self.rejects = n_it * M_total - self.accepts
         end_time = time.time()
@@ -188,23 +215,31 @@ class SGLDMixin:
         """epsilon_t = a (b + t)^(-gamma) in Python float64 (inference.py:300-302)."""
         return self.sgld_epa * ((self.sgld_epb + t) ** (-1 * self.sgld_epgamma))
 
-    def _sgld_noise(self, ts, M, dev):
+    def _sgld_noise(self, ts, M, dev, lo=0, hi=None):
+        """Injected noise (len(ts), hi-lo, D) ~ N(0, eps_t) for chains [lo, hi) of M; same conventions as HMCMixin._hmc_draw
+        (one chain: the reference's stream, inference.py:339; several chains: one draw per chunk over all M chains, sliced)."""
         Dw = self.nweights
+        hi = M if hi is None else hi
+        sd = torch.tensor([self.get_stepsize(t) ** 0.5 for t in ts], dtype=torch.float32)
         if getattr(self, "rng", "host") == "device":
-            sd = torch.tensor([self.get_stepsize(t) ** 0.5 for t in ts], device=dev, dtype=torch.float32)
-            return torch.randn(len(ts), M, Dw, device=dev) * sd[:, None, None]
-        z = torch.empty(len(ts), M, Dw)
-        for i, t in enumerate(ts):
-            eps = self.get_stepsize(t)
-            for c in range(M):
-                z[i, c] = Normal(torch.zeros(Dw), (eps ** 0.5) * torch.ones(Dw)).sample()     # inference.py:339
-        return z.to(dev)
+            return torch.randn(len(ts), hi - lo, Dw, device=dev, generator=_device_generator(self, dev)) * sd.to(dev)[:, None, None]
+        if M == 1:
+            z = torch.empty(len(ts), 1, Dw)
+            for i, t in enumerate(ts):
+                eps = self.get_stepsize(t)
+                z[i, 0] = Normal(torch.zeros(Dw), (eps ** 0.5) * torch.ones(Dw)).sample()     # inference.py:339
+            return z[:, lo:hi].to(dev)
+        z = torch.randn(len(ts), M, Dw) * sd[:, None, None]
+        return z[:, lo:hi].contiguous().to(dev)
 
-    def sgld_run(self, w, t_first, n_steps, with_data, collect_every=0):
+    def sgld_run(self, w, t_first, n_steps, with_data, collect_every=0, chains=None):
         prob = self.engine_problem()
         M = w.shape[0]
+        c_lo, M_total = (0, M) if chains is None else chains
         nsamp = n_steps // collect_every if collect_every else 0
         samples = torch.empty(nsamp, M, self.nweights, device=w.device) if nsamp else None
+        if M == 0:                                       # a rank without chains only joins the collectives of infer()
+            return samples
         chunk = max(1, min(1024, (64 << 20) // max(1, M * self.nweights)))
         if collect_every:
             chunk = max(collect_every, chunk - chunk % collect_every)
@@ -213,7 +248,7 @@ class SGLDMixin:
         while done < n_steps:
             n = min(chunk, n_steps - done)
             ts = list(range(t_first + done, t_first + done + n))
-            noise = self._sgld_noise(ts, M, w.device)
+            noise = self._sgld_noise(ts, M_total, w.device, c_lo, c_lo + M)
             half = np.array([np.float32(self.get_stepsize(t) / 2) for t in ts], dtype=np.float32)
             offs = np.array([t % nb if nb > 1 else 0 for t in ts], dtype=np.int32)
             sl = samples[done // collect_every:(done + n) // collect_every] if collect_every else None
@@ -232,12 +267,13 @@ class SGLDMixin:
         M_total = max(1, int(getattr(self, "nchains", 1) or 1))
         lo, hi = D.shard(M_total)
         w = HMCMixin._hmc_state(self, M_total, dev)[lo:hi].contiguous()
-        self.sgld_run(w, 1, self.sgld_nburnin, with_data)
+        self.sgld_run(w, 1, self.sgld_nburnin, with_data, chains=(lo, M_total))
         if self.sgld_nburnin:
             logging.info(f"  All {self.sgld_nburnin} burn-in steps completed.")
         logging.info("  Collecting samples now...")
         rounds = -(-self.infer_nsamples // M_total)
-        samples = self.sgld_run(w, self.sgld_nburnin + 1, rounds * self.sgld_ninterval, with_data, collect_every=self.sgld_ninterval)
+        samples = self.sgld_run(w, self.sgld_nburnin + 1, rounds * self.sgld_ninterval, with_data, collect_every=self.sgld_ninterval,
+                                chains=(lo, M_total))
         end_time = time.time()
         if self.infer_nsamples:
             logging.info(f"  All {self.infer_nsamples} samples collected. Time took: {(end_time - start_time):.0f} seconds.")
@@ -255,41 +291,46 @@ class SVGDMixin:
     """Stein Variational Gradient Descent (inference.py:203-292); particles shard over ranks."""
 
     def svgd_setup(self, particles, use_tensor=-1):
-        """particles: (n, D) host or device tensor; this rank keeps rows [lo, hi).  use_tensor: 0 exact SIMT kernels,
-        1 tcgen05 path, -1 choose (tensor path from 1024 particles up)."""
+        """particles: (n, D) host or device tensor, the same on every rank (rank 0's copy is broadcast); every rank keeps all n
+        particles on its device and owns rows [lo, hi).  use_tensor: 0 exact SIMT kernels, 1 tcgen05 path, -1 choose (tensor path
+        from 1024 particles up)."""
         dev = self._device()
         n = particles.shape[0]
         lo, hi = D.shard(n)
         tensor = E.svgd_use_tensor(int(use_tensor), n)
-        ws = E.svgd_workspace(n, self.nweights, dev, n_rows=(n if D.world() == 1 else hi - lo), use_tensor=1 if tensor else 0)
-        hist, state = E.svgd_ws_views(ws)
-        return {"n": n, "lo": lo, "hi": hi, "tensor": tensor, "ws": ws, "hist": hist, "state": state, "prob": self.engine_problem(),
-                "X": particles[lo:hi].to(dev, torch.float32).contiguous(),
-                "G": torch.empty(hi - lo, self.nweights, device=dev), "phi": torch.empty(hi - lo, self.nweights, device=dev),
+        ws = E.svgd_workspace(n, self.nweights, dev, n_rows=hi - lo, use_tensor=1 if tensor else 0)
+        Xall = particles.to(dev, torch.float32).contiguous().clone()
+        D.broadcast_(Xall)
+        Gall = torch.empty_like(Xall)
+        return {"n": n, "lo": lo, "hi": hi, "tensor": tensor, "ws": ws, "prob": self.engine_problem(), "comm": D.comm(),
+                "Xall": Xall, "Gall": Gall, "X": Xall[lo:hi], "G": Gall[lo:hi], "phi": torch.empty(hi - lo, self.nweights, device=dev),
                 "acc": torch.zeros(hi - lo, self.nweights, device=dev), "h": torch.empty(1, device=dev)}
 
     def svgd_epoch(self, st, epoch, with_data, use_tensor=None):
-        """One SVGD epoch on the device: gradients (K1), all-gather, bandwidth (K3a), phi (K3b), Adagrad (K3c).
+        """One SVGD epoch = ONE library call (`ocbnn_svgd_step`: gradients K1, all-gather, bandwidth K3a, phi K3b, Adagrad K3c,
+        all-gather), on any number of ranks.
 
-        Single rank: the ~16 launches of an epoch are captured once per (minibatch offset, with_data, path) into a CUDA graph
-        and replayed (the epoch is launch-gap bound at a few thousand particles); `svgd_graph: false` in the config, a
-        multi-rank run (NCCL + host-driven select) or a failed capture use the eager path."""
-        if D.world() != 1 or not st.get("graph_ok", True) or not bool(getattr(self, "svgd_graph", True)):
+        The ~16 launches (and, across ranks, the NCCL collectives the library issues on the same stream) are captured once per
+        (minibatch offset, with_data, path) into a CUDA graph and replayed - the epoch is launch-gap bound at a few thousand
+        particles.  `svgd_graph: false` in the config or a failed capture use the eager path."""
+        if not st.get("graph_ok", True) or not bool(getattr(self, "svgd_graph", True)):
             return self._svgd_epoch_eager(st, epoch, with_data, use_tensor)
         key = (_batch_for(self, epoch), bool(with_data), use_tensor)
         graphs = st.setdefault("graphs", {})
         ent = graphs.get(key)
-        if ent is None:                         # first use of this key: eager (also warms per-kernel attributes)
+        if ent is None:                         # first use of this key: eager (also warms per-kernel attributes and the side stream)
             graphs[key] = "warm"
             return self._svgd_epoch_eager(st, epoch, with_data, use_tensor)
         if ent == "warm":
             try:
                 g = torch.cuda.CUDAGraph()
                 torch.cuda.synchronize()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     self._svgd_epoch_eager(st, epoch, with_data, use_tensor)
                 graphs[key] = ent = g
             except Exception as exc:            # capture not possible here: stay eager from now on
+                if D.world() > 1:               # the ranks must agree on the path; a one-sided fallback would deadlock the collectives
+                    raise
                 logging.warning(f"[{self.uid}] SVGD epoch graph capture failed ({exc}); running eagerly.")
                 st["graph_ok"] = False
                 graphs.clear()
@@ -299,59 +340,9 @@ class SVGDMixin:
         return st
 
     def _svgd_epoch_eager(self, st, epoch, with_data, use_tensor=None):
-        prob = st["prob"]                      # compiled once per infer(): the reference also fixes data and constraints per infer()
-        X = st["X"]
         tensor = st["tensor"] if use_tensor is None else E.svgd_use_tensor(int(use_tensor), st["n"]) and st["tensor"]
-        if D.world() == 1:                      # gradients (K1) on a side stream: they overlap the distance / bandwidth chain, which
-            main = torch.cuda.current_stream()  # depends on X only and has narrow kernels (the one-CTA bracket)
-            side = st.get("side")
-            if side is None:
-                side = st["side"] = torch.cuda.Stream(device=X.device)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                _, G = prob.logpost_grad(X, _batch_for(self, epoch), with_data, want_lp=False, out_grad=st["G"])
-            E.svgd_bandwidth(X, st["ws"], st["h"], use_tensor=1 if tensor else 0)
-            main.wait_stream(side)
-            n, lo, rows = st["n"], st["lo"], st["hi"] - st["lo"]
-            phi = E.svgd_phi(X, G, st["h"], lo, rows, st["ws"], 2 if tensor else 0, out=st["phi"])
-            E.adagrad_step(X, st["acc"], phi, self.svgd_init_lr, -1.0)
-            st["phi"] = phi
-            return st
-        _, G = prob.logpost_grad(X, _batch_for(self, epoch), with_data, want_lp=False, out_grad=st["G"])
-        if D.world() == 1:
-            Xall, Gall = X, G
-        else:                                   # shard sizes follow from n: no size exchange, no host sync; buffers reused
-            if "Xall" not in st:
-                st["Xall"], st["Gall"] = torch.empty(st["n"], self.nweights, device=X.device), torch.empty(st["n"], self.nweights, device=X.device)
-            Xall, Gall = D.gather_rows(X, st["n"], out=st["Xall"]), D.gather_rows(G, st["n"], out=st["Gall"])
-        n, lo, rows = st["n"], st["lo"], st["hi"] - st["lo"]
-        if D.world() == 1:
-            E.svgd_bandwidth(Xall, st["ws"], st["h"], use_tensor=1 if tensor else 0)
-        elif tensor and E.svgd_select_mode(-1) != 0:
-            # exact global median by the bracket select across ranks: one all-reduce of the counters + linear histogram, then three
-            # 8 KB all-reduces of the radix histograms over the short candidate lists (OCBNN_SVGD_SELECT=legacy: radix select below)
-            d_ = self.nweights
-            E.svgd_prepare(Xall, lo, rows, st["ws"])
-            red = E.svgd_sel_count(n, d_, lo, rows, st["ws"])
-            D.all_sum_(red)
-            E.svgd_sel_gather(n, d_, lo, rows, st["ws"])
-            for p in range(3):
-                E.svgd_sel_hist(n, d_, lo, rows, p, st["hist"], st["state"], st["ws"])
-                D.all_sum_(st["hist"][p * 2048:(p + 1) * 2048])
-                E.svgd_sel_update(n, d_, lo, rows, p, st["hist"], st["state"], st["ws"], st["h"])
-        else:                                   # exact global median: all-reduce the select histograms between passes
-            if tensor:
-                E.svgd_prepare(Xall, lo, rows, st["ws"])
-            for p in range(3):
-                if tensor:
-                    E.svgd_hist_pass_prepared(n, self.nweights, lo, rows, p, st["hist"], st["state"], st["ws"])
-                else:
-                    E.svgd_hist_pass(Xall, D.rank(), D.world(), len(range(D.rank(), n, D.world())), p, st["hist"], st["state"])
-                D.all_sum_(st["hist"][p * 2048:(p + 1) * 2048])
-                E.svgd_select_update(p, st["hist"], st["state"], n, st["h"])
-        phi = E.svgd_phi(Xall, Gall, st["h"], lo, rows, st["ws"], 2 if tensor else 0, out=st["phi"])
-        E.adagrad_step(X, st["acc"], phi, self.svgd_init_lr, -1.0)      # particles.grad = -update (inference.py:280)
-        st["phi"] = phi
+        E.svgd_step(st["prob"], st["Xall"], st["Gall"], st["acc"], st["phi"], st["h"], st["lo"], st["hi"] - st["lo"], self.svgd_init_lr,
+                    _batch_for(self, epoch), with_data, 1 if tensor else 0, st["ws"], st["comm"])
         return st
 
     def infer(self, verbose=True, with_data=True):
@@ -366,7 +357,7 @@ class SVGDMixin:
                 logging.info(f"  Epoch {epoch} reached.")
         end_time = time.time()
         logging.info(f"  {self.svgd_epochs} epochs completed. Time took: {(end_time - start_time):.0f} seconds.")
-        self.particles = D.gather_cat(st["X"], dim=0).cpu()
+        self.particles = st["Xall"].cpu()             # every rank holds all particles after the step's closing all-gather
         if bool(torch.isnan(self.particles).any()):
             _raise_nan(self)
         if D.rank() == 0:
@@ -386,16 +377,16 @@ class BBBMixin:
         weights = mean + eps * std
         return weights, Normal(mean, std).log_prob(weights)
 
-    def bbb_epoch(self, qp, acc, eps, epoch, with_data, k_total=None):
-        """One ELBO-gradient step on the device.  eps: this rank's (k_local, D) standard normal draws."""
-        prob = self.engine_problem()
+    def bbb_epoch(self, qp, acc, eps, epoch, with_data, k_total=None, state=None):
+        """One ELBO-gradient step = ONE library call (`ocbnn_bbb_step`: sample, K1, closed-form (D,2) gradient, one all-reduce of
+        gradient + ELBO, Adagrad).  eps: this rank's (k_local, D) standard normal draws.  state: dict reused across epochs
+        (workspace, communicator, ELBO scalar); returns the ELBO as a 1-element device tensor."""
+        state = {} if state is None else state
         k_total = eps.shape[0] * D.world() if k_total is None else k_total
-        W = E.bbb_sample(qp, eps)
-        lp, G = prob.logpost_grad(W, _batch_for(self, epoch), with_data)
-        gq, elbo = E.bbb_reduce(qp, eps, lp, G, k_total, add_entropy=(D.rank() == 0))
-        D.all_sum_(gq)
-        D.all_sum_(elbo)
-        E.adagrad_step(qp, acc, gq, self.bbb_init_lr, -1.0)             # loss = -ELBO
+        if state.get("k") != eps.shape[0]:
+            state.update(k=eps.shape[0], ws=E.bbb_workspace(eps.shape[0], self.nweights, qp.device), comm=D.comm(), prob=self.engine_problem())
+        elbo = torch.empty(1, device=qp.device)
+        E.bbb_step(state["prob"], qp, acc, eps, k_total, self.bbb_init_lr, _batch_for(self, epoch), with_data, elbo, state["ws"], state["comm"])
         return elbo
 
     def infer(self, verbose=True, with_data=True):
@@ -406,17 +397,24 @@ class BBBMixin:
         init_means = self.bbb_init_mean + torch.randn(self.nweights, 1)
         init_log_stds = self.bbb_init_std * torch.ones(self.nweights, 1)
         qp = torch.cat([init_means, init_log_stds], dim=1).to(dev).contiguous()
+        D.broadcast_(qp)                        # replicated state: rank 0's draw, whatever the other ranks' seeds are
         acc = torch.zeros_like(qp)
         k = int(self.bbb_esamples)
         lo, hi = D.shard(k)
         device_rng = getattr(self, "rng", "host") == "device"
-        elbos = []
+        gen = None
+        if device_rng:                          # distinct Monte-Carlo draws on every rank even when the user seeded all ranks alike
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(int(torch.initial_seed()) + 7919 * (D.rank() + 1))
+        elbos, state = [], {}
         for epoch in range(1, self.bbb_epochs + 1):
             if device_rng:
-                eps = torch.randn(hi - lo, self.nweights, device=dev)
-            else:
-                eps = torch.randn(k, self.nweights)[lo:hi].to(dev).contiguous()    # inference.py:138
-            elbos.append(self.bbb_epoch(qp, acc, eps, epoch, with_data, k_total=k))
+                eps = torch.randn(hi - lo, self.nweights, device=dev, generator=gen)
+            else:                               # inference.py:138; rank 0's stream, so that N ranks reproduce one rank
+                eps_all = torch.randn(k, self.nweights)
+                D.broadcast_(eps_all)
+                eps = eps_all[lo:hi].to(dev).contiguous()
+            elbos.append(self.bbb_epoch(qp, acc, eps, epoch, with_data, k_total=k, state=state))
             if verbose and epoch % 100 == 0:
                 logging.info(f"  Epoch {epoch}: {float(elbos[-1]):.2f}")
         self.elbos = [float(e) for e in torch.cat(elbos).cpu()] if elbos else []

@@ -50,7 +50,7 @@ def main():
     st = ms.svgd_setup(X0)
     for ep in range(1, 4):
         ms.svgd_epoch(st, ep, True, use_tensor=0)
-    Xs, hs = D.gather_cat(st["X"], 0), st["h"].clone()
+    Xs, hs = st["Xall"].clone(), st["h"].clone()
     # single-rank arm: same model code with the process group hidden
     saved = D.active
     D.active = lambda: False
@@ -78,7 +78,7 @@ def main():
             stt = mt.svgd_setup(Xt, use_tensor=1)
             for ep in range(1, 3):
                 mt.svgd_epoch(stt, ep, True)
-            res[mode] = (D.gather_cat(stt["X"], 0), stt["h"].clone())
+            res[mode] = (stt["Xall"].clone(), stt["h"].clone())
         E.svgd_select_mode(1)
         D.active = lambda: False
         st1 = mt.svgd_setup(Xt, use_tensor=1)

@@ -1,47 +1,37 @@
-"""Per-kernel timing of one SVGD epoch (W4 shapes) with CUDA events: K1 gradients, K3a bandwidth, K3b phi, K3c Adagrad."""
+"""GPU probe: SVGD epoch time (W4 = F3b shape, D = 31) and its two big phases, per particle count."""
 import os, sys, tempfile
-import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "ocbnn-public_b200"))
+for p in ("ocbnn-public_b200", "oracle", "tests"):
+    sys.path.insert(0, os.path.join(ROOT, p))
+import torch
 from ocbnn_b200 import engine as E, workloads
 
-def t(fn, reps=5):
-    fn(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps): fn()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
+def t_cuda(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
 
 os.chdir(tempfile.mkdtemp())
 wl = sys.argv[1] if len(sys.argv) > 1 else "W4"
-for n in [int(a) for a in sys.argv[2:]] or [4096, 16384]:
+for n in [int(v) for v in (sys.argv[2:] or ["4096", "16384", "32768"])]:
     m = workloads.build(wl, seed=0, infer_nsamples=n)
-    prob = m.engine_problem()
-    dev = torch.device("cuda")
-    if m.aocp_mean is not None:
-        X = (m.aocp_mean[None] + 3 * m.aocp_std[None] * torch.randn(n, m.nweights)).to(dev).contiguous()
-    else:
-        X = torch.randn(n, m.nweights, device=dev)
-    use_t = int(os.environ.get("SVGD_TENSOR", "0"))
-    ws = E.svgd_workspace(n, m.nweights, dev, use_tensor=use_t)
-    h = torch.empty(1, device=dev); acc = torch.zeros_like(X)
-    G = torch.empty_like(X); phi = torch.empty_like(X)
-    r = {}
-    r["K1 grad"] = t(lambda: prob.logpost_grad(X, (1, m.nbatches) if m.nbatches else (0, 1), True, want_lp=False, out_grad=G))
-    r["K3a bandwidth"] = t(lambda: E.svgd_bandwidth(X, ws, h, use_tensor=use_t))
-    r["K3b phi"] = t(lambda: E.svgd_phi(X, G, h, 0, n, ws, 2 if use_t else 0, out=phi))
-    r["K3c adagrad"] = t(lambda: E.adagrad_step(X.clone(), acc, phi, 0.5, -1.0))
-    def raw_epoch():
-        prob.logpost_grad(X, (1, m.nbatches) if m.nbatches else (0, 1), True, want_lp=False, out_grad=G)
-        E.svgd_bandwidth(X, ws, h, use_tensor=use_t)
-        E.svgd_phi(X, G, h, 0, n, ws, 2 if use_t else 0, out=phi)
-        E.adagrad_step(X, acc, phi, 1e-6, -1.0)
-    r["epoch (raw engine calls)"] = t(raw_epoch)
-    import time
-    torch.cuda.synchronize(); t0 = time.perf_counter(); raw_epoch(); t1 = time.perf_counter(); torch.cuda.synchronize()
-    r["host time of raw epoch"] = (t1 - t0) * 1e3
-    st = m.svgd_setup(X.cpu(), use_tensor=use_t)
-    m.svgd_epoch(st, 1, True); m.svgd_epoch(st, 1, True)      # eager, then graph capture
-    r["epoch (host API)"] = t(lambda: m.svgd_epoch(st, 1, True))
-    print(wl, "n", n, "D", m.nweights, {k: f"{v:.3f} ms" for k, v in r.items()}, "particle-iters/s %.3e" % (n / (r["epoch (host API)"] * 1e-3)))
+    X0 = torch.randn(n, m.nweights, generator=torch.Generator().manual_seed(3))
+    st = m.svgd_setup(X0)
+    ep = [0]
+    def epoch():
+        ep[0] += 1
+        m.svgd_epoch(st, ep[0], True)
+    t_ep = t_cuda(epoch, reps=20, warm=4)
+    X, G = st["X"], st["G"]
+    t_bw = t_cuda(lambda: E.svgd_bandwidth(X, st["ws"], st["h"], use_tensor=1))
+    t_phi = t_cuda(lambda: E.svgd_phi(X, G, st["h"], 0, n, st["ws"], 2, out=st["phi"]))
+    t_g = t_cuda(lambda: st["prob"].logpost_grad(X, (0, 1), True, want_lp=False, out_grad=G))
+    print(f"{wl} n={n}: epoch {t_ep*1e3:.1f} us ({n/t_ep/1e3:.2f} M particle-iters/s); bandwidth {t_bw*1e3:.1f} us, phi {t_phi*1e3:.1f} us, grad {t_g*1e3:.1f} us, "
+          f"ws {st['ws'].numel()*8/2**20:.0f} MiB, finite {bool(torch.isfinite(st['X']).all())}", flush=True)

@@ -166,7 +166,7 @@ def test_hmc_infer_driver_semantics():
     m.weights = torch.tensor(g["hmcdrv_q0"]).requires_grad_(True)
     p_all, u_all, pos = g["hmcdrv_p0"], g["hmcdrv_u"], [0]
 
-    def draw(n_it, M, device):
+    def draw(n_it, M, device, lo=0, hi=None):
         p = torch.tensor(p_all[pos[0]:pos[0] + n_it])[:, None, :].to(device)
         u = torch.tensor(u_all[pos[0]:pos[0] + n_it])[:, None].to(device)
         pos[0] += n_it
@@ -199,7 +199,7 @@ def test_k4_sgld(name):
     m.weights = torch.tensor(g["sgld_w0"]).requires_grad_(True)
     z, pos = g["sgld_z"], [0]
 
-    def noise(ts, M, device):
+    def noise(ts, M, device, lo=0, hi=None):
         sd = np.array([np.float32(m.get_stepsize(t) ** 0.5) for t in ts], dtype=np.float32)
         out = torch.tensor(z[pos[0]:pos[0] + len(ts)] * sd[:, None])[:, None, :].to(device)
         pos[0] += len(ts)
@@ -212,20 +212,25 @@ def test_k4_sgld(name):
     assert rel_err(m.weights.detach().numpy()[None], g["sgld_final"][None]).max() < 1e-4
 
 
+@pytest.mark.parametrize("tensor", [0, 1], ids=["simt", "tcgen05"])
 @pytest.mark.parametrize("name", cases.SAMPLER_CASES + cases.BATCHED_SAMPLER_CASES)
-def test_k3_svgd(name):
+def test_k3_svgd(name, tensor):
+    """Three SVGD epochs against the reference's golden vectors (n = 6-10 particles), on the exact SIMT arm and on the
+    tcgen05 path (forced: the default picks it from 1024 particles up)."""
     g = load_golden(name)
     n = g["svgd_x0"].shape[0]
     m = make_model(name, g, sampler="SVGD", svgd_epochs=3, infer_nsamples=n)
     spec = spec_from_golden(name, g)
     cfg = golden_config(g)
-    st = m.svgd_setup(torch.tensor(g["svgd_x0"]))
+    st = m.svgd_setup(torch.tensor(g["svgd_x0"]), use_tensor=tensor)
+    assert bool(st["tensor"]) == bool(tensor)
     # bandwidth: exact lower median -> h equal to the reference's to fp32 rounding
-    h = E.svgd_bandwidth(st["X"], st["ws"])
-    assert abs(float(h) - g["svgd_h"][0]) <= 2e-6 * g["svgd_h"][0]
-    assert abs(float(h) - orc.svgd_rbf_h(g["svgd_x0"])) <= 2e-6 * g["svgd_h"][0]
+    h = E.svgd_bandwidth(st["X"], st["ws"], use_tensor=tensor)
+    h_tol = 2e-6 if (tensor == 0 or m.nweights <= 64) else 1e-5
+    assert abs(float(h) - g["svgd_h"][0]) <= h_tol * g["svgd_h"][0]
+    assert abs(float(h) - orc.svgd_rbf_h(g["svgd_x0"])) <= h_tol * g["svgd_h"][0]
     for ep in range(1, 4):
-        m.svgd_epoch(st, ep, True, use_tensor=0)
+        m.svgd_epoch(st, ep, True, use_tensor=tensor)
         if ep == 1:
             assert rel_err(st["phi"].cpu().numpy(), g["svgd_phi"][0]).max() < 2e-5
         assert abs(float(st["h"]) - g["svgd_h"][ep - 1]) <= 1e-4 * g["svgd_h"][ep - 1]
