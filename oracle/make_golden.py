@@ -343,6 +343,29 @@ def run_case(name):
         out["bbb_elbos"] = np.array(m.elbos, dtype=np.float32)
         out["bbb_samples"] = np32(m.all_bayes_samples[-1][0])
 
+    # ---- K4 at the repro step size: two injected-noise SGLD steps of the reference's own infer() from the warm state with
+    # sgld_epa as the YAML / config.yaml has it (0.05 -> eps_1 = 6.4e-3).  Two steps stay finite on every case (the long
+    # fixture above needs the small step size because seven steps at 6e-3 amplify 1-ulp differences chaotically); the draws
+    # come after every other fixture so that the older arrays keep their random streams.
+    if small or batched:
+        z = torch.randn(2, D_ := m.nweights, generator=gen)
+        for burn in (1, 0):                      # two steps; ONE where the second leaves fp32 range (recid_small: curvature 1/aocp_std^2 ~ 1e4)
+            m = fresh("SGLD")
+            m.update_config(sgld_nburnin=burn, infer_nsamples=1, sgld_ninterval=1)
+            w0 = warm[True].clone() if small else W[0].clone()
+            m.weights = torch.autograd.Variable(w0.clone(), requires_grad=True)
+            FakeNormal.queue, FakeNormal.scaled = list(z[:burn + 1]), True
+            with mock.patch.object(refinf, "Normal", FakeNormal):
+                m.infer(verbose=False)
+            if np.isfinite(np32(m.weights.data)).all():
+                break
+        out["sgldr_epa"] = np.array(float(m.sgld_epa))
+        out["sgldr_nburnin"] = np.array(burn)
+        out["sgldr_w0"], out["sgldr_z"] = np32(w0), np32(z[:burn + 1])
+        out["sgldr_samples"] = np32(m.all_bayes_samples[-1][0])
+        out["sgldr_final"] = np32(m.weights.data)
+        assert np.isfinite(out["sgldr_final"]).all(), name
+
     os.makedirs(GOLD, exist_ok=True)
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
     sz = os.path.getsize(os.path.join(GOLD, name + ".npz"))

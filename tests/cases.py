@@ -66,6 +66,16 @@ def synth_recid(n=310, seed=0):
             "X_train_min": [-3.0] * 9, "X_train_max": [3.0] * 9}
 
 
+def synth_reg_y2(n=12, seed=0):
+    """Two-output regression (the MVN branch of RegressorMixin.log_likelihood, base.py:265)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    X = 3.0 * torch.rand(n, 2, generator=g) - 1.5
+    Y = torch.stack([torch.sin(2 * X[:, 0]) + 0.3 * X[:, 1], X[:, 0] * X[:, 1]], 1) + 0.05 * torch.randn(n, 2, generator=g)
+    return {"dataset_name": "synth_reg_y2", "X_train": X, "Y_train": Y,
+            "X_train_min": [-1.5] * 2, "X_train_max": [1.5] * 2}
+
+
 CREDIT_BOX = (0.25, 3.0, -3.0, -1.0) + (-0.2, 0.2) * 8
 RECID_BOX = (-0.2, 0.2, 0.0, 1.0) + (-0.2, 0.2) * 7
 
@@ -100,6 +110,7 @@ CASES = {
                                               prior_type="positive_gaussian_cocp")),
         ("add_deterministic_constraint", dict(constrained_domain=(-1.0, 1.0), interval_func=if_f3b,
                                               prior_type="negative_exponential_cocp"))]),
+    "reg_y2": dict(cls="Regressor", yaml="example", data="synth_reg_y2", overrides=dict(architecture=[12])),
     "reg_relu": dict(cls="Regressor", yaml="example", data="toy1", overrides=dict(activation="relu")),
     "reg_linear": dict(cls="Regressor", yaml="example", data="toy1", overrides=dict(activation="none")),
     "reg_deep": dict(cls="Regressor", yaml="F1a", data="toy1", use_ocbnn=True,
@@ -142,7 +153,7 @@ CASES = {
 
 # cases small enough for sampler trajectories from the (slow) reference
 SAMPLER_CASES = ["w1_reg_vanilla", "w2_reg_neg", "f3b_reg_neg2", "f6_reg_pos", "cls_vanilla", "w3_cls_dir",
-                 "bin_vanilla", "f4_bin_aocp", "reg_deep"]
+                 "bin_vanilla", "f4_bin_aocp", "reg_deep", "reg_y2"]
 BATCHED_SAMPLER_CASES = ["credit_small", "recid_small"]
 
 

@@ -90,3 +90,43 @@ def rel_err(a, b):
         return np.abs(a - b) / np.maximum(np.abs(b), 1e-30)
     ax = tuple(range(1, a.ndim))
     return np.sqrt(((a - b) ** 2).sum(axis=ax)) / np.maximum(np.sqrt((b ** 2).sum(axis=ax)), 1e-30)
+
+
+# ---- measured-error bookkeeping of the GPU parity tests ------------------------------------------------------------------
+# Every comparison of the GPU parity tests goes through hold(): the measured maximum error is recorded (conftest.py writes the
+# table to gpurun_out/parity_errors.json at the end of a GPU session; a copy is committed as profiles/r02_parity_errors.json)
+# and the asserted bound is
+#       min(default_tol + slack, max(1e-5, 2 x the error measured on the B200 when tests/parity_floors.json was refreshed))
+# i.e. BASELINE.json's 1e-5 wherever the engine reaches it and never more than twice the achieved error elsewhere.  `slack` is
+# the conditioning allowance of a row (fp32-vs-float64 gap of the oracle itself), used only until a floor has been measured.
+NORTH_STAR_TOL = 1e-5
+PARITY = {}
+_FLOORS = None
+
+
+def _floors():
+    global _FLOORS
+    if _FLOORS is None:
+        p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "parity_floors.json")
+        _FLOORS = json.load(open(p)) if os.path.exists(p) else {}
+    return _FLOORS
+
+
+def bound(test, case, what, default_tol, slack=0.0):
+    measured = _floors().get(f"{test}:{case}:{what}")
+    loose = float(default_tol) + float(slack)
+    return loose if measured is None else min(loose, max(NORTH_STAR_TOL, 2.0 * float(measured)))
+
+
+def hold(test, case, what, err, default_tol, slack=0.0):
+    """err, slack: scalars or per-row arrays (the row with the largest err - slack decides)."""
+    key = f"{test}:{case}:{what}"
+    err, slack = np.atleast_1d(np.asarray(err, dtype=np.float64)), np.broadcast_to(np.asarray(slack, dtype=np.float64), np.atleast_1d(err).shape)
+    i = int(np.argmax(err - slack)) if np.isfinite(err).all() else int(np.argmax(~np.isfinite(err)))
+    e, sl = float(err[i]), float(slack[i])
+    tol = bound(test, case, what, default_tol, sl)
+    ent = PARITY.setdefault(key, {"max_err": 0.0, "tol": tol, "default_tol": float(default_tol), "slack": sl})
+    if not np.isfinite(e) or float(err.max()) > ent["max_err"]:
+        ent.update(max_err=float(err.max()) if np.isfinite(e) else e, tol=max(tol, ent["tol"]), slack=max(sl, ent["slack"]))
+    assert e <= tol, (key, "measured", e, "bound", tol)
+    return e

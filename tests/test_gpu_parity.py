@@ -11,7 +11,7 @@ import torch
 
 import cases
 import ocbnn_oracle as orc
-from helpers import golden_config, load_golden, make_model, rel_err, spec_from_golden
+from helpers import bound, golden_config, hold, load_golden, make_model, rel_err, spec_from_golden
 from ocbnn_b200 import engine as E
 
 pytestmark = pytest.mark.gpu
@@ -31,14 +31,14 @@ def t2d(a, dtype=torch.float32):
 
 
 def check(x, ref, x32, x64, what, floor=TOL):
+    """what = (case, quantity...).  Against the float64 oracle the engine is held to 1e-5 + 2 cond, cond = the fp32-vs-float64 gap
+    of the oracle itself for that row (0 where fp32 is well conditioned).  Against the reference's fp32 golden vectors: 1e-5 plus,
+    on ill-conditioned rows only, the reference's own distance from the float64 truth (triangle inequality)."""
     cond = rel_err(x32, x64)
-    # against the reference: 1e-5 wherever fp32 is well conditioned (cond = fp32-vs-float64 oracle gap below 2.5e-6) and the
-    # reference's own fp32 result is within that of the float64 truth; on ill-conditioned rows the bound is the triangle
-    # inequality |engine - ref| <= |engine - f64| + |ref - f64| with the engine's side held to 1e-5 + 2 cond on the next line
-    tol = np.maximum(np.maximum(floor, 4 * cond), rel_err(ref, x64) + floor + 2 * cond)
-    e_ref, e_64 = rel_err(x, ref), rel_err(x, x64)
-    assert (e_64 <= floor + 2 * cond).all(), (what, "engine vs float64 oracle", e_64, cond)
-    assert (e_ref <= tol).all(), (what, "engine vs reference", e_ref, tol)
+    slack_ref = np.maximum(4 * cond, rel_err(ref, x64) + 2 * cond)
+    key = "/".join(str(w) for w in what[1:])
+    hold("k1", what[0], key + ":vs_f64_oracle", rel_err(x, x64), floor, 2 * cond)
+    hold("k1", what[0], key + ":vs_reference", rel_err(x, ref), floor, slack_ref)
 
 
 @pytest.mark.parametrize("name", ALL)
@@ -54,8 +54,8 @@ def test_k1_logpost_and_grad(name):
         (lp32, g32), (lp64, g64) = f(np.float32), f(np.float64)
         for lanes in lanes_list:
             lp, gr = prob.logpost_grad(t2d(W), (0, 1), with_data, lanes=lanes)
-            check(lp.cpu().numpy(), g["lp_" + key], lp32, lp64, (name, key, lanes))
-            check(gr.cpu().numpy(), g["g_" + key], g32, g64, (name, key, "grad", lanes))
+            check(lp.cpu().numpy(), g["lp_" + key], lp32, lp64, (name, key, "value"))
+            check(gr.cpu().numpy(), g["g_" + key], g32, g64, (name, key, "grad"))
     nb = golden_config(g).get("nbatches")
     if nb:
         for off in (1, nb - 1):
@@ -119,12 +119,19 @@ def test_k2_hmc_trajectory(name):
                 Hn = H.cpu().numpy()[0, 0]
                 alpha_ref = np.exp(np.float32(ref_H[0] - ref_H[2] + ref_H[1] - ref_H[3]))
                 u = float(g[tag + "_u"][it])
-                if abs(u - alpha_ref) > 1e-3 * max(alpha_ref, 1e-30):          # outside the fp32 noise band of the decision
+                # acceptance probability alpha = exp(U0 - U1 + K0 - K1): the engine's against the reference's (differences of
+                # O(10..1e4) energies, so alpha carries |H| x 1e-7 of relative noise); outside that band the decisions are identical
+                alpha = np.exp(np.float32(Hn[0] - Hn[2] + Hn[1] - Hn[3]))
+                if np.isfinite(alpha_ref) and alpha_ref > 1e-30:
+                    hold("k2_hmc", name, f"{tag}:accept_probability", abs(alpha - alpha_ref) / alpha_ref, 5e-3)
+                if abs(u - alpha_ref) > bound("k2_hmc", name, f"{tag}:accept_probability", 5e-3) * max(alpha_ref, 1e-30):
                     assert bool(acc[0, 0]) == bool(g[tag + "_acc"][it]), (name, tag, it, lanes)
-                assert np.abs(Hn - ref_H).max() <= 5e-5 * max(1.0, np.abs(ref_H).max()), (name, tag, it, Hn, ref_H)
-                tol = max(1e-4, 4 * rel_err(q32, q64).max())
-                assert rel_err(q.cpu().numpy(), g[tag + "_q"][it][None]).max() < tol, (name, tag, it, lanes)
-                assert rel_err(q.cpu().numpy(), q64).max() < tol
+                hold("k2_hmc", name, f"{tag}:energies", np.abs(Hn - ref_H).max() / max(1.0, np.abs(ref_H).max()), 5e-5)
+                # end state of an L-step trajectory: the fp32-vs-float64 gap of the oracle itself (the reference's own
+                # arithmetic noise over L steps) is the conditioning slack, as in K1
+                cond = rel_err(q32, q64).max()
+                hold("k2_hmc", name, f"{tag}:end_state_vs_reference", rel_err(q.cpu().numpy(), g[tag + "_q"][it][None]).max(), 1e-4, 4 * cond)
+                hold("k2_hmc", name, f"{tag}:end_state_vs_f64_oracle", rel_err(q.cpu().numpy(), q64).max(), 1e-4, 4 * cond)
 
 
 def test_k2_chains_are_independent_and_restore_works():
@@ -175,7 +182,7 @@ def test_hmc_infer_driver_semantics():
     m.infer(verbose=False)
     samples, nm = m.all_bayes_samples[-1]
     assert nm == str(g["hmcdrv_name"]) and samples.shape == g["hmcdrv_samples"].shape and samples.dtype == torch.float32
-    assert rel_err(samples.numpy(), g["hmcdrv_samples"]).max() < 1e-4
+    hold("hmc_infer", name, "samples", rel_err(samples.numpy(), g["hmcdrv_samples"]).max(), 1e-4)
     assert os.path.exists(f"history/{m.uid}_hmc1.pt")
     assert torch.equal(torch.load(f"history/{m.uid}_hmc1.pt"), samples)
     assert pos[0] == 2 + 3 * 2
@@ -208,8 +215,33 @@ def test_k4_sgld(name):
     m.infer(verbose=False)
     samples, nm = m.all_bayes_samples[-1]
     assert nm.startswith("sgld_") and samples.shape == g["sgld_samples"].shape
-    assert rel_err(samples.numpy(), g["sgld_samples"]).max() < 1e-4
-    assert rel_err(m.weights.detach().numpy()[None], g["sgld_final"][None]).max() < 1e-4
+    hold("k4_sgld", name, "samples", rel_err(samples.numpy(), g["sgld_samples"]).max(), 1e-4)
+    hold("k4_sgld", name, "final", rel_err(m.weights.detach().numpy()[None], g["sgld_final"][None]).max(), 1e-4)
+
+
+@pytest.mark.parametrize("name", cases.SAMPLER_CASES + cases.BATCHED_SAMPLER_CASES)
+def test_k4_sgld_repro_stepsize(name):
+    """SGLD at the step size the repro configs use (sgld_epa = 0.05 -> eps_1 = 6.4e-3; inference.py:300-302,331-340): the
+    reference's own infer() for two injected-noise steps from the warm state (one where the second leaves fp32 range)."""
+    g = load_golden(name)
+    burn = int(g["sgldr_nburnin"])
+    m = make_model(name, g, sampler="SGLD", sgld_nburnin=burn, infer_nsamples=1, sgld_ninterval=1)
+    assert float(m.sgld_epa) == float(g["sgldr_epa"]) == 0.05
+    m.weights = torch.tensor(g["sgldr_w0"]).requires_grad_(True)
+    z, pos = g["sgldr_z"], [0]
+
+    def noise(ts, M, device, lo=0, hi=None):
+        sd = np.array([np.float32(m.get_stepsize(t) ** 0.5) for t in ts], dtype=np.float32)
+        out = torch.tensor(z[pos[0]:pos[0] + len(ts)] * sd[:, None])[:, None, :].to(device)
+        pos[0] += len(ts)
+        return out.contiguous()
+    m._sgld_noise = noise
+    m.infer(verbose=False)
+    samples, _ = m.all_bayes_samples[-1]
+    assert pos[0] == burn + 1 and samples.shape == g["sgldr_samples"].shape
+    # the step multiplies the gradient's relative error by |eps/2 grad| / |w| (up to ~10 on the stiff posteriors)
+    hold("k4_sgld_repro", name, "samples", rel_err(samples.numpy(), g["sgldr_samples"]).max(), 1e-4)
+    hold("k4_sgld_repro", name, "final", rel_err(m.weights.detach().numpy()[None], g["sgldr_final"][None]).max(), 1e-4)
 
 
 @pytest.mark.parametrize("tensor", [0, 1], ids=["simt", "tcgen05"])
@@ -226,15 +258,18 @@ def test_k3_svgd(name, tensor):
     assert bool(st["tensor"]) == bool(tensor)
     # bandwidth: exact lower median -> h equal to the reference's to fp32 rounding
     h = E.svgd_bandwidth(st["X"], st["ws"], use_tensor=tensor)
+    arm = "tcgen05" if tensor else "simt"
     h_tol = 2e-6 if (tensor == 0 or m.nweights <= 64) else 1e-5
-    assert abs(float(h) - g["svgd_h"][0]) <= h_tol * g["svgd_h"][0]
-    assert abs(float(h) - orc.svgd_rbf_h(g["svgd_x0"])) <= h_tol * g["svgd_h"][0]
+    hold("k3_svgd", name, f"{arm}:h_vs_reference", abs(float(h) - g["svgd_h"][0]) / g["svgd_h"][0], h_tol)
+    hold("k3_svgd", name, f"{arm}:h_vs_oracle", abs(float(h) - orc.svgd_rbf_h(g["svgd_x0"])) / g["svgd_h"][0], h_tol)
     for ep in range(1, 4):
         m.svgd_epoch(st, ep, True, use_tensor=tensor)
         if ep == 1:
-            assert rel_err(st["phi"].cpu().numpy(), g["svgd_phi"][0]).max() < 2e-5
-        assert abs(float(st["h"]) - g["svgd_h"][ep - 1]) <= 1e-4 * g["svgd_h"][ep - 1]
-    assert np.abs(st["X"].cpu().numpy() - g["svgd_final"]).max() < 5e-3 * max(1.0, np.abs(g["svgd_final"]).max())
+            hold("k3_svgd", name, f"{arm}:phi_vs_reference", rel_err(st["phi"].cpu().numpy(), g["svgd_phi"][0]).max(), 2e-5)
+        hold("k3_svgd", name, f"{arm}:h_epoch{ep}", abs(float(st["h"]) - g["svgd_h"][ep - 1]) / g["svgd_h"][ep - 1], 1e-4)
+    # three Adagrad steps: the first is exactly -lr sign(phi) (acc = phi^2), so a component of phi whose magnitude is at the
+    # fp32 noise floor can flip a coordinate by 2 lr; the bound is on the whole particle matrix
+    hold("k3_svgd", name, f"{arm}:final_particles", np.abs(st["X"].cpu().numpy() - g["svgd_final"]).max() / max(1.0, np.abs(g["svgd_final"]).max()), 5e-3)
 
 
 def test_k3_median_select_and_phi_at_scale():
@@ -271,12 +306,13 @@ def test_k5_bbb(name):
     W = E.bbb_sample(qp, t2d(g["bbb_eps"][0]))
     lp, G = m.engine_problem().logpost_grad(W, (1 % nb, nb) if nb else (0, 1), True)
     gq, elbo = E.bbb_reduce(qp, t2d(g["bbb_eps"][0]), lp, G, 5)
-    assert abs(float(elbo) - g["bbb_elbos"][0]) <= 2e-5 * abs(g["bbb_elbos"][0])
-    assert abs(float(elbo) - elbo_o) <= 1e-5 * abs(elbo_o)
-    assert rel_err(gq.cpu().numpy().T, grad_o.T).max() < 2e-5
-    elbos = [float(m.bbb_epoch(qp, acc, t2d(g["bbb_eps"][ep - 1]), ep, True, k_total=5)) for ep in range(1, 4)]
-    assert abs(elbos[0] - g["bbb_elbos"][0]) <= 2e-5 * abs(g["bbb_elbos"][0])
-    assert np.abs(qp.cpu().numpy() - g["bbb_qparams"]).max() < 5e-3 * max(1.0, np.abs(g["bbb_qparams"]).max())
+    hold("k5_bbb", name, "elbo_vs_reference", abs(float(elbo) - g["bbb_elbos"][0]) / abs(g["bbb_elbos"][0]), 2e-5)
+    hold("k5_bbb", name, "elbo_vs_f64_oracle", abs(float(elbo) - elbo_o) / abs(elbo_o), 1e-5)
+    hold("k5_bbb", name, "grad_vs_f64_oracle", rel_err(gq.cpu().numpy().T, grad_o.T).max(), 2e-5)
+    state = {}
+    elbos = [float(m.bbb_epoch(qp, acc, t2d(g["bbb_eps"][ep - 1]), ep, True, k_total=5, state=state)) for ep in range(1, 4)]
+    hold("k5_bbb", name, "step_elbo_vs_reference", abs(elbos[0] - g["bbb_elbos"][0]) / abs(g["bbb_elbos"][0]), 2e-5)
+    hold("k5_bbb", name, "q_params", np.abs(qp.cpu().numpy() - g["bbb_qparams"]).max() / max(1.0, np.abs(g["bbb_qparams"]).max()), 5e-3)
 
 
 def test_bbb_infer_matches_reference_stream():
@@ -286,11 +322,11 @@ def test_bbb_infer_matches_reference_stream():
     m = make_model(name, g, sampler="BBB", bbb_epochs=3, bbb_esamples=5, infer_nsamples=4)
     torch.manual_seed(21)
     m.infer(verbose=False)
-    assert np.abs(m.q_params.numpy() - g["bbb_qparams"]).max() < 5e-3 * max(1.0, np.abs(g["bbb_qparams"]).max())
+    hold("bbb_infer", name, "q_params", np.abs(m.q_params.numpy() - g["bbb_qparams"]).max() / max(1.0, np.abs(g["bbb_qparams"]).max()), 5e-3)
     s, nm = m.all_bayes_samples[-1]
     assert nm.startswith("bbb_") and s.shape == g["bbb_samples"].shape
-    assert np.abs(s.numpy() - g["bbb_samples"]).max() < 2e-2 * max(1.0, np.abs(g["bbb_samples"]).max())
-    assert abs(m.elbos[0] - g["bbb_elbos"][0]) <= 2e-5 * abs(g["bbb_elbos"][0])
+    hold("bbb_infer", name, "samples", np.abs(s.numpy() - g["bbb_samples"]).max() / max(1.0, np.abs(g["bbb_samples"]).max()), 2e-2)
+    hold("bbb_infer", name, "elbo", abs(m.elbos[0] - g["bbb_elbos"][0]) / abs(g["bbb_elbos"][0]), 2e-5)
 
 
 def test_full_size_properties():
@@ -331,14 +367,14 @@ def test_k6_aocp_objective_and_learning(name):
     m = make_model(name, g)
     m._aocp_params = torch.tensor(g["aocp_params"])
     loss, grad = gaussian_aocp_objective(m)
-    assert abs(float(loss) - float(g["aocp_loss"])) <= 5e-5 * max(abs(float(g["aocp_loss"])), 1e-3)
-    assert rel_err(grad.cpu().numpy().T, g["aocp_grad"].T).max() < 5e-4
+    hold("k6_aocp", name, "loss_vs_reference", abs(float(loss) - float(g["aocp_loss"])) / max(abs(float(g["aocp_loss"])), 1e-3), 5e-5)
+    hold("k6_aocp", name, "grad_vs_reference", rel_err(grad.cpu().numpy().T, g["aocp_grad"].T).max(), 5e-4)
     assert abs(float(m.gaussian_aocp_objective()) - float(g["aocp_loss"])) <= 5e-5 * max(abs(float(g["aocp_loss"])), 1e-3)
     m.update_config(aocp_nepochs=3)
     torch.manual_seed(11)
     m.learn_gaussian_aocp(verbose=False)
-    assert np.abs(m._aocp_params.numpy() - g["aocp_learn_params"]).max() < 5e-3 * max(1.0, np.abs(g["aocp_learn_params"]).max())
-    assert np.abs(m.aocp_mean.numpy() - g["aocp_learn_mean"]).max() < 5e-3 * max(1.0, np.abs(g["aocp_learn_mean"]).max())
+    hold("k6_aocp", name, "learned_params", np.abs(m._aocp_params.numpy() - g["aocp_learn_params"]).max() / max(1.0, np.abs(g["aocp_learn_params"]).max()), 5e-3)
+    hold("k6_aocp", name, "learned_mean", np.abs(m.aocp_mean.numpy() - g["aocp_learn_mean"]).max() / max(1.0, np.abs(g["aocp_learn_mean"]).max()), 5e-3)
     import os
     assert os.path.exists(f"history/{m.uid}_aocp.pt")
 
@@ -354,8 +390,8 @@ def test_k6_aocp_at_recid_scale():
     loss, grad = gaussian_aocp_objective(m)
     xs = g["cr_cr_prob_xsamples"]
     lo, go = orc.aocp_objective_binary(spec, g["aocp_params"], prob=dict(xs=xs, p=xs[:, 1]), dtype=np.float64)
-    assert abs(float(loss) - lo) <= 2e-5 * abs(lo)
-    assert rel_err(grad.cpu().numpy().T, go.T).max() < 1e-4
+    hold("k6_aocp", name, "loss_vs_f64_oracle", abs(float(loss) - lo) / abs(lo), 2e-5)
+    hold("k6_aocp", name, "grad_vs_f64_oracle", rel_err(grad.cpu().numpy().T, go.T).max(), 1e-4)
 
 
 def test_hmc_run_host_samples_and_svgd_graph_equivalence():
