@@ -93,6 +93,76 @@ def main():
             print(f"SVGD tensor path {wl} n={n_t}: bandwidth bit-identical (bracket select x{world}, radix select x{world}, 1 rank) = {h_same}, "
                   f"particles rel diff {rel:.2e}")
 
+    # ---- SVGD: CUDA-graph replay of the multi-rank epoch (the NCCL collectives ocbnn_svgd_step issues are captured with the
+    # kernels) against the same ranks running eagerly: same work split, so bit-identical -----------------------------------------
+    mg = workloads.build("W4", seed=0, infer_nsamples=1500)
+    Xg = torch.randn(1500, mg.nweights, generator=g)
+    mg.update_config(svgd_graph=True)
+    stg = mg.svgd_setup(Xg, use_tensor=1)
+    for ep in range(1, 7):
+        mg.svgd_epoch(stg, ep, True)
+    captured = any(not isinstance(v, str) for v in stg.get("graphs", {}).values())
+    mg.update_config(svgd_graph=False)
+    ste = mg.svgd_setup(Xg, use_tensor=1)
+    for ep in range(1, 7):
+        mg.svgd_epoch(ste, ep, True)
+    same = torch.equal(stg["Xall"], ste["Xall"]) and torch.equal(stg["h"], ste["h"])
+    ok &= captured and same
+    if rank == 0:
+        print(f"SVGD graph replay x{world} vs eager x{world} (n=1500, 6 epochs): captured = {captured}, bit-identical = {same}")
+
+    # ---- infer() end to end: HMC / SGLD with host RNG (streams defined over all chains -> N ranks = 1 rank bit for bit, ragged
+    # shares and nchains < world included), SVGD and BBB replicated state independent of per-rank seeding ----------------------
+    import copy
+    for nch in (5, 1):
+        outs = {}
+        for arm in ("sharded", "single"):
+            if arm == "single":
+                D.active = lambda: False
+            mi = workloads.build("W2", seed=0, nchains=nch, hmc_nburnin=2, infer_nsamples=6, hmc_ninterval=2, hmc_l=5, rng="host")
+            torch.manual_seed(123)
+            import numpy as _np
+            _np.random.seed(123)
+            mi.infer(verbose=False)
+            outs[arm] = mi.all_bayes_samples[-1][0].clone()
+            D.active = saved
+        same = torch.equal(outs["sharded"], outs["single"])
+        ok &= same
+        if rank == 0:
+            print(f"HMC infer() nchains={nch} x{world} ranks vs 1 rank (host RNG, same seed): bit-identical = {same}")
+    outs = {}
+    for arm in ("sharded", "single"):
+        if arm == "single":
+            D.active = lambda: False
+        mi = workloads.build("W1", sampler="SGLD", seed=0, nchains=3, sgld_nburnin=3, infer_nsamples=4, sgld_ninterval=2, rng="host")
+        torch.manual_seed(321)
+        mi.infer(verbose=False)
+        outs[arm] = mi.all_bayes_samples[-1][0].clone()
+        D.active = saved
+    same = torch.equal(outs["sharded"], outs["single"])
+    ok &= same
+    if rank == 0:
+        print(f"SGLD infer() nchains=3 x{world} ranks vs 1 rank: bit-identical = {same}")
+    # ranks seeded DIFFERENTLY: replicated state (SVGD particles, BBB q_params) must still agree across ranks
+    mi = workloads.build("W4", seed=0, infer_nsamples=64, svgd_epochs=3)
+    torch.manual_seed(1000 + rank)
+    mi.infer(verbose=False)
+    pr = mi.particles.to(dev)
+    p0_ = pr.clone()
+    dist.broadcast(p0_, src=0)
+    same = torch.equal(pr, p0_)
+    ok &= same
+    mi = workloads.build("W1", sampler="BBB", seed=0, bbb_epochs=4, bbb_esamples=8, infer_nsamples=3)
+    torch.manual_seed(2000 + rank)
+    mi.infer(verbose=False)
+    qr = mi.q_params.to(dev)
+    q0_ = qr.clone()
+    dist.broadcast(q0_, src=0)
+    same_q = torch.equal(qr, q0_)
+    ok &= same_q
+    if rank == 0:
+        print(f"ranks seeded differently: SVGD particles identical on all ranks = {same}, BBB q_params identical = {same_q}")
+
     # ---- BBB: all-reduce of the (D,2) gradient ----------------------------------------------------------------------------
     mb = workloads.build("W1", sampler="BBB", seed=0)
     k = 64
