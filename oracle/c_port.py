@@ -39,7 +39,71 @@ def lib():
         _lib.oc_logpost_grad.argtypes = [C.POINTER(oc_spec), _fp, C.c_int, C.c_int, _fp, _fp]
         _lib.oc_hmc_iterate.argtypes = [C.POINTER(oc_spec), _fp, _fp, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                                         C.POINTER(C.c_ubyte)]
+        _lib.oc_svgd_pair_dists.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp]
+        _lib.oc_svgd_pair_dists.restype = C.c_long
+        _lib.oc_svgd_phi_rows.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _fp]
     return _lib
+
+
+def _fan_out(n_rows, threads, fn, balance_triangle=False):
+    """fn(lo, hi) over `threads` contiguous row ranges (equal pair counts of the i<j triangle when balance_triangle)."""
+    threads = max(1, min(int(threads), n_rows))
+    if balance_triangle:            # rows [0, r) of the upper triangle hold r n - r(r+1)/2 pairs: cut at equal areas
+        n = n_rows
+        tot = n * (n - 1) / 2
+        cuts = [0]
+        for t in range(1, threads):
+            target = tot * t / threads
+            r = int(n - 0.5 - math.sqrt(max((n - 0.5) ** 2 - 2 * target, 0.0)))
+            cuts.append(min(max(r, cuts[-1]), n))
+        cuts.append(n)
+        bounds = list(zip(cuts[:-1], cuts[1:]))
+    else:
+        bounds = [(n_rows * t // threads, n_rows * (t + 1) // threads) for t in range(threads)]
+    if threads == 1:
+        return [fn(*bounds[0])]
+    import concurrent.futures as cf
+    with cf.ThreadPoolExecutor(threads) as ex:
+        return list(ex.map(lambda b: fn(*b), bounds))
+
+
+def svgd_rbf_h(X, threads=1):
+    """h = med^2 / ln n, med = LOWER median of the nonzero ||x_i - x_j + 1e-6||, i < j (inference.py:208-217)."""
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    n, d = X.shape
+
+    def run(lo, hi):
+        cnt = sum(n - 1 - i for i in range(lo, hi))
+        out = np.empty(cnt, dtype=np.float32)
+        k = lib().oc_svgd_pair_dists(X.ctypes.data_as(_fp), n, d, lo, hi, out.ctypes.data_as(_fp))
+        assert k == cnt
+        return out
+    dist = np.concatenate(_fan_out(n, threads, run, balance_triangle=True))
+    dist = dist[dist != 0]
+    k = (len(dist) - 1) // 2
+    med = np.partition(dist, k)[k]
+    return np.float32(med * med) / np.float32(math.log(n))
+
+
+def svgd_phi(X, G, h, threads=1):
+    X, G = np.ascontiguousarray(X, dtype=np.float32), np.ascontiguousarray(G, dtype=np.float32)
+    n, d = X.shape
+
+    def run(lo, hi):
+        out = np.empty((hi - lo, d), dtype=np.float32)
+        lib().oc_svgd_phi_rows(X.ctypes.data_as(_fp), G.ctypes.data_as(_fp), n, d, float(h), lo, hi, out.ctypes.data_as(_fp))
+        return out
+    return np.concatenate(_fan_out(n, threads, run), 0)
+
+
+def svgd_step(cspec, X, acc, lr, with_data=True, threads=1):
+    """One SVGD epoch + Adagrad (full batch): the C counterpart of ocbnn_oracle.svgd_step."""
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    G = np.concatenate(_fan_out(X.shape[0], threads, lambda lo, hi: cspec.logpost_grad(X[lo:hi], with_data)[1]), 0)
+    h = svgd_rbf_h(X, threads)
+    phi = svgd_phi(X, G, h, threads)
+    Xn, accn = orc.adagrad_step(X, np.asarray(acc, dtype=np.float32), -phi, lr, np.float32)
+    return Xn, accn, phi, h
 
 
 class CSpec:

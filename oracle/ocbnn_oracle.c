@@ -233,3 +233,41 @@ void oc_hmc_iterate(const oc_spec *s, float *q, const float *p0, const double *u
         free(p);
     }
 }
+
+/* ---- SVGD (inference.py:208-259), row ranges so that the caller can fan rows out over host threads -------------------- */
+/* distances ||x_i - x_j + 1e-6|| of the pairs i < j with i in [row_begin, row_end), appended to out; returns their number */
+long oc_svgd_pair_dists(const float *x, int n, int d, int row_begin, int row_end, float *out) {
+    long k = 0;
+    for (int i = row_begin; i < row_end; ++i)
+        for (int j = i + 1; j < n; ++j) {
+            float acc = 0.f;
+            for (int c = 0; c < d; ++c) {
+                const float e = x[(long)i * d + c] - x[(long)j * d + c] + 1e-6f;
+                acc += e * e;
+            }
+            out[k++] = sqrtf(acc);
+        }
+    return k;
+}
+
+/* phi_i = (1/n) sum_j [K_ji g_j - (2/h) K_ji (x_j - x_i)],  K_ji = exp(-||x_j - x_i||^2 / h), rows i in [row_begin, row_end) */
+void oc_svgd_phi_rows(const float *x, const float *g, int n, int d, float h, int row_begin, int row_end, float *phi) {
+    const float c2 = 2.f / h, invn = 1.f / (float)n;
+    float *acc = (float *)malloc(sizeof(float) * d);
+    for (int i = row_begin; i < row_end; ++i) {
+        memset(acc, 0, sizeof(float) * d);
+        const float *xi = x + (long)i * d;
+        for (int j = 0; j < n; ++j) {
+            const float *xj = x + (long)j * d, *gj = g + (long)j * d;
+            float d2 = 0.f;
+            for (int c = 0; c < d; ++c) {
+                const float e = xj[c] - xi[c];
+                d2 += e * e;
+            }
+            const float k = expf(-d2 / h);
+            for (int c = 0; c < d; ++c) acc[c] += k * (gj[c] - c2 * (xj[c] - xi[c]));
+        }
+        for (int c = 0; c < d; ++c) phi[(long)(i - row_begin) * d + c] = acc[c] * invn;
+    }
+    free(acc);
+}

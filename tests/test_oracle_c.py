@@ -39,3 +39,20 @@ def test_c_port_hmc(name):
         q32, _, _ = orc.hmc_iterate(spec, q0, g["hmc_p0"][it][None, None], g["hmc_u"][it][None, None], cfg["hmc_epsilon"], L)
         assert bool(acc[0, 0]) == bool(g["hmc_acc"][it])
         assert rel_err(q, g["hmc_q"][it][None]).max() < max(1e-4, 4 * rel_err(q32, q64).max())
+
+
+@pytest.mark.parametrize("name", ["f3b_reg_neg2", "w1_reg_vanilla", "bin_vanilla"])
+def test_c_port_svgd(name):
+    """The C SVGD epoch (bench.py's multi-core CPU baseline for the SVGD metric) against the reference's golden vectors."""
+    g = load_golden(name)
+    spec = spec_from_golden(name, g)
+    cfg = golden_config(g)
+    cs = c_port.CSpec(spec)
+    X, acc = g["svgd_x0"].copy(), np.zeros_like(g["svgd_x0"])
+    for threads in (1, 3):
+        h = c_port.svgd_rbf_h(g["svgd_x0"], threads)
+        assert abs(h - g["svgd_h"][0]) <= 2e-6 * g["svgd_h"][0]
+    Xn, accn, phi, h = c_port.svgd_step(cs, X, acc, cfg["svgd_init_lr"], True, threads=2)
+    assert rel_err(phi, g["svgd_phi"][0]).max() < 2e-5
+    Xo, _, phi_o, h_o = orc.svgd_step(spec, X, acc, cfg["svgd_init_lr"], None, True)
+    assert abs(h - h_o) <= 2e-6 * h_o and rel_err(phi, phi_o).max() < 2e-5
