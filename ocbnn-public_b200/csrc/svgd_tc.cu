@@ -145,16 +145,18 @@ static int pick_splits(long long n_rows, long long n4, int two_dp, int bn) {
 long long tc_workspace_bytes(long long n, long long d, long long n_rows);      // K splits of the fused phi kernel (defined with it)
 
 constexpr int kSelSamplesHost = 32768;      // = kSelSamples (pair sample of the bracket select, defined with its kernels)
-constexpr int kSelSamplesMaxHost = 1 << 20;
+constexpr int kSelSamplesMaxHost = 1 << 17;
 // work split of the flash phi kernel: `tiles` 128-row tiles per CTA (2 when D <= 32 and there are enough rows to fill the
 // SMs that way), column blocks of 64 particles, at most 8 of them (512 columns) accumulated into one TMEM accumulator
 static void flash_plan(long long n, long long n_rows, int dp, int* tiles, int* splits, int* per, int* nj_total) {
     const int nj = (int)((n + 63) / 64);
-    const int t = (dp == 32 && n_rows >= 3072) ? 2 : 1;
+    const int t = (dp == 32 && n_rows > 128) ? 2 : 1;
     const long long row_blocks = (n_rows + 128 * t - 1) / (128 * t);
-    int p = 8;                                                   // column blocks per split (accumulation chain limit)
-    const long long want = (148 + row_blocks - 1) / row_blocks;  // splits needed to put a CTA on every SM
-    if (want > (nj + p - 1) / p) p = (int)((nj + want - 1) / want);
+    // as many column splits as fit ONE wave of 148 CTAs (a 149th CTA would double the kernel time).  A CTA walks all column blocks
+    // of its split; the accumulation chain limit is handled inside the kernel (accumulators drained every kFlashChainBlocks blocks).
+    long long want = 148 / row_blocks;
+    if (want < 1) want = 1;
+    int p = (int)((nj + want - 1) / want);
     if (p < 1) p = 1;
     *tiles = t;
     *per = p;
@@ -325,6 +327,33 @@ __device__ __forceinline__ float pair_w(float d2v, float si, float sj, int d) { 
 __device__ __forceinline__ float pair_dist(const float* __restrict__ d2, const float* __restrict__ ssum, long long n4, int d, long long i, long long j) {
     return pair_w(d2[i * n4 + j], ssum[i], ssum[j], d);
 }
+// THE exact squared distance of the flash path (D <= 64), one definition for every evaluator (bracket sample, counting kernel,
+// fallback select) so that they agree bit for bit: per 32-float block, eight partial sums - one per 16-byte chunk, e0^2 then
+// three sequential fmas - combined by the xor-butterfly tree ((p0+p1)+(p2+p3))+((p4+p5)+(p6+p7)); blocks are added in order.
+// The tree is what eight cooperating lanes compute with three shuffles (fp32 addition is commutative, so every lane of the
+// butterfly holds the same bits), which lets the counting kernel read its operand rows conflict-free.
+__device__ __forceinline__ float d2_chunk(const float4 a, const float4 b) {
+    float e = a.x - b.x;
+    float p = __fmul_rn(e, e);
+    e = a.y - b.y; p = fmaf(e, e, p);
+    e = a.z - b.z; p = fmaf(e, e, p);
+    e = a.w - b.w; p = fmaf(e, e, p);
+    return p;
+}
+__device__ __forceinline__ float d2_block32(const float4* __restrict__ a4, const float4* __restrict__ b4) {
+    float p[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) p[c] = d2_chunk(__ldg(a4 + c), __ldg(b4 + c));
+    return __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1]), __fadd_rn(p[2], p[3])), __fadd_rn(__fadd_rn(p[4], p[5]), __fadd_rn(p[6], p[7])));
+}
+__device__ __forceinline__ float d2_exact_rows(const float* __restrict__ xc, int dp, long long i, long long j) {
+    const float4* a4 = reinterpret_cast<const float4*>(xc + i * dp);
+    const float4* b4 = reinterpret_cast<const float4*>(xc + j * dp);
+    float acc = d2_block32(a4, b4);
+    for (int kb = 1; kb < dp / 32; ++kb) acc = __fadd_rn(acc, d2_block32(a4 + 8 * kb, b4 + 8 * kb));
+    return acc;
+}
+
 // distance source of the select's fallback: the materialised matrix (D > 64) or, on the flash path, the centred particles
 // themselves (exact fp32 differences, the arithmetic of exact_d2 in svgd_flash.cuh)
 struct DistSrc {
@@ -334,17 +363,7 @@ struct DistSrc {
     int dp;
     __device__ __forceinline__ float operator()(const float* __restrict__ ssum, int d, long long i, long long j) const {
         if (d2) return pair_w(d2[(i - row_off) * n4 + j], ssum[i], ssum[j], d);
-        const float4* a4 = reinterpret_cast<const float4*>(xc + i * dp);
-        const float4* b4 = reinterpret_cast<const float4*>(xc + j * dp);
-        float acc = 0.f;
-        for (int c = 0; c < dp / 4; ++c) {
-            const float4 a = __ldg(a4 + c), b = __ldg(b4 + c);
-            float e;
-            e = a.x - b.x; acc = fmaf(e, e, acc);
-            e = a.y - b.y; acc = fmaf(e, e, acc);
-            e = a.z - b.z; acc = fmaf(e, e, acc);
-            e = a.w - b.w; acc = fmaf(e, e, acc);
-        }
+        const float acc = d2_exact_rows(xc, dp, i, j);
         return pair_w(acc, ssum[i], ssum[j], d);
     }
 };
@@ -682,17 +701,7 @@ k_sel_sample_x(const float* __restrict__ xc, const float* __restrict__ ssum, lon
     long long i = (long long)(a % (unsigned)n), j = (long long)(b % (unsigned)n);
     if (i == j) j = (j + 1) % n;
     if (i > j) { const long long tmp = i; i = j; j = tmp; }
-    const float4* x4 = reinterpret_cast<const float4*>(xc);
-    float acc = 0.f;
-#pragma unroll
-    for (int c = 0; c < DP / 4; ++c) {
-        const float4 a = __ldg(x4 + i * (DP / 4) + c), b = __ldg(x4 + j * (DP / 4) + c);
-        float e;
-        e = a.x - b.x; acc = fmaf(e, e, acc);
-        e = a.y - b.y; acc = fmaf(e, e, acc);
-        e = a.z - b.z; acc = fmaf(e, e, acc);
-        e = a.w - b.w; acc = fmaf(e, e, acc);
-    }
+    const float acc = d2_exact_rows(xc, DP, i, j);
     samples[idx] = pair_w(acc, ssum[i], ssum[j], d);
 }
 
@@ -825,12 +834,13 @@ __device__ __forceinline__ float ex2_fast(float x) {
 namespace ocbnn {
 namespace tc {
 
-// pairs sampled for the bracket of the median select: 32768 up to n = 4096, then proportional to the pair count (the
-// bracket holds 5.6 sigma of the sample-rank error = 2.8 / sqrt(samples) of all pairs on each side, and every pair inside it
-// is re-evaluated exactly), capped at 2^20
+// pairs sampled for the bracket of the median select: 8192 up to n = 4096, then proportional to the pair count, capped at 2^17.
+// The bracket holds 5.6 sigma of the sample-rank error = 2.8 / sqrt(samples) of all pairs on each side (6 % of the pairs at 8192
+// samples, 1.5 % at 2^17); every pair inside it is re-evaluated exactly out of shared memory by the counting kernel, which is
+// cheap - the one-CTA bracket kernel over a large sample was not (165 us for 2^20 samples at n = 32768).
 static int sel_samples(long long n) {
-    long long s = n * n / 512;
-    if (s < kSelSamplesHost) s = kSelSamplesHost;
+    long long s = n * n / 2048;
+    if (s < 8192) s = 8192;
     if (s > kSelSamplesMaxHost) s = kSelSamplesMaxHost;
     return (int)(s / 1024 * 1024);
 }
@@ -840,7 +850,9 @@ static DistSrc dist_src(const TcWs& w) { return DistSrc{w.d2, w.xc, w.n4, w.row_
 // centre + split X (every rank holds all particles); D > 64: also the squared distances of rows [row_begin, row_begin + n_rows)
 // by the Gram GEMM on the tensor cores.  D <= 64: nothing else - the select and phi recompute their tiles (svgd_flash.cuh).
 static int tc_prepare(const TcWs& w, const float* x, cudaStream_t st) {
-    k_colmean<<<(unsigned)w.dp, 256, 0, st>>>(x, w.n, (int)w.d, (int)w.dp, w.mean);
+    // centre = column means of the first min(n, 1024) particles: phi is translation invariant and the centre only has to sit inside
+    // the cloud (it removes the cancellation in r_i + r_j - 2 S); a full-column mean would be a 24 us latency chain at n = 32768
+    k_colmean<<<(unsigned)w.dp, 256, 0, st>>>(x, w.n < 1024 ? w.n : 1024, (int)w.d, (int)w.dp, w.mean);
     OCBNN_LAUNCH_CHECK();
     k_center_split<<<(unsigned)((w.n * 32 + 255) / 256), 256, 0, st>>>(x, w.mean, w.n, (int)w.d, (int)w.dp, w.xc, w.xc_hi, w.xc_lo, w.r, w.s);
     OCBNN_LAUNCH_CHECK();
@@ -868,6 +880,11 @@ static int sel_bracket(const TcWs& w, int mode, cudaStream_t st) {
     return OCBNN_OK;
 }
 
+static int count_dbg() {        // OCBNN_COUNT_DBG: timing probes of k_count_tc (1 no classification, 2 no exact re-evaluation, 4 no MMAs)
+    static const int v = [] { const char* e = getenv("OCBNN_COUNT_DBG"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
 // counting pass of this rank's share of the pairs.  Flash path: the 128 x 128 tiles on or above the diagonal, dealt out
 // cyclically (tile index % world == rank); D > 64: the rows [row_begin, row_begin + n_rows) of the materialised distances.
 static int sel_count(const TcWs& w, int rank, int world, cudaStream_t st) {
@@ -891,16 +908,25 @@ static int sel_count(const TcWs& w, int rank, int world, cudaStream_t st) {
     if (w.dp == 32) {
         auto kern = k_count_tc<32>;
         OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CountCfg<32>::kSmemBytes));
-        kern<<<(unsigned)mine, kCntThreads, CountCfg<32>::kSmemBytes, st>>>(tm_hi, tm_lo, w.xc, w.r, w.s, w.n, (int)w.d, T, rank, world, hdr, w.cand,
-                                                                          w.cand_cap, w.ghist);
+        const long long grid = mine < 148 * CountCfg<32>::kCtasPerSm ? mine : 148 * CountCfg<32>::kCtasPerSm;
+        kern<<<(unsigned)grid, kCntThreads, CountCfg<32>::kSmemBytes, st>>>(tm_hi, tm_lo, w.r, w.s, w.n, (int)w.d, T, rank, world, mine, hdr, w.cand,
+                                                                          w.cand_cap, w.ghist, count_dbg());
     } else {
         auto kern = k_count_tc<64>;
         OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CountCfg<64>::kSmemBytes));
-        kern<<<(unsigned)mine, kCntThreads, CountCfg<64>::kSmemBytes, st>>>(tm_hi, tm_lo, w.xc, w.r, w.s, w.n, (int)w.d, T, rank, world, hdr, w.cand,
-                                                                          w.cand_cap, w.ghist);
+        const long long grid = mine < 148 * CountCfg<64>::kCtasPerSm ? mine : 148 * CountCfg<64>::kCtasPerSm;
+        kern<<<(unsigned)grid, kCntThreads, CountCfg<64>::kSmemBytes, st>>>(tm_hi, tm_lo, w.r, w.s, w.n, (int)w.d, T, rank, world, mine, hdr, w.cand,
+                                                                          w.cand_cap, w.ghist, count_dbg());
     }
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
+}
+
+// experiment switch (OCBNN_FLASH_DBG, bit mask; 0 = the real kernel): 1 SIMT warps only hand the buffers on, 2 no O MMAs, 4 no S
+// MMAs, 8 no TMEM load, 16 no TMEM store - timing probes for the phase costs, results are garbage
+static int flash_dbg() {
+    static const int v = [] { const char* e = getenv("OCBNN_FLASH_DBG"); return e ? atoi(e) : 0; }();
+    return v;
 }
 
 template <int DP, int TILES>
@@ -916,7 +942,7 @@ static int launch_flash(const TcWs& w, const float* h, cudaStream_t st) {
     OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     dim3 grid((unsigned)((w.n_rows + 128 * TILES - 1) / (128 * TILES)), (unsigned)w.fl_splits);
     kern<<<grid, kFlashThreads, Cfg::kSmemBytes, st>>>(xj_hi, xj_lo, vt_hi, vt_lo, w.xc_hi, w.xc_lo, w.r, w.ncr, h, w.n, w.row_begin, w.n_rows, w.o,
-                                                     w.k_hi, w.fl_nj, w.fl_per);
+                                                     w.k_hi, w.fl_nj, w.fl_per, flash_dbg());
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }
@@ -930,7 +956,7 @@ static int tc_phi(const TcWs& w, const float* g, const float* h, float* phi, cud
         if (w.dp == 32) rc = w.fl_tiles == 2 ? launch_flash<32, 2>(w, h, st) : launch_flash<32, 1>(w, h, st);
         else rc = launch_flash<64, 1>(w, h, st);
         if (rc) return rc;
-        k_phi_finalize<<<grid_for_ll(w.n_rows * w.d), 256, 0, st>>>(w.o, w.fl_splits, w.k_hi, w.fl_splits * (w.fl_tiles == 2 ? 1 : 2), w.xc_hi, w.xc_lo, h,
+        k_phi_finalize<<<grid_for_ll(w.n_rows * w.d), 256, 0, st>>>(w.o, w.fl_splits, w.k_hi, 2 * w.fl_splits, w.xc_hi, w.xc_lo, h,
                                                                   w.n, (int)w.d, (int)w.dp, w.row_begin, w.n_rows, phi);
         OCBNN_LAUNCH_CHECK();
         return OCBNN_OK;
@@ -979,6 +1005,7 @@ int tc_svgd_select_local(long long n, long long d, void* ws, float* out_h, int m
     int rc;
     if ((rc = sel_bracket(w, mode, st))) return rc;
     if (mode == 1 && (rc = sel_count(w, 0, 1, st))) return rc;
+    if (count_dbg()) return OCBNN_OK;          // timing probe: the counters are garbage, do not let the select fall back on them
     k_sel_gather<<<148, 256, 0, st>>>(n, hdr, w.ghist, w.cand, w.list2, w.cand_cap, 0, dist_src(w), w.s, (int)d, out_h, dbg);      // gather + final
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;

@@ -23,6 +23,22 @@ constexpr uint32_t kSpinLimit = 1u << 28;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp.  TMA / tcgen05 instructions take their operands from uniform registers; issued under a
+// `lane == 0` branch the compiler cannot prove the region is single-threaded and wraps EVERY such instruction in an
+// ELECT / branch "waterfall" loop (measured: ~100 clk per tcgen05.mma instead of the 32-64 clk the tensor pipe needs).
+// elect.sync tells it.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// warp index, known to be warp-uniform by the compiler
+__device__ __forceinline__ int warp_idx_sync() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -134,7 +150,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t bars = base + Cfg::kStages * Cfg::kStageBytes;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + Cfg::kStages * Cfg::kStageBytes + 8 * Cfg::kNumBars);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_idx_sync(), lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
     const int kb_begin = blockIdx.z * kb_per_split;
     const int kb_end = min(num_kb, kb_begin + kb_per_split);
@@ -164,7 +180,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
     const uint32_t tmem_d = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % Cfg::kStages;
                 const uint32_t ph = (i / Cfg::kStages) & 1;
@@ -179,7 +195,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc = make_idesc_tf32(kBM, BN);
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % Cfg::kStages;

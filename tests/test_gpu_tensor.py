@@ -44,7 +44,7 @@ def test_svgd_tensor_path_matches_float64_oracle(n, D):
     assert torch.equal(phi_1, phi_t)
     ws_part = E.svgd_workspace(n, D, Xd.device, n_rows=157, use_tensor=1)
     part = E.svgd_phi(Xd, Gd, h_t, 300, 157, ws_part, use_tensor=1)             # a rank's row share
-    assert (part - phi_t[300:457]).norm() / phi_t[300:457].norm() < 2e-6
+    assert (part - phi_t[300:457]).norm() / phi_t[300:457].norm() < 5e-6      # different column splits: fp32 reassociation only
 
 
 def test_svgd_epoch_tensor_vs_simt():
