@@ -832,11 +832,30 @@ def run_reference(args):
             "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": rate, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # libraries write to fd 1 behind Python's back (NCCL prints its version banner there when the engine's own communicator
+    # comes up): everything but the JSON line goes to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     wl = args.workload.upper()
@@ -867,7 +886,7 @@ def main():
         else:
             raise SystemExit(f"unknown workload {wl}")
         if cx.rank == 0:
-            print(json.dumps(line), flush=True)
+            emit(line)
     finally:
         cx.close()
 
