@@ -127,6 +127,25 @@ OCBNN_API int ocbnn_logpost_grad(ocbnn_problem *p, const float *w, int64_t m, in
 /* forward pass f(x; w) for M weight vectors on P points: out (M x P x s_K).  Replaces forward/predict (base.py:89-104,267-277). */
 OCBNN_API int ocbnn_forward(ocbnn_problem *p, const float *w, int64_t m, const float *x, int64_t npoints, float *out, void *stream);
 
+/* predict(): forward + the output head, in the library.  Replaces RegressorMixin.predict (base.py:267-277),
+ * ClassifierMixin.predict (base.py:446-461: softmax over the s_K logits, argmax) and BinaryClassifierMixin.predict
+ * (base.py:544-559: sigmoid of the single logit, p >= 0.5).
+ *   head = OCBNN_PREDICT_RAW   : out (M x P x s_K) network outputs
+ *          OCBNN_PREDICT_PROBS : out (M x P x s_K) softmax probabilities, or (M x P) p(Y=1) for a Bernoulli problem
+ *          OCBNN_PREDICT_CLASS : out holds the raw outputs (scratch), out_class (M x P, int32) the decisions
+ * out_class may also be given with OCBNN_PREDICT_PROBS.  out_mean (P x s_K, or NULL): mean over the M samples of what `out`
+ * holds — the posterior-mean predictive every evaluation of the reference starts from (bnn/utils.py:217-232). */
+#define OCBNN_PREDICT_RAW 0
+#define OCBNN_PREDICT_PROBS 1
+#define OCBNN_PREDICT_CLASS 2
+OCBNN_API int ocbnn_predict(ocbnn_problem *p, const float *w, int64_t m, const float *x, int64_t npoints, int32_t head,
+                  float *out, int32_t *out_class, float *out_mean, void *stream);
+
+/* Constraint-violation flags of posterior samples (the rejection count of run_toys.py:229-250, Figure 3c):
+ * out_flags[m] = 1 when lo < f(x_p; w_m)[0] < hi for any of the P domain points.  scratch: M x P x s_K floats. */
+OCBNN_API int ocbnn_violation_flags(ocbnn_problem *p, const float *w, int64_t m, const float *x, int64_t npoints, float lo, float hi,
+                          float *scratch, uint8_t *out_flags, void *stream);
+
 /* K2 — n_it HMC iterations (L leapfrog steps + Metropolis-Hastings each) for M independent chains.
  * Replaces HMCMixin.single (inference.py:39-78).  q (M x D) in/out; p0 (n_it x M x D) momenta ~N(0,1) and
  * u (n_it x M, float64) uniforms are injected by the host.  restore_on_reject = 0 reproduces the reference

@@ -71,7 +71,7 @@ __global__ void k_axpy_rn(float* __restrict__ y, const float* __restrict__ x, fl
 }
 __global__ void k_hmc_finish(const float* __restrict__ p, const float* __restrict__ lp, float* __restrict__ q, const float* __restrict__ q0,
                              float* __restrict__ hbuf, const double* __restrict__ u, long long m, int d, int restore,
-                             uint8_t* __restrict__ out_acc, float* __restrict__ out_h, int* __restrict__ flags, int* __restrict__ need_eval,
+                             uint8_t* __restrict__ out_acc, float* __restrict__ out_h, int* __restrict__ flags,
                              float* __restrict__ sample_dst) {
     const long long chain = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -94,7 +94,6 @@ __global__ void k_hmc_finish(const float* __restrict__ p, const float* __restric
         if (out_acc) out_acc[chain] = acc ? 1 : 0;
         if (out_h) reinterpret_cast<float4*>(out_h)[chain] = make_float4(U0, K0, U1, K1);
         if (flags && isn) flags[chain] |= 1;
-        if (restore && !acc) *need_eval = 1;
     }
     if (restore && !acc)
         for (int i = lane; i < d; i += 32) q[chain * d + i] = q0[chain * d + i];
@@ -347,14 +346,11 @@ extern "C" OCBNN_API int ocbnn_hmc_iterate(ocbnn_problem* h, float* q, const flo
     // generic nets: K1 (one CTA per chain) + elementwise leapfrog kernels, driven from the host on the caller's stream
     const int d = p.d;
     const long long md = m * d;
-    float *pbuf = nullptr, *gbuf = nullptr, *q0 = nullptr, *lp = nullptr, *hbuf = nullptr;
-    int* need = nullptr;
-    OCBNN_CUDA(cudaMallocAsync(&pbuf, md * sizeof(float), st));
-    OCBNN_CUDA(cudaMallocAsync(&gbuf, md * sizeof(float), st));
-    OCBNN_CUDA(cudaMallocAsync(&q0, md * sizeof(float), st));
-    OCBNN_CUDA(cudaMallocAsync(&lp, m * sizeof(float), st));
-    OCBNN_CUDA(cudaMallocAsync(&hbuf, 4 * m * sizeof(float), st));
-    OCBNN_CUDA(cudaMallocAsync(&need, sizeof(int), st));
+    // one stream-ordered allocation for every temporary (nothing to unwind if it fails): p | grad | q0 | lp | (U0,K0,U1,K1)
+    float* tmp = nullptr;
+    const long long mda = (md + 63) & ~63LL, ma = (m + 63) & ~63LL;      // every segment starts 256-byte aligned
+    OCBNN_CUDA(cudaMallocAsync(&tmp, (size_t)(3 * mda + ma + 4 * m) * sizeof(float), st));
+    float *pbuf = tmp, *gbuf = tmp + mda, *q0 = tmp + 2 * mda, *lp = tmp + 3 * mda, *hbuf = tmp + 3 * mda + ma;
     const unsigned wb = (unsigned)((m * 32 + 255) / 256);
     int rc = OCBNN_OK;
     if (out_flags) { k_zero_i32<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(out_flags, m); count_launch(); }
@@ -376,15 +372,10 @@ extern "C" OCBNN_API int ocbnn_hmc_iterate(ocbnn_problem* h, float* q, const flo
         float* dst = (out_samples && thin > 0 && (it + 1) % thin == 0) ? out_samples + (long long)((it + 1) / thin - 1) * md : nullptr;
         k_hmc_finish<<<wb, 256, 0, st>>>(pbuf, lp, q, q0, hbuf, u + (long long)it * m, m, d, restore_on_reject,
                                          out_accept ? out_accept + (long long)it * m : nullptr, out_h ? out_h + (long long)it * m * 4 : nullptr,
-                                         out_flags, need, dst);
+                                         out_flags, dst);
         count_launch();
     }
-    cudaFreeAsync(pbuf, st);
-    cudaFreeAsync(gbuf, st);
-    cudaFreeAsync(q0, st);
-    cudaFreeAsync(lp, st);
-    cudaFreeAsync(hbuf, st);
-    cudaFreeAsync(need, st);
+    cudaFreeAsync(tmp, st);
     if (rc) return rc;
     OCBNN_CUDA(cudaGetLastError());
     return OCBNN_OK;
@@ -396,6 +387,10 @@ extern "C" OCBNN_API int ocbnn_sgld_iterate(ocbnn_problem* h, float* w, const fl
     OCBNN_REQUIRE(h && w && noise && half_eps && m >= 0 && t_steps >= 0, OCBNN_EINVAL, "ocbnn_sgld_iterate: bad argument");
     OCBNN_REQUIRE(batch_stride <= 1 || batch_offsets, OCBNN_EINVAL, "ocbnn_sgld_iterate: batch_offsets required when batch_stride > 1");
     if (m == 0 || t_steps == 0) return OCBNN_OK;
+    if (batch_stride > 1)
+        for (int t = 0; t < t_steps; ++t)
+            OCBNN_REQUIRE(batch_offsets[t] >= 0 && batch_offsets[t] < batch_stride, OCBNN_EINVAL,
+                          "ocbnn_sgld_iterate: batch_offsets[%d] = %d is outside [0, %d)", t, (int)batch_offsets[t], (int)batch_stride);
     ProblemImpl& p = *reinterpret_cast<ProblemImpl*>(h);
     cudaStream_t st = (cudaStream_t)stream;
     EvalArgs a = eval_args(p, 0, batch_stride, with_data);

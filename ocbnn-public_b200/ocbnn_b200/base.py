@@ -28,44 +28,47 @@ from . import engine as E
 from .compiler import batch_spec, compile_problem
 
 
+# knobs debug_mode() shrinks (value while debugging); the first five are put back by switch_off_debug_mode (base.py:207-242)
+_DEBUG_KNOBS = {"infer_nsamples": 3, "hmc_nburnin": 5, "bbb_epochs": 100, "svgd_epochs": 10, "sgld_nburnin": 5}
+
+
+def _tag(bnn, text):
+    logging.info(f"[{bnn.uid}] {text}")
+
+
 class BayesianNeuralNetwork:
     """Bayesian inference over an MLP.  API of bnn/base.py:27-242."""
 
     def __init__(self, uid="bnn-0", configfile="config.yaml"):
+        """Flat YAML config -> attributes; a copy of it goes to history/{uid}.yaml (base.py:28-48)."""
+        with open(configfile) as fh:
+            settings = yaml.load(fh, Loader=yaml.FullLoader)
         self.uid = uid
-        with open(configfile, "r") as rf:
-            config = yaml.load(rf, Loader=yaml.FullLoader)
-            self.__dict__.update(config)
-        if not os.path.isdir("history"):
-            os.mkdir("history")
-        with open(f"history/{self.uid}.yaml", "w") as wf:
-            yaml.dump(config, wf)
-        self.all_bayes_samples = []
-        self.dconstraints = dict()
-        self.pconstraints = dict()
-        self.aocp_mean = None
-        self.aocp_std = None
-        self._problem = None
-        self._problem_key = None
-        logging.info(f"[{self.uid}] BNN instantiated. Configs saved as `history/{self.uid}.yaml`.")
+        vars(self).update(settings)
+        os.makedirs("history", exist_ok=True)
+        with open(os.path.join("history", f"{uid}.yaml"), "w") as fh:
+            yaml.dump(settings, fh)
+        self.all_bayes_samples, self.dconstraints, self.pconstraints = [], {}, {}
+        self.aocp_mean = self.aocp_std = None
+        self._problem = self._problem_key = None
+        _tag(self, f"BNN instantiated. Configs saved as `history/{self.uid}.yaml`.")
 
     # ---- data ------------------------------------------------------------------------------------------------
-    def load(self, **kwargs):
-        """Loads dataset (base.py:50-70)."""
-        self.__dict__.update(kwargs)
-        self.Xdim = self.X_train.shape[1]
-        self.Ydim = self._Ydim
-        self.N_train = self.Y_train.shape[0]
+    def load(self, **dataset):
+        """Attach a dataset dict (X_train, Y_train, [X_test, Y_test], X_train_min/max, dataset_name ...), derive the layer
+        shapes and draw the initial weights from N(0, sigma_w) — one draw of nweights values, as base.py:50-70."""
+        vars(self).update(dataset)
+        self.Xdim, self.Ydim, self.N_train = self.X_train.shape[1], self._Ydim, self.Y_train.shape[0]
+        counted = f"{self.N_train} training points"
         if hasattr(self, "Y_test"):
             self.N_test = self.Y_test.shape[0]
-            test_stats = f" and {self.N_test} test points"
-        else:
-            test_stats = ""
-        self.layer_sizes = [self.Xdim] + self.architecture + [self.Ydim]
-        self.layer_shapes = list(zip(self.layer_sizes[:-1], self.layer_sizes[1:]))
-        self.nweights = sum((m + 1) * n for m, n in self.layer_shapes)
+            counted += f" and {self.N_test} test points"
+        widths = [self.Xdim, *self.architecture, self.Ydim]
+        self.layer_sizes = widths
+        self.layer_shapes = list(zip(widths, widths[1:]))
+        self.nweights = sum(fan_out * (fan_in + 1) for fan_in, fan_out in self.layer_shapes)
         self.weights = Normal(0, self.sigma_w).sample(torch.Size([self.nweights])).requires_grad_(True)
-        logging.info(f"[{self.uid}] Dataset <{self.dataset_name}> loaded: {self.N_train} training points{test_stats}.")
+        _tag(self, f"Dataset <{self.dataset_name}> loaded: {counted}.")
 
     # ---- engine plumbing ----------------------------------------------------------------------------------------
     def _device(self):
@@ -98,6 +101,10 @@ class BayesianNeuralNetwork:
         if w.ndimension() == 1:
             w = w.unsqueeze(0)
         return w.to(self._device(), torch.float32).contiguous()
+
+    def _predict_operands(self, bayes_samples, domain):
+        W = self._weights_matrix(torch.as_tensor(bayes_samples))
+        return W, torch.as_tensor(domain).to(W.device, torch.float32).contiguous()
 
     # ---- model evaluation (CUDA) -----------------------------------------------------------------------------------
     def forward(self, X, weights=None):
@@ -138,22 +145,20 @@ class BayesianNeuralNetwork:
         return Normal(mean, std).log_prob(weights.detach()).sum()
 
     # ---- constraint point sampling (base.py:135-157) --------------------------------------------------------------------
+    def _region_bounds(self, region):
+        """[(lower, upper)] per input dimension: the region's bound where it is finite, the training range otherwise."""
+        lows, highs = region[0::2], region[1::2]
+        return [(float(lows[d] if lows[d] > -np.inf else self.X_train_min[d]),
+                 float(highs[d] if highs[d] < np.inf else self.X_train_max[d])) for d in range(self.Xdim)]
+
     def _sample_from_hypercube(self, region, nsamples, mode="uniform"):
-        samples = torch.tensor([])
-        for d in range(self.Xdim):
-            lower = self.X_train_min[d]
-            if region[2 * d] > -np.inf:
-                lower = region[2 * d]
-            upper = self.X_train_max[d]
-            if region[2 * d + 1] < np.inf:
-                upper = region[2 * d + 1]
-            lower, upper = float(lower), float(upper)
-            if mode == "uniform":
-                unif = Uniform(lower, upper).sample(torch.Size([nsamples])).unsqueeze(0)
-                samples = torch.cat((samples, unif), 0)
-            elif mode == "even":
-                samples = torch.cat((samples, torch.linspace(lower, upper, nsamples).unsqueeze(0)), 0)
-        return torch.t(samples)
+        """(nsamples, Xdim) points of the hypercube `region` = (lo_0, hi_0, lo_1, hi_1, ...).  'uniform' draws one
+        Uniform(lo, hi) vector per dimension, in dimension order (the reference's RNG order); 'even' is a linspace."""
+        draw = {"uniform": lambda lo, hi: Uniform(lo, hi).sample(torch.Size([nsamples])),
+                "even": lambda lo, hi: torch.linspace(lo, hi, nsamples)}.get(mode)
+        if draw is None:
+            return torch.empty(0)
+        return torch.stack([draw(lo, hi) for lo, hi in self._region_bounds(region)], dim=1)
 
     def _sample_region_blocks(self, constraints):
         """One (ocp_nsamples, Xdim) block per registered constraint, stacked (re-sampled on every add_* call)."""
@@ -167,8 +172,10 @@ class BayesianNeuralNetwork:
 
     # ---- samples / AOCP parameters / config -------------------------------------------------------------------------------
     def load_bayes_samples(self, filename, descriptor="sample"):
-        self.all_bayes_samples.append((torch.load(filename), descriptor))
-        logging.info(f"[{self.uid}] Posterior Sample #{len(self.all_bayes_samples)}: Loaded from `{filename}`.")
+        """Append a saved (M, nweights) sample tensor to all_bayes_samples (base.py:159-162)."""
+        entry = (torch.load(filename), descriptor)
+        self.all_bayes_samples.append(entry)
+        _tag(self, f"Posterior Sample #{len(self.all_bayes_samples)}: Loaded from `{filename}`.")
 
     def _set_aocp(self, params):
         self.aocp_mean = params[:, 0]
@@ -189,40 +196,30 @@ class BayesianNeuralNetwork:
         from .aocp import gaussian_aocp_objective
         return gaussian_aocp_objective(self)[0].cpu()[0]
 
-    def update_config(self, **kwargs):
-        self.__dict__.update(**kwargs)
-        logging.info(f"[{self.uid}] Configs updated.")
+    def update_config(self, **overrides):
+        vars(self).update(overrides)
+        _tag(self, "Configs updated.")
 
     def clear_all_samples(self):
         self.all_bayes_samples = []
-        logging.info(f"[{self.uid}] All posterior samples cleared from memory.")
+        _tag(self, "All posterior samples cleared from memory.")
 
     def debug_mode(self):
-        """Debug mode (base.py:207-222)."""
-        self.old_infer_nsamples = self.infer_nsamples
-        self.old_hmc_nburnin = self.hmc_nburnin
-        self.old_bbb_epochs = self.bbb_epochs
-        self.old_svgd_epochs = self.svgd_epochs
-        self.old_sgld_nburnin = self.sgld_nburnin
-        self.infer_nsamples = 3
-        self.hmc_nburnin = 5
-        self.bbb_epochs = 100
-        self.svgd_epochs = 10
-        self.sgld_nburnin = 5
+        """A few samples / epochs only, to check a pipeline end to end (base.py:207-222); the previous values are kept
+        as old_<name> attributes."""
+        for knob, small in _DEBUG_KNOBS.items():
+            setattr(self, "old_" + knob, getattr(self, knob))
+            setattr(self, knob, small)
         self.aocp_nepochs = 1
-        logging.info(f"[{self.uid}] Debug mode activated.")
+        _tag(self, "Debug mode activated.")
 
     def switch_off_debug_mode(self):
         if not hasattr(self, "old_infer_nsamples"):
             logging.error("You cannot switch off debug mode without having turned it on first!")
             raise Exception
-        self.infer_nsamples = self.old_infer_nsamples
-        self.hmc_nburnin = self.old_hmc_nburnin
-        self.bbb_epochs = self.old_bbb_epochs
-        self.svgd_epochs = self.old_svgd_epochs
-        self.sgld_nburnin = self.old_sgld_nburnin
-        del self.old_infer_nsamples, self.old_hmc_nburnin, self.old_bbb_epochs, self.old_svgd_epochs, self.old_sgld_nburnin
-        logging.info(f"[{self.uid}] Debug mode turned off.")
+        for knob in _DEBUG_KNOBS:
+            setattr(self, knob, vars(self).pop("old_" + knob))
+        _tag(self, "Debug mode turned off.")
 
 
 class RegressorMixin:
@@ -236,9 +233,8 @@ class RegressorMixin:
 
     def predict(self, bayes_samples, domain):
         """(M,D),(K,Xdim) -> (M,K,Ydim) network outputs (base.py:267-277), one batched kernel instead of a per-sample loop."""
-        W = self._weights_matrix(torch.as_tensor(bayes_samples))
-        X = torch.as_tensor(domain).to(W.device, torch.float32).contiguous()
-        return self.engine_problem().forward(W, X).cpu()
+        W, X = self._predict_operands(bayes_samples, domain)
+        return self.engine_problem().predict(W, X, E.PREDICT_RAW)[0].cpu()
 
     def add_deterministic_constraint(self, constrained_domain, interval_func, prior_type):
         """Positive or negative deterministic constraint, 1-D output (base.py:279-342)."""
@@ -282,12 +278,9 @@ class ClassifierMixin:
 
     def predict(self, bayes_samples, domain, return_probs=False):
         """(M,K) predicted classes, or (M,K,Ydim) softmax probabilities (base.py:446-461)."""
-        W = self._weights_matrix(torch.as_tensor(bayes_samples))
-        X = torch.as_tensor(domain).to(W.device, torch.float32).contiguous()
-        softprobs = torch.softmax(self.engine_problem().forward(W, X), dim=2).cpu()
-        if return_probs:
-            return softprobs
-        return softprobs.argmax(dim=2)
+        W, X = self._predict_operands(bayes_samples, domain)
+        probs, classes, _ = self.engine_problem().predict(W, X, E.PREDICT_PROBS if return_probs else E.PREDICT_CLASS)
+        return probs.cpu() if return_probs else classes.cpu().long()
 
     def add_deterministic_constraint(self, constrained_domain, forbidden_classes, prior_type="positive_dirichlet_cocp"):
         """Forbidden classes over a region (base.py:463-496)."""
@@ -315,12 +308,9 @@ class BinaryClassifierMixin:
 
     def predict(self, bayes_samples, domain, return_probs=False):
         """(M,K) p(Y=1) or the decision p >= 0.5 (base.py:544-559)."""
-        W = self._weights_matrix(torch.as_tensor(bayes_samples))
-        X = torch.as_tensor(domain).to(W.device, torch.float32).contiguous()
-        probs = torch.sigmoid(self.engine_problem().forward(W, X)[:, :, 0]).cpu()
-        if return_probs:
-            return probs
-        return probs >= 0.5
+        W, X = self._predict_operands(bayes_samples, domain)
+        probs, classes, _ = self.engine_problem().predict(W, X, E.PREDICT_PROBS if return_probs else E.PREDICT_CLASS)
+        return probs[:, :, 0].cpu() if return_probs else classes.cpu().bool()
 
     def add_deterministic_constraint(self, constrained_domain, desired_class, prior_type="gaussian_aocp"):
         """Desired class over a region (base.py:561-590)."""

@@ -20,6 +20,7 @@ OCBNN_ABI_VERSION = 2
 OCBNN_MAX_LAYERS = 8
 ACT_IDENTITY, ACT_RBF, ACT_RELU = 0, 1, 2
 HEAD_LIK_GAUSS, HEAD_NEG_EXP, HEAD_POS_GAUSS, HEAD_DIRICHLET, HEAD_LIK_SOFTMAX, HEAD_LIK_BERNOULLI = range(6)
+PREDICT_RAW, PREDICT_PROBS, PREDICT_CLASS = range(3)
 
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int32)
@@ -71,6 +72,10 @@ _SIGS = {
     "ocbnn_logpost_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                      C.c_int32, C.c_void_p]),
     "ocbnn_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ocbnn_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p]),
+    "ocbnn_violation_flags": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
     "ocbnn_hmc_iterate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_void_p]),
@@ -201,6 +206,7 @@ class DeviceProblem:
         self._h = h
         self.D = cp.nweights
         self.sK = cp.layer_sizes[-1]
+        self.s0 = cp.layer_sizes[0]
         self.device = torch.device("cuda", torch.cuda.current_device())
 
     def close(self):
@@ -224,11 +230,38 @@ class DeviceProblem:
                                        int(lanes), _stream()))
         return lp, g
 
-    def forward(self, W, X):
+    def _domain(self, W, X):
         W, X = _f32(W, "W"), _f32(X, "X")
+        if W.ndim != 2 or W.shape[1] != self.D:
+            raise EngineError(f"weights must be (M, {self.D}), got {tuple(W.shape)}")
+        if X.ndim != 2 or X.shape[1] != self.s0:
+            raise EngineError(f"domain must be (K, {self.s0}), got {tuple(X.shape)}")
+        return W, X
+
+    def forward(self, W, X):
+        W, X = self._domain(W, X)
         out = torch.empty(W.shape[0], X.shape[0], self.sK, device=W.device)
         check(lib().ocbnn_forward(self._h, _ptr(W), W.shape[0], _ptr(X), X.shape[0], _ptr(out), _stream()))
         return out
+
+    def predict(self, W, X, head=PREDICT_RAW, want_class=False, want_mean=False):
+        """ocbnn_predict: (out (M, K, sK) raw outputs or probabilities, classes (M, K) int32 or None, mean over M (K, sK) or None)."""
+        W, X = self._domain(W, X)
+        M, K = W.shape[0], X.shape[0]
+        out = torch.empty(M, K, self.sK, device=W.device)
+        cls = torch.empty(M, K, dtype=torch.int32, device=W.device) if (want_class or head == PREDICT_CLASS) else None
+        mean = torch.empty(K, self.sK, device=W.device) if want_mean else None
+        check(lib().ocbnn_predict(self._h, _ptr(W), M, _ptr(X), K, int(head), _ptr(out), _ptr(cls), _ptr(mean), _stream()))
+        return out, cls, mean
+
+    def violation_flags(self, W, X, lo, hi):
+        """ocbnn_violation_flags: (M,) uint8, 1 where sample m predicts inside (lo, hi) somewhere on the domain X."""
+        W, X = self._domain(W, X)
+        M, K = W.shape[0], X.shape[0]
+        scratch = torch.empty(max(1, M * K * self.sK), device=W.device)
+        flags = torch.empty(M, dtype=torch.uint8, device=W.device)
+        check(lib().ocbnn_violation_flags(self._h, _ptr(W), M, _ptr(X), K, float(lo), float(hi), _ptr(scratch), _ptr(flags), _stream()))
+        return flags
 
     # ---- K2 -------------------------------------------------------------------------------------------
     def hmc_iterate(self, q, p0, u, eps, L, with_data=True, restore_on_reject=False, want_h=False, want_flags=True, samples=None,

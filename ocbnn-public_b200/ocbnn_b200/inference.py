@@ -174,6 +174,11 @@ class HMCMixin:
         collection round yields M samples (round-major order); the first infer_nsamples are kept."""
         infer_id = len(self.all_bayes_samples) + 1
         logging.info(f"[{self.uid}] Posterior Sample #{infer_id}: Beginning HMC inference...")
+        if not getattr(self, "restore_on_reject", False):
+            # the reference keeps a rejected proposal (inference.py:46,78: original_q aliases the live weights); reproduced by default
+            logging.warning(f"[{self.uid}] restore_on_reject is false: rejected HMC proposals are kept, as in the reference. "
+                            "The chain is not Metropolis-corrected and the logged acceptance rate is diagnostic only; "
+                            "set restore_on_reject: true for textbook HMC.")
         start_time = time.time()
         dev = self._device()
         M_total = max(1, int(getattr(self, "nchains", 1) or 1))

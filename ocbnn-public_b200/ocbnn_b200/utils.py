@@ -1,7 +1,7 @@
 """
 Evaluation on top of the posterior samples: the reference's `bnn/utils.py:217-232`
 (`eval_accuracy_and_f1_score`), `run_apps.py:31-41` (`recid_evaluate_high_risk`), `run_apps.py:130-143`
-(`credit_evaluate_recourse`) and the feature standardisation of `data/dataloader.py:134-142, 167-176`.
+(`credit_evaluate_recourse`), the constraint-violation fraction of `run_toys.py:229-250` (Figure 3c) and the feature standardisation of `data/dataloader.py:134-142, 167-176`.
 
 Same names, arguments and return values as the reference.  The posterior-mean predictive probability
 `predict(samples, X, return_probs=True).mean(dim=0)` — the only heavy part — is formed on the device: one batched
@@ -28,10 +28,22 @@ def posterior_mean_probs(bnn, samples, X, chunk=1 << 26):
     per = max(1, chunk // max(1, W.shape[0] * prob.sK))
     outs = []
     for k0 in range(0, X.shape[0], per):
-        f = prob.forward(W, X[k0:k0 + per].contiguous())                  # (M, k, sK) logits
-        p = torch.sigmoid(f[:, :, 0]) if binary else torch.softmax(f, dim=2)
-        outs.append(p.mean(dim=0))
+        # forward + softmax / sigmoid + mean over the samples in one library call (ocbnn_predict)
+        mean = prob.predict(W, X[k0:k0 + per].contiguous(), E.PREDICT_PROBS, want_mean=True)[2]
+        outs.append(mean[:, 0] if binary else mean)
     return torch.cat(outs, 0).cpu()
+
+
+def constraint_violation_fraction(bnn, samples, domain, forbidden):
+    """Fraction of posterior samples whose prediction enters the open interval `forbidden` = (lo, hi) at any point of
+    `domain` (K, Xdim): the "fraction of rejected posterior samples" of Figure 3c (run_toys.py:229-233, 245-249, where the
+    interval is (1.0, 2.5) and the domain arange(-1, 1, 0.05)).  Forward pass and the per-sample any() run in the library
+    (ocbnn_violation_flags); only the M flags come back."""
+    E.require_cuda()
+    W = bnn._weights_matrix(torch.as_tensor(samples))
+    X = torch.as_tensor(domain).to(W.device, torch.float32).contiguous()
+    flags = bnn.engine_problem().violation_flags(W, X, forbidden[0], forbidden[1])
+    return int(flags.sum()) / max(1, W.shape[0])
 
 
 def _binary_f1(y_true, y_pred):

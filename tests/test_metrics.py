@@ -93,3 +93,64 @@ def test_metrics_through_the_cuda_predictive():
             Xn[young][preds[young] == 0, 0].mean(), Xn[young][preds[young] == 1, 0].mean()]
     got = [float(v) for v in U.credit_evaluate_recourse(m)]
     assert np.allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["w3_cls_dir", "credit_small", "recid_small", "bin_vanilla"])
+def test_predict_heads_run_in_the_library(name):
+    """ocbnn_predict: softmax / sigmoid probabilities, the decisions and the mean over samples against the reference's golden
+    probabilities (base.py:446-461, 544-559) and the float64 oracle."""
+    import os, tempfile
+    import ocbnn_oracle as orc
+    from ocbnn_b200 import engine as E
+    from helpers import load_golden, make_model, spec_from_golden
+    os.chdir(tempfile.mkdtemp())
+    gold = load_golden(name)
+    m, spec = make_model(name, gold), spec_from_golden(name, gold)
+    W, dom = torch.tensor(gold["W"]), torch.tensor(gold["predict_domain"])
+    P = m.predict(W, dom, return_probs=True)
+    assert P.shape == tuple(gold["predict_probs"].shape) and np.abs(P.numpy() - gold["predict_probs"]).max() < 1e-5
+    P64 = orc.predict(spec, gold["W"], gold["predict_domain"], return_probs=True, dtype=np.float64)
+    cls = m.predict(W, dom)
+    want = orc.predict(spec, gold["W"], gold["predict_domain"], dtype=np.float64)
+    margin = np.abs(P64 - 0.5) if spec.task == "binary" else np.sort(P64, axis=2)[:, :, -1] - np.sort(P64, axis=2)[:, :, -2]
+    clear = margin > 1e-5                                       # decisions may differ only where fp32 cannot tell
+    assert cls.shape == want.shape and cls.dtype == (torch.bool if spec.task == "binary" else torch.int64)
+    assert np.array_equal(cls.numpy()[clear], want[clear])
+    prob = m.engine_problem()
+    Wd, Xd = W.cuda().contiguous(), dom.cuda().float().contiguous()
+    out, both, mean = prob.predict(Wd, Xd, E.PREDICT_PROBS, want_class=True, want_mean=True)
+    assert np.abs(mean.cpu().numpy().reshape(P64.mean(axis=0).shape) - P64.mean(axis=0)).max() < 1e-5
+    assert np.array_equal(both.cpu().numpy()[clear], want.astype(np.int32)[clear])
+    with pytest.raises(E.EngineError):                          # a domain of the wrong width is refused, not read out of bounds
+        prob.predict(Wd, torch.zeros(3, m.Xdim + 1, device="cuda"))
+
+
+@pytest.mark.gpu
+def test_constraint_violation_fraction_f3c():
+    """Figure 3c's metric (run_toys.py:229-233): fraction of posterior samples that enter (1.0, 2.5) anywhere on
+    arange(-1, 1, 0.05), against the reference's own loop over the oracle's predictions; edge cases: no samples inside,
+    all inside, empty domain, a single sample."""
+    import os, tempfile
+    import ocbnn_oracle as orc
+    from ocbnn_b200 import engine as E
+    from helpers import load_golden, make_model, spec_from_golden
+    os.chdir(tempfile.mkdtemp())
+    name = "w2_reg_neg"
+    gold = load_golden(name)
+    m, spec = make_model(name, gold), spec_from_golden(name, gold)
+    g = torch.Generator().manual_seed(7)
+    samples = torch.cat([torch.tensor(gold["W"]), 0.8 * torch.randn(300, m.nweights, generator=g)])
+    domain = torch.arange(-1.0, 1.0, 0.05).unsqueeze(dim=1)
+    results = orc.predict(spec, samples.numpy(), domain.numpy(), dtype=np.float64)[:, :, 0]
+    clear = ~((np.abs(results - 1.0) < 1e-5) | (np.abs(results - 2.5) < 1e-5)).any(axis=1)
+    violation_count = 0
+    for line in results[clear]:                                 # the reference's loop, run_toys.py:230-232
+        violation_count += any([(point > 1.0 and point < 2.5) for point in line])
+    want = violation_count / int(clear.sum())
+    got = U.constraint_violation_fraction(m, samples[torch.tensor(clear)], domain, (1.0, 2.5))
+    assert 0.0 < want < 1.0 and got == want
+    assert U.constraint_violation_fraction(m, samples, domain, (1e6, 2e6)) == 0.0
+    assert U.constraint_violation_fraction(m, samples, domain, (-1e6, 1e6)) == 1.0
+    assert U.constraint_violation_fraction(m, samples[:1], domain, (-1e6, 1e6)) == 1.0
+    assert U.constraint_violation_fraction(m, samples, domain[:0], (-1e6, 1e6)) == 0.0
