@@ -101,6 +101,10 @@ int launch_logpost_generic(const Problem& p, const EvalArgs& a, const float* w, 
                            cudaStream_t st);
 int launch_forward_generic(const Problem& p, const float* w, long long m, const float* x, long long npts, float* out,
                            cudaStream_t st);
+// gen_tc.cu: the tcgen05 K1 of the application nets.  Returns 1 when it took the launch (*rc = its result), 0 when the net does
+// not fit it and the caller should use generic_net.cu's kernels.
+int try_launch_logpost_gen_tc(const Problem& p, const EvalArgs& a, const float* w, long long m, float* out_lp, float* out_grad,
+                              cudaStream_t st, int* rc);
 
 int choose_lanes(const Problem& p, long long m, int points);
 

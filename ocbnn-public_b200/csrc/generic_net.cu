@@ -728,6 +728,10 @@ int launch_logpost_generic(const Problem& p, const EvalArgs& a, const float* w, 
                            cudaStream_t st) {
     OCBNN_REQUIRE(p.desc.layer_sizes[p.desc.n_layers] <= kMaxRt, OCBNN_EUNSUPPORTED, "output width %d > %d not supported",
                   p.desc.layer_sizes[p.desc.n_layers], kMaxRt);
+    {   // tcgen05 kernel (gen_tc.cu) for every net whose operand arrays fit one SM; OCBNN_GEN_TC=0 forces the kernels below
+        int rc = OCBNN_OK;
+        if (try_launch_logpost_gen_tc(p, a, w, m, out_lp, out_grad, st, &rc)) return rc;
+    }
     GenLayout L;
     int sm = pick_tp(p, L, true);
     OCBNN_REQUIRE(sm > 0, OCBNN_EUNSUPPORTED, "network with %d weights does not fit the shared-memory resident kernel", p.d);

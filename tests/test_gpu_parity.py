@@ -473,11 +473,13 @@ def test_full_size_properties_hmc_262144_chains_and_svgd_4096_particles():
 
 @pytest.mark.parametrize("env, select", [
     # small generic nets run the SIMT variant by default: force the 3xTF32 tensor variant on them
-    (dict(OCBNN_GEN_MMA="1", OCBNN_GEN_MINB="2"), "test_k1_logpost_and_grad and (odd or wide1 or deep)"),
+    (dict(OCBNN_GEN_TC="0", OCBNN_GEN_MMA="1", OCBNN_GEN_MINB="2"), "test_k1_logpost_and_grad and (odd or wide1 or deep)"),
+    # mma.sync 3xTF32 variant on the nets the tcgen05 kernel (gen_tc.cu) serves by default
+    (dict(OCBNN_GEN_TC="0", OCBNN_GEN_MMA="1"), "test_k1_logpost_and_grad and (credit or recid)"),
     # credit / recid run the tensor variant by default: force the SIMT register-tile variant, both backward schedules
-    (dict(OCBNN_GEN_MMA="0", OCBNN_GEN_SCHED="1"), "test_k1_logpost_and_grad and (credit or recid)"),
-    (dict(OCBNN_GEN_MMA="0", OCBNN_GEN_SCHED="0", OCBNN_GEN_TP="16"), "test_k1_logpost_and_grad and (credit or odd)"),
-], ids=["tensor_path_forced", "simt_path_forced", "simt_16_point_tiles"])
+    (dict(OCBNN_GEN_TC="0", OCBNN_GEN_MMA="0", OCBNN_GEN_SCHED="1"), "test_k1_logpost_and_grad and (credit or recid)"),
+    (dict(OCBNN_GEN_TC="0", OCBNN_GEN_MMA="0", OCBNN_GEN_SCHED="0", OCBNN_GEN_TP="16"), "test_k1_logpost_and_grad and (credit or odd)"),
+], ids=["tensor_path_forced", "mma_sync_path_forced", "simt_path_forced", "simt_16_point_tiles"])
 def test_generic_net_kernel_variants(env, select):
     """The generic-net K1 picks its variant (tile size, threads, SIMT / tensor path) from the net's shared-memory footprint; the
     variant knobs are read once per process, so each combination runs the K1 parity test in a child process."""
