@@ -20,7 +20,7 @@
 // a bf16x3 and not a 3xTF32 kernel).  Activations / dZ are [point][feature] with point-groups contiguous, so a warp's 32 threads
 // (one point each) store 512 contiguous bytes per 8-feature chunk: conflict-free 16-byte stores.
 //
-// Epilogues (256 threads: warp w owns TMEM lanes 32 (w%4).., column half w/4): tcgen05.ld the accumulator row, activation /
+// Epilogues (512 threads: warp w owns TMEM lanes 32 (w%4).., column quarter w/4): tcgen05.ld the accumulator row, activation /
 // activation derivative (Z_l stays in TMEM for the backward pass), head at the output layer, split into the three bf16 parts,
 // store.  dZ_l overwrites A_l in place (A_l is dead once GEMM3_{l+1} has retired).
 //
@@ -37,7 +37,12 @@ namespace gtc {
 using tc::smem_u32;
 
 constexpr int kTP = 128;            // points per tile = TMEM lanes
-constexpr int kThreads = 256;       // 8 epilogue warps (warp 0 also issues the MMAs)
+#ifndef OCBNN_GTC_THREADS
+#define OCBNN_GTC_THREADS 512
+#endif
+constexpr int kThreads = OCBNN_GTC_THREADS;   // 16 epilogue warps: 4 per TMEM subpartition, a quarter of the columns each (warp 0 also issues the MMAs)
+constexpr int kParts = kThreads / 128;        // column shares per TMEM lane
+constexpr int kBatch = kThreads >= 512 ? 2 : 4;   // 8-column chunks loaded from TMEM before one wait
 constexpr int kRG = 128;            // bytes between 8-row groups of a core-tiled array (row groups contiguous)
 constexpr int kActCG = (kTP / 8) * kRG;   // bytes between 8-feature column cores of an activation array (2048)
 constexpr int kCutTiles = 4;        // dW accumulation chains are drained after this many tiles (48 MMAs per tile and layer)
@@ -171,7 +176,7 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
     const uint32_t sm_base = smem_u32(sm);
 
     const int warp = tc::warp_idx_sync(), lane = threadIdx.x & 31;
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, part = warp >> 2;
     const int pt = q * 32 + lane;                       // this thread's point of the tile = its TMEM lane
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int nl = Y.nl, sk = Y.sk;
@@ -197,12 +202,12 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
         const int count = min(kTP, c.npts - begin);
         const int rs = a.rs, stride = a.batch_stride > 1 ? a.batch_stride : 1, offset = a.batch_stride > 1 ? a.batch_offset : 0;
         const uint32_t dst0 = smem_u32(rec0 + buf * rec_floats);
-        for (int j = warp; j < count; j += kThreads / 32) {
-            const int pj = begin + j;
+        if ((int)threadIdx.x < count) {                 // one thread per record: the row address is formed once
+            const int j = threadIdx.x, pj = begin + j;
             const long long row = pj < c.nb ? (long long)offset + (long long)pj * stride : a.n_train + (pj - c.nb);
             const float* src = a.pts + row * rs;
-            for (int k = lane; k < rs; k += 32)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst0 + (uint32_t)((j * rs + k) * 4)), "l"(src + k) : "memory");
+            uint32_t dst = dst0 + (uint32_t)(j * rs * 4);
+            for (int k = 0; k < rs; ++k, dst += 4, ++src) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -276,16 +281,17 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
             // ---- A_0 = [x | 1 | 0..] ------------------------------------------------------------------------------------------
             {
                 const Layer& L1 = Y.L[1];
-                const int nch = L1.kp >> 3, per = (nch + 1) >> 1;
+                const int nch = L1.kp >> 3, per = (nch + kParts - 1) / kParts;
                 const float* r = rec + pt * a.rs;
-                for (int ch = half * per; ch < min(nch, (half + 1) * per); ++ch) {
+                const int a_off = L1.a_off, a_part = L1.a_part;
+                for (int ch = part * per; ch < min(nch, (part + 1) * per); ++ch) {
                     float v[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int f = ch * 8 + i;
                         v[i] = f < Y.s0 ? (pt < count ? r[f] : 0.f) : (f == Y.s0 ? 1.f : 0.f);
                     }
-                    store_chunk(sm + L1.a_off, L1.a_part, act_chunk_off(pt, ch), v);
+                    store_chunk(sm + a_off, a_part, act_chunk_off(pt, ch), v);
                 }
             }
             fence_async_smem();
@@ -314,27 +320,31 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
                 if (l < nl) {
                     // A_l = [act(Z_l) | 1 | 0..]: features of layer l+1's input
                     const Layer& N = Y.L[l + 1];
-                    const int nch = N.kp >> 3, per = (nch + 1) >> 1;
-                    const int c_lo = half * per, c_hi = min(nch, (half + 1) * per);
-                    for (int c0 = c_lo; c0 < c_hi; c0 += 4) {
-                        uint32_t raw[4][8];
+                    const int nch = N.kp >> 3, per = (nch + kParts - 1) / kParts;
+                    const int c_lo = part * per, c_hi = min(nch, (part + 1) * per);
+                    const int n_real = L.n, np = L.np, act = Y.act, a_off = N.a_off, a_part = N.a_part;
+                    for (int c0 = c_lo; c0 < c_hi; c0 += kBatch) {
+                        uint32_t raw[kBatch][8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (c0 + j < c_hi && (c0 + j) * 8 < L.np) tmem_ld8_nowait(tmem + lane_base + zc + (uint32_t)((c0 + j) * 8), raw[j]);
+                        for (int j = 0; j < kBatch; ++j)
+                            if (c0 + j < c_hi && (c0 + j) * 8 < np) tmem_ld8_nowait(tmem + lane_base + zc + (uint32_t)((c0 + j) * 8), raw[j]);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int j = 0; j < kBatch; ++j) {
                             if (c0 + j >= c_hi) break;
+                            const int f0 = (c0 + j) * 8;
                             float v[8];
+                            if (f0 + 8 <= n_real) {             // interior chunk: no masks
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int f = (c0 + j) * 8 + i;
-                                v[i] = f < L.n ? act_f(Y.act, __uint_as_float(raw[j][i])) : (f == L.n ? 1.f : 0.f);
+                                for (int i = 0; i < 8; ++i) v[i] = act_f(act, __uint_as_float(raw[j][i]));
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = f0 + i < n_real ? act_f(act, __uint_as_float(raw[j][i])) : (f0 + i == n_real ? 1.f : 0.f);
                             }
-                            store_chunk(sm + N.a_off, N.a_part, act_chunk_off(pt, c0 + j), v);
+                            store_chunk(sm + a_off, a_part, act_chunk_off(pt, c0 + j), v);
                         }
                     }
-                } else if (half == 0) {
+                } else if (part == 0) {
                     // heads: value and dZ of the output layer (weighted); dead points get a zero gradient
                     uint32_t raw[2][8];
                     tmem_ld8_nowait(tmem + lane_base + zc, raw[0]);
@@ -414,27 +424,32 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
                 // dZ_{l-1} = dA_{l-1} * act'(Z_{l-1})
                 {
                     const Layer& P = Y.L[l - 1];
-                    const int nch = P.np >> 3, per = (nch + 1) >> 1;
-                    const int c_lo = half * per, c_hi = min(nch, (half + 1) * per);
-                    for (int c0 = c_lo; c0 < c_hi; c0 += 4) {
-                        uint32_t rd[4][8], rz[4][8];
+                    const int nch = P.np >> 3, per = (nch + kParts - 1) / kParts;
+                    const int c_lo = part * per, c_hi = min(nch, (part + 1) * per);
+                    const int n_real = P.n, act = Y.act, pg_off = P.g_off, pg_part = P.g_part;
+                    const uint32_t t_da = tmem + lane_base + (uint32_t)Y.da_col, t_z = tmem + lane_base + (uint32_t)P.z_col;
+                    for (int c0 = c_lo; c0 < c_hi; c0 += kBatch) {
+                        uint32_t rd[kBatch][8], rz[kBatch][8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
+                        for (int j = 0; j < kBatch; ++j)
                             if (c0 + j < c_hi) {
-                                tmem_ld8_nowait(tmem + lane_base + (uint32_t)Y.da_col + (uint32_t)((c0 + j) * 8), rd[j]);
-                                tmem_ld8_nowait(tmem + lane_base + (uint32_t)P.z_col + (uint32_t)((c0 + j) * 8), rz[j]);
+                                tmem_ld8_nowait(t_da + (uint32_t)((c0 + j) * 8), rd[j]);
+                                tmem_ld8_nowait(t_z + (uint32_t)((c0 + j) * 8), rz[j]);
                             }
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int j = 0; j < kBatch; ++j) {
                             if (c0 + j >= c_hi) break;
+                            const int f0 = (c0 + j) * 8;
                             float v[8];
+                            if (f0 + 8 <= n_real) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int f = (c0 + j) * 8 + i;
-                                v[i] = f < P.n ? __uint_as_float(rd[j][i]) * dact_f(Y.act, __uint_as_float(rz[j][i])) : 0.f;
+                                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(rd[j][i]) * dact_f(act, __uint_as_float(rz[j][i]));
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = f0 + i < n_real ? __uint_as_float(rd[j][i]) * dact_f(act, __uint_as_float(rz[j][i])) : 0.f;
                             }
-                            store_chunk(sm + P.g_off, P.g_part, act_chunk_off(pt, c0 + j), v);
+                            store_chunk(sm + pg_off, pg_part, act_chunk_off(pt, c0 + j), v);
                         }
                     }
                 }
@@ -454,8 +469,8 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
                     const Layer& L = Y.L[l];
                     const int row = L.dw_m == 128 ? pt : q * 16 + lane;           // M = 64: 16 rows per TMEM subpartition
                     const bool row_ok = L.dw_m == 128 || lane < 16;
-                    const int nch = L.dw_n >> 3, per = (nch + 1) >> 1;
-                    const int c_lo = half * per, c_hi = min(nch, (half + 1) * per);
+                    const int nch = L.dw_n >> 3, per = (nch + kParts - 1) / kParts;
+                    const int c_lo = part * per, c_hi = min(nch, (part + 1) * per);
                     for (int ch = c_lo; ch < c_hi; ++ch) {
                         uint32_t raw[8];
                         tmem_ld8_nowait(tmem + lane_base + (uint32_t)L.dw_col + (uint32_t)(ch * 8), raw);
