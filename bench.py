@@ -774,8 +774,20 @@ def bench_bbb(cx, wl="W6"):
     peak_ffma2 = E.probe_peak(1)
     flop_pt = workloads.flops_per_point(mb.layer_sizes)
     flop = float(hi - lo) * npts * flop_pt
-    roofline = {"bound": "fp32-simt", "kernel": "k_logpost_generic (K1 on the credit net; the 3xTF32 variant computes an fp32-accurate result, so the fp32 FMA peak is the yardstick)",
+    tc_k1 = os.environ.get("OCBNN_GEN_TC", "1") != "0"
+    ls = mb.layer_sizes
+    up16 = lambda v: (v + 15) // 16 * 16
+    # bf16 MMA work the tcgen05 kernel issues per point (padded operand extents, 6 part products, 2 FLOP per MAC): GEMM1 + GEMM2 + GEMM3
+    macs = sum(up16(ls[l - 1] + 1) * up16(ls[l]) for l in range(1, len(ls))) + sum(up16(ls[l]) * up16(ls[l - 1]) for l in range(2, len(ls))) \
+        + sum(min(64 * -(-(ls[l - 1] + 1) // 64) * up16(ls[l]), 64 * -(-ls[l] // 64) * up16(ls[l - 1] + 1)) for l in range(1, len(ls)))
+    bf16_peak = load_peaks()[1]
+    roofline = {"bound": "fp32-simt",
+                "kernel": ("k_logpost_gen_tc (K1 on the credit net: tcgen05 kind::f16, every fp32 operand split into three bf16 parts, six MMAs per product; "
+                           "the result is fp32-accurate, so the fp32 FMA peak is the yardstick and the issued tensor work is reported beside it)") if tc_k1 else
+                          "k_logpost_generic (K1 on the credit net; mma.sync 3xTF32 variant, fp32-accurate result: the fp32 FMA peak is the yardstick)",
                 "achieved": flop / t_k1 / 1e12, "peak": peak_ffma2 / 1e12, "unit": "TFLOP/s", "frac": flop / t_k1 / peak_ffma2,
+                "tensor_issued_tflops": (float(hi - lo) * npts * macs * 12 / t_k1 / 1e12) if tc_k1 else None,
+                "tensor_issued_frac_of_bf16_peak": (float(hi - lo) * npts * macs * 12 / t_k1 / 1e12 / bf16_peak) if (tc_k1 and bf16_peak) else None,
                 "traffic": ncu_traffic("r02_generic_k1_ncu.json", workload=wl, samples=hi - lo),
                 "peak_source": "packed FFMA2 probe measured in this run (ocbnn_probe_peak)", "flop_per_point": flop_pt, "points_per_sample": int(npts),
                 "samples_this_rank": hi - lo, "kernel_seconds": t_k1, "algorithmic_hbm_bytes_per_launch": int(8 * D * (hi - lo)),
@@ -787,7 +799,7 @@ def bench_bbb(cx, wl="W6"):
         os.chdir(cx.cwd)
         cpu = {"value": rate, "unit": BBB_UNIT, "cores": cores, "kind": "port", "sample": sample}
     return {"metric": BBB_METRIC, "value": value, "unit": BBB_UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (3xTF32 mma for the layer GEMMs)", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (bf16x3 on tcgen05 for the layer GEMMs)", "data": "synthetic",
             "config": {"workload": NAMES[wl], "mc_samples_total": k, "mc_samples_per_gpu": hi - lo, "weights": D, "points_per_sample": int(npts),
                        "l2": "flushed between timed steps (256 MiB write)", "elbo": float(elbo[0]),
                        "collectives_per_step": 0 if world == 1 else f"1 all-reduce of {2 * D + 1} floats (NCCL inside ocbnn_bbb_step)"},

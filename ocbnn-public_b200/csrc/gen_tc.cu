@@ -36,7 +36,7 @@ namespace gtc {
 
 using tc::smem_u32;
 
-constexpr int kTP = 128;            // points per tile = TMEM lanes
+constexpr int kTPmax = 128;         // points per tile: 128 (= the TMEM lanes, MMA M = 128) or 64 (M = 64: 16 lanes of every subpartition)
 #ifndef OCBNN_GTC_THREADS
 #define OCBNN_GTC_THREADS 512
 #endif
@@ -44,7 +44,6 @@ constexpr int kThreads = OCBNN_GTC_THREADS;   // 16 epilogue warps: 4 per TMEM s
 constexpr int kParts = kThreads / 128;        // column shares per TMEM lane
 constexpr int kBatch = kThreads >= 512 ? 2 : 4;   // 8-column chunks loaded from TMEM before one wait
 constexpr int kRG = 128;            // bytes between 8-row groups of a core-tiled array (row groups contiguous)
-constexpr int kActCG = (kTP / 8) * kRG;   // bytes between 8-feature column cores of an activation array (2048)
 constexpr int kCutTiles = 4;        // dW accumulation chains are drained after this many tiles (48 MMAs per tile and layer)
 constexpr int kMaxRt = 10;
 
@@ -62,6 +61,7 @@ struct Layer {
 struct Layout {
     int nl, act, d, s0, sk;
     Layer L[OCBNN_MAX_LAYERS + 1];      // index 1..nl
+    int tp;                             // points per tile
     int rec_off, rec_bytes, bar_off, zero_bytes, smem_bytes;    // rec: two buffers (the next tile's records are prefetched)
     int da_col, tmem_cols;
 };
@@ -124,7 +124,8 @@ __device__ __forceinline__ void store_chunk(uint8_t* part0, int part_bytes, int 
     *reinterpret_cast<uint4*>(part0 + part_bytes + byte_off) = q1;
     *reinterpret_cast<uint4*>(part0 + 2 * part_bytes + byte_off) = q2;
 }
-__device__ __forceinline__ int act_chunk_off(int p, int chunk) { return chunk * kActCG + (p >> 3) * kRG + (p & 7) * 16; }
+template <int TP>
+__device__ __forceinline__ int act_chunk_off(int p, int chunk) { return chunk * ((TP / 8) * kRG) + (p >> 3) * kRG + (p & 7) * 16; }
 
 __device__ __forceinline__ float act_f(int act, float z) {
     if (act == OCBNN_ACT_RBF) return ex2_approx(z * z * -1.4426950408889634f);
@@ -162,6 +163,7 @@ __device__ __forceinline__ float head_switch(int sk, int kind, const float (&z)[
     }
 }
 
+template <int kTP>
 __global__ void __launch_bounds__(kThreads, 1)
 k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __restrict__ w, long long m, float* __restrict__ out_lp,
                  float* __restrict__ out_grad) {
@@ -177,7 +179,11 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
 
     const int warp = tc::warp_idx_sync(), lane = threadIdx.x & 31;
     const int q = warp & 3, part = warp >> 2;
-    const int pt = q * 32 + lane;                       // this thread's point of the tile = its TMEM lane
+    constexpr int kActCG = (kTP / 8) * kRG;            // bytes between 8-feature column cores of an activation array
+    // this thread's point of the tile <-> its TMEM lane.  M = 64 accumulators keep 16 rows in lanes 0..15 of every subpartition:
+    // the upper half-warp has no point (it still takes part in the warp-wide tcgen05.ld)
+    const int pt = kTP == 128 ? q * 32 + lane : q * 16 + (lane & 15);
+    const bool has_pt = kTP == 128 || lane < 16;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int nl = Y.nl, sk = Y.sk;
     const bool want_grad = out_grad != nullptr;
@@ -215,6 +221,10 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
     for (long long chain = blockIdx.x; chain < m; chain += gridDim.x) {
         const float* wc = w + chain * Y.d;
         float* gc = want_grad ? out_grad + chain * Y.d : nullptr;
+        if (chain + gridDim.x < m) {          // the next weight vector of this CTA: into L2 behind this one's work
+            const float* nx = w + (chain + gridDim.x) * Y.d;
+            for (int i = threadIdx.x * 32; i < Y.d; i += kThreads * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
+        }
         // ---- weights -> three bf16 parts, core-tiled [k][n]; prior value and prior gradient ----------------------------------
         double lp = 0.0;
         {
@@ -291,7 +301,7 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
                         const int f = ch * 8 + i;
                         v[i] = f < Y.s0 ? (pt < count ? r[f] : 0.f) : (f == Y.s0 ? 1.f : 0.f);
                     }
-                    store_chunk(sm + a_off, a_part, act_chunk_off(pt, ch), v);
+                    if (has_pt) store_chunk(sm + a_off, a_part, act_chunk_off<kTP>(pt, ch), v);
                 }
             }
             fence_async_smem();
@@ -341,7 +351,7 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) v[i] = f0 + i < n_real ? act_f(act, __uint_as_float(raw[j][i])) : (f0 + i == n_real ? 1.f : 0.f);
                             }
-                            store_chunk(sm + a_off, a_part, act_chunk_off(pt, c0 + j), v);
+                            if (has_pt) store_chunk(sm + a_off, a_part, act_chunk_off<kTP>(pt, c0 + j), v);
                         }
                     }
                 } else if (part == 0) {
@@ -356,20 +366,20 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
                         z[i] = __uint_as_float(raw[i >> 3][i & 7]);
                         dz[i] = 0.f;
                     }
-                    if (pt < count) {
+                    if (has_pt && pt < count) {
                         const float* r = rec + pt * a.rs;
                         const float wgt = begin + pt < c.nb ? r[a.s0 + 1] * c.mult : r[a.s0 + 1];      // likelihood rows: N/|B|
                         lp += (double)head_switch(sk, __float_as_int(r[a.s0]), z, r + a.s0 + 2, c.hc, wgt, dz);
                     }
-                    if (want_grad) {
+                    if (want_grad && has_pt) {
                         float v0[8], v1[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             v0[i] = dz[i];
                             v1[i] = dz[8 + i];
                         }
-                        store_chunk(sm + Y.L[nl].g_off, Y.L[nl].g_part, act_chunk_off(pt, 0), v0);
-                        store_chunk(sm + Y.L[nl].g_off, Y.L[nl].g_part, act_chunk_off(pt, 1), v1);
+                        store_chunk(sm + Y.L[nl].g_off, Y.L[nl].g_part, act_chunk_off<kTP>(pt, 0), v0);
+                        store_chunk(sm + Y.L[nl].g_off, Y.L[nl].g_part, act_chunk_off<kTP>(pt, 1), v1);
                     }
                 }
                 tc::tc_fence_before();
@@ -449,7 +459,7 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) v[i] = f0 + i < n_real ? __uint_as_float(rd[j][i]) * dact_f(act, __uint_as_float(rz[j][i])) : 0.f;
                             }
-                            store_chunk(sm + pg_off, pg_part, act_chunk_off(pt, c0 + j), v);
+                            if (has_pt) store_chunk(sm + pg_off, pg_part, act_chunk_off<kTP>(pt, c0 + j), v);
                         }
                     }
                 }
@@ -467,7 +477,7 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
                 tc::tc_fence_after();
                 for (int l = 1; l <= nl; ++l) {
                     const Layer& L = Y.L[l];
-                    const int row = L.dw_m == 128 ? pt : q * 16 + lane;           // M = 64: 16 rows per TMEM subpartition
+                    const int row = L.dw_m == 128 ? q * 32 + lane : q * 16 + lane;           // M = 64: 16 rows per TMEM subpartition
                     const bool row_ok = L.dw_m == 128 || lane < 16;
                     const int nch = L.dw_n >> 3, per = (nch + kParts - 1) / kParts;
                     const int c_lo = part * per, c_hi = min(nch, (part + 1) * per);
@@ -512,8 +522,9 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------------------------
-static bool make_layout(const Problem& p, Layout& Y, bool overlap) {
+static bool make_layout(const Problem& p, Layout& Y, bool overlap, int tp) {
     Y = Layout{};
+    Y.tp = tp;
     Y.nl = p.desc.n_layers;
     Y.act = p.desc.activation;
     Y.s0 = p.desc.layer_sizes[0];
@@ -530,7 +541,7 @@ static bool make_layout(const Problem& p, Layout& Y, bool overlap) {
         L.np = up16(L.n);
         if (L.kin > 128 || L.np > 256) return false;
         L.a_off = off;
-        L.a_part = kTP * L.kp * 2;
+        L.a_part = tp * L.kp * 2;
         off += 3 * L.a_part;
         L.coff = coff;
         coff += L.kin * L.n;
@@ -542,13 +553,13 @@ static bool make_layout(const Problem& p, Layout& Y, bool overlap) {
     {
         Layer& O = Y.L[Y.nl];
         O.g_off = off;
-        O.g_part = kTP * 16 * 2;
+        O.g_part = tp * 16 * 2;
         O.g_overlap = 1;
         off += 3 * O.g_part;
     }
     for (int l = Y.nl - 1; l >= 1; --l) {
         Layer& L = Y.L[l];
-        L.g_part = kTP * L.np * 2;
+        L.g_part = tp * L.np * 2;
         if (l == Y.nl - 1 && overlap) {
             L.g_off = off;
             L.g_overlap = 1;
@@ -573,7 +584,7 @@ static bool make_layout(const Problem& p, Layout& Y, bool overlap) {
     }
     Y.zero_bytes = off;
     Y.rec_off = off;
-    Y.rec_bytes = ((kTP * p.rs * 4) + 15) & ~15;
+    Y.rec_bytes = ((tp * p.rs * 4) + 15) & ~15;
     off += 2 * Y.rec_bytes;
     Y.bar_off = off;
     off += 16 + 8 * (kThreads / 32) + 16;
@@ -617,13 +628,23 @@ int try_launch_logpost_gen_tc(const Problem& p, const EvalArgs& a, const float* 
     if (!enabled) return 0;
     gtc::Layout Y;
     static const bool want_overlap = [] { const char* e = getenv("OCBNN_GEN_TC_OVERLAP"); return e ? atoi(e) != 0 : true; }();
-    bool ok = want_overlap && gtc::make_layout(p, Y, true) && Y.smem_bytes + 2048 <= p.max_smem_optin;
-    if (!ok) ok = gtc::make_layout(p, Y, false) && Y.smem_bytes + 2048 <= p.max_smem_optin;   // dZ in place: one array less
+    // 128-point tiles (all TMEM lanes, full warps in the epilogues) when the operand arrays fit one SM, else 64-point tiles; with
+    // an array of its own for dZ (GEMM3 retires under the epilogue) when that fits too, else dZ in place.  A point set of at most
+    // 64 points (recid: 62 per minibatch + constraint points) never needs the larger tile.
+    static const int force_tp = [] { const char* e = getenv("OCBNN_GEN_TC_TP"); return e ? atoi(e) : 0; }();
+    const int npts = (a.with_data ? batch_count(a.n_train, a.batch_offset, a.batch_stride) : 0) + a.n_cpoints;
+    bool ok = false;
+    for (int tp : {128, 64}) {
+        if (force_tp ? tp != force_tp : (tp == 128 && npts <= 64)) continue;
+        for (int ov = want_overlap ? 1 : 0; ov >= 0 && !ok; --ov) ok = gtc::make_layout(p, Y, ov != 0, tp) && Y.smem_bytes + 2048 <= p.max_smem_optin;
+        if (ok) break;
+    }
     if (!ok) return 0;
     auto launch = [&]() -> int {
-        OCBNN_CUDA(cudaFuncSetAttribute(gtc::k_logpost_gen_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, Y.smem_bytes));
+        auto kern = Y.tp == 128 ? gtc::k_logpost_gen_tc<128> : gtc::k_logpost_gen_tc<64>;
+        OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Y.smem_bytes));
         const long long grid = m < (long long)p.sm_count ? m : (long long)p.sm_count;
-        gtc::k_logpost_gen_tc<<<(unsigned)grid, gtc::kThreads, Y.smem_bytes, st>>>(a, Y, w, m, out_lp, out_grad);
+        kern<<<(unsigned)grid, gtc::kThreads, Y.smem_bytes, st>>>(a, Y, w, m, out_lp, out_grad);
         OCBNN_LAUNCH_CHECK();
         return OCBNN_OK;
     };
