@@ -479,7 +479,11 @@ def test_full_size_properties_hmc_262144_chains_and_svgd_4096_particles():
     # credit / recid run the tensor variant by default: force the SIMT register-tile variant, both backward schedules
     (dict(OCBNN_GEN_TC="0", OCBNN_GEN_MMA="0", OCBNN_GEN_SCHED="1"), "test_k1_logpost_and_grad and (credit or recid)"),
     (dict(OCBNN_GEN_TC="0", OCBNN_GEN_MMA="0", OCBNN_GEN_SCHED="0", OCBNN_GEN_TP="16"), "test_k1_logpost_and_grad and (credit or odd)"),
-], ids=["tensor_path_forced", "mma_sync_path_forced", "simt_path_forced", "simt_16_point_tiles"])
+    # tcgen05 kernel (gen_tc.cu): 64-point tiles (MMA M = 64) and the in-place dZ layout on nets that default to 128-point tiles /
+    # their own dZ array
+    (dict(OCBNN_GEN_TC_TP="64"), "test_k1_logpost_and_grad and (credit or odd or deep or wide1)"),
+    (dict(OCBNN_GEN_TC_TP="128", OCBNN_GEN_TC_OVERLAP="0"), "test_k1_logpost_and_grad and (credit or odd or deep)"),
+], ids=["tensor_path_forced", "mma_sync_path_forced", "simt_path_forced", "simt_16_point_tiles", "tcgen05_64_point_tiles", "tcgen05_dz_in_place"])
 def test_generic_net_kernel_variants(env, select):
     """The generic-net K1 picks its variant (tile size, threads, SIMT / tensor path) from the net's shared-memory footprint; the
     variant knobs are read once per process, so each combination runs the K1 parity test in a child process."""
