@@ -546,10 +546,11 @@ extern "C" OCBNN_API int ocbnn_svgd_step(ocbnn_problem* ph, float* x_all, float*
 
     // ---- phi (K3b) and Adagrad (K3c) on the owned rows, then the particles go round ----
     if (n_rows > 0) {
-        if (tensor) rc = tc::tc_svgd_phi(g_all, h, n, d, row_begin, n_rows, phi, tcws, st);
+        // particles.grad = -phi (inference.py:280); on the tensor path the Adagrad update rides in the finalize kernel of phi
+        if (tensor) rc = tc::tc_svgd_phi(g_all, h, n, d, row_begin, n_rows, phi, tcws, st, x_all + row_begin * d, acc, lr);
         else rc = simt_phi(x_all, g_all, n, d, row_begin, n_rows, h, phi, d > 64 ? reinterpret_cast<float*>(tcws) : nullptr, st);
         if (rc) return rc;
-        if ((rc = adagrad_launch(x_all + row_begin * d, acc, phi, n_rows * d, lr, -1.f, st))) return rc;      // particles.grad = -phi (inference.py:280)
+        if (!tensor && (rc = adagrad_launch(x_all + row_begin * d, acc, phi, n_rows * d, lr, -1.f, st))) return rc;
     }
     return comm_all_gather_rows(comm, x_all, n, d, st);
 }

@@ -801,7 +801,7 @@ k_vt_split(const float* __restrict__ g, const float* __restrict__ xc_hi, const f
 __global__ void __launch_bounds__(256)
 k_phi_finalize(const float* __restrict__ o, int splits, const float* __restrict__ rowsum, int rs_splits, const float* __restrict__ xc_hi,
                const float* __restrict__ xc_lo, const float* __restrict__ hptr, long long n, int d, int dp, long long row_begin, long long n_rows,
-               float* __restrict__ phi) {
+               float* __restrict__ phi, float* __restrict__ ad_x, float* __restrict__ ad_acc, float ad_lr) {
     const float c2 = 2.f / *hptr, invn = 1.f / (float)n;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long tot = n_rows * d, stride = (long long)gridDim.x * blockDim.x;
@@ -818,7 +818,16 @@ k_phi_finalize(const float* __restrict__ o, int splits, const float* __restrict_
         const float xi = xc_hi[i * dp + c] + xc_lo[i * dp + c];
         float rsum = 0.f;                       // rs_splits partial row sums (fused path) or one finished sum
         for (int sp = 0; sp < rs_splits; ++sp) rsum += rowsum[(long long)sp * n_rows + t];
-        phi[idx] = (og - c2 * (ox - xi * rsum)) * invn;
+        const float v = (og - c2 * (ox - xi * rsum)) * invn;
+        phi[idx] = v;
+        if (ad_x) {
+            // K3c fused (same arithmetic as k_adagrad with grad = -phi, inference.py:280): one launch less on the epoch's chain
+            const float gr = -v;
+            const float a = __fadd_rn(ad_acc[idx], __fmul_rn(gr, gr));
+            ad_acc[idx] = a;
+            const float sd = __fadd_rn(sqrtf(a), 1e-10f);
+            ad_x[idx] = __fadd_rn(ad_x[idx], __fmul_rn(-ad_lr, __fdiv_rn(gr, sd)));
+        }
     }
 }
 
@@ -947,7 +956,7 @@ static int launch_flash(const TcWs& w, const float* h, cudaStream_t st) {
     return OCBNN_OK;
 }
 
-static int tc_phi(const TcWs& w, const float* g, const float* h, float* phi, cudaStream_t st) {
+static int tc_phi(const TcWs& w, const float* g, const float* h, float* phi, float* ad_x, float* ad_acc, float ad_lr, cudaStream_t st) {
     dim3 gv((unsigned)((w.n4 + 31) / 32), (unsigned)(2 * w.dp / 32));
     k_vt_split<<<gv, 256, 0, st>>>(g, w.xc_hi, w.xc_lo, w.n, w.n4, (int)w.d, (int)w.dp, w.vt_hi, w.vt_lo, w.r, h, w.ncr, (long long)w.fl_nj * 64);
     OCBNN_LAUNCH_CHECK();
@@ -957,7 +966,7 @@ static int tc_phi(const TcWs& w, const float* g, const float* h, float* phi, cud
         else rc = launch_flash<64, 1>(w, h, st);
         if (rc) return rc;
         k_phi_finalize<<<grid_for_ll(w.n_rows * w.d), 256, 0, st>>>(w.o, w.fl_splits, w.k_hi, 2 * w.fl_splits, w.xc_hi, w.xc_lo, h,
-                                                                  w.n, (int)w.d, (int)w.dp, w.row_begin, w.n_rows, phi);
+                                                                  w.n, (int)w.d, (int)w.dp, w.row_begin, w.n_rows, phi, ad_x, ad_acc, ad_lr);
         OCBNN_LAUNCH_CHECK();
         return OCBNN_OK;
     }
@@ -973,7 +982,7 @@ static int tc_phi(const TcWs& w, const float* g, const float* h, float* phi, cud
                     : launch_gemm<128>(ta_hi, ta_lo, tb_hi, tb_lo, epi, w.n_rows, 2 * w.dp, w.n4, w.splits, st);
     if (rc) return rc;
     k_phi_finalize<<<grid_for_ll(w.n_rows * w.d), 256, 0, st>>>(w.o, w.splits, w.rowsum, 1, w.xc_hi, w.xc_lo, h, w.n, (int)w.d, (int)w.dp, w.row_begin,
-                                                              w.n_rows, phi);
+                                                              w.n_rows, phi, ad_x, ad_acc, ad_lr);
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }
@@ -1063,8 +1072,10 @@ int tc_svgd_sel_update(long long n, long long d, long long row_begin, long long 
     OCBNN_LAUNCH_CHECK();
     return OCBNN_OK;
 }
-int tc_svgd_phi(const float* g, const float* h, long long n, long long d, long long row_begin, long long n_rows, float* phi, void* ws, cudaStream_t st) {
-    return tc_phi(carve(ws, n, d, row_begin, n_rows), g, h, phi, st);
+// ad_x / ad_acc (n_rows x d, or NULL): the owned particle rows and their Adagrad accumulator, updated with grad = -phi by the finalize kernel
+int tc_svgd_phi(const float* g, const float* h, long long n, long long d, long long row_begin, long long n_rows, float* phi, void* ws, cudaStream_t st,
+                float* ad_x, float* ad_acc, float ad_lr) {
+    return tc_phi(carve(ws, n, d, row_begin, n_rows), g, h, phi, ad_x, ad_acc, ad_lr, st);
 }
 
 }  // namespace tc

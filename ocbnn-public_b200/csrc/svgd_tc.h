@@ -25,6 +25,7 @@ int tc_svgd_sel_stage2(long long n, long long d, long long row_begin, long long 
 int tc_svgd_sel_hist(long long n, long long d, long long row_begin, long long n_rows, int rank, int world, int pass, void* ws, unsigned** hist_out,
                      cudaStream_t st);
 int tc_svgd_sel_update(long long n, long long d, long long row_begin, long long n_rows, int pass, void* ws, float* out_h, cudaStream_t st);
-int tc_svgd_phi(const float* g, const float* h, long long n, long long d, long long row_begin, long long n_rows, float* phi, void* ws, cudaStream_t st);
+int tc_svgd_phi(const float* g, const float* h, long long n, long long d, long long row_begin, long long n_rows, float* phi, void* ws, cudaStream_t st,
+                float* ad_x = nullptr, float* ad_acc = nullptr, float ad_lr = 0.f);
 }  // namespace tc
 }  // namespace ocbnn
