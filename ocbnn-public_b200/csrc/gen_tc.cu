@@ -163,7 +163,7 @@ __device__ __forceinline__ float head_switch(int sk, int kind, const float (&z)[
     }
 }
 
-template <int kTP>
+template <int kTP, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __restrict__ w, long long m, float* __restrict__ out_lp,
                  float* __restrict__ out_grad) {
@@ -332,7 +332,8 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
                     const Layer& N = Y.L[l + 1];
                     const int nch = N.kp >> 3, per = (nch + kParts - 1) / kParts;
                     const int c_lo = part * per, c_hi = min(nch, (part + 1) * per);
-                    const int n_real = L.n, np = L.np, act = Y.act, a_off = N.a_off, a_part = N.a_part;
+                    const int n_real = L.n, np = L.np, a_off = N.a_off, a_part = N.a_part;
+                    constexpr int act = ACT;                 // compile-time activation: the per-element dispatch folds away
                     for (int c0 = c_lo; c0 < c_hi; c0 += kBatch) {
                         uint32_t raw[kBatch][8];
 #pragma unroll
@@ -436,7 +437,8 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
                     const Layer& P = Y.L[l - 1];
                     const int nch = P.np >> 3, per = (nch + kParts - 1) / kParts;
                     const int c_lo = part * per, c_hi = min(nch, (part + 1) * per);
-                    const int n_real = P.n, act = Y.act, pg_off = P.g_off, pg_part = P.g_part;
+                    const int n_real = P.n, pg_off = P.g_off, pg_part = P.g_part;
+                    constexpr int act = ACT;
                     const uint32_t t_da = tmem + lane_base + (uint32_t)Y.da_col, t_z = tmem + lane_base + (uint32_t)P.z_col;
                     for (int c0 = c_lo; c0 < c_hi; c0 += kBatch) {
                         uint32_t rd[kBatch][8], rz[kBatch][8];
@@ -641,7 +643,12 @@ int try_launch_logpost_gen_tc(const Problem& p, const EvalArgs& a, const float* 
     }
     if (!ok) return 0;
     auto launch = [&]() -> int {
-        auto kern = Y.tp == 128 ? gtc::k_logpost_gen_tc<128> : gtc::k_logpost_gen_tc<64>;
+        void (*kern)(EvalArgs, const gtc::Layout, const float*, long long, float*, float*) = nullptr;
+        const int act = p.desc.activation;
+        if (Y.tp == 128) kern = act == OCBNN_ACT_RBF ? gtc::k_logpost_gen_tc<128, OCBNN_ACT_RBF> : act == OCBNN_ACT_RELU ? gtc::k_logpost_gen_tc<128, OCBNN_ACT_RELU>
+                                                                                                                        : gtc::k_logpost_gen_tc<128, OCBNN_ACT_IDENTITY>;
+        else kern = act == OCBNN_ACT_RBF ? gtc::k_logpost_gen_tc<64, OCBNN_ACT_RBF> : act == OCBNN_ACT_RELU ? gtc::k_logpost_gen_tc<64, OCBNN_ACT_RELU>
+                                                                                                        : gtc::k_logpost_gen_tc<64, OCBNN_ACT_IDENTITY>;
         OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Y.smem_bytes));
         const long long grid = m < (long long)p.sm_count ? m : (long long)p.sm_count;
         kern<<<(unsigned)grid, gtc::kThreads, Y.smem_bytes, st>>>(a, Y, w, m, out_lp, out_grad);
