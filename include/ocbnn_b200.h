@@ -119,6 +119,8 @@ OCBNN_API int ocbnn_problem_nweights(const ocbnn_problem *p, int64_t *out_d);
 
 /* K1 — log posterior / log prior value and gradient for M packed weight vectors.
  * Replaces forward + log_prior + log_likelihood + autograd .backward() (base.py:89-133,252-265,344-388,432-444,498-511,528-542).
+ * with_data: 0 log prior, 1 log posterior, 2 log likelihood alone (log_likelihood, base.py:252-265,432-444,524-542 - evaluated on its
+ * own rather than as posterior - prior, which cancels digits when the prior term is large).
  * batch_stride <= 1 means full batch.  out_lp (M) and out_grad (M x D) may each be NULL.
  * lanes: threads cooperating on one weight vector (0 = choose). */
 OCBNN_API int ocbnn_logpost_grad(ocbnn_problem *p, const float *w, int64_t m, int32_t batch_offset, int32_t batch_stride,

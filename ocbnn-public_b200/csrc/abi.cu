@@ -253,7 +253,9 @@ extern "C" OCBNN_API int ocbnn_problem_create(const ocbnn_desc* desc, ocbnn_prob
         pri[i] = make_float2(mu, 1.f / (sd * sd));
     }
     cudaError_t e = cudaMalloc(&p->pts, pts.size() * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&p->pri, pri.size() * sizeof(float2));
+    // the prior table is followed by a second one of zeros (mean 0, 1/var 0): what a likelihood-only evaluation points at
+    if (e == cudaSuccess) e = cudaMalloc(&p->pri, 2 * pri.size() * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMemset(p->pri, 0, 2 * pri.size() * sizeof(float2));
     if (e == cudaSuccess) e = cudaMemcpy(p->pts, pts.data(), pts.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->pri, pri.data(), pri.size() * sizeof(float2), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -317,6 +319,11 @@ extern "C" OCBNN_API int ocbnn_logpost_grad(ocbnn_problem* h, const float* w, in
     const ProblemImpl& p = *reinterpret_cast<ProblemImpl*>(h);
     OCBNN_REQUIRE(batch_stride <= 1 || (batch_offset >= 0 && batch_offset < batch_stride), OCBNN_EINVAL, "batch_offset must be in [0, stride)");
     EvalArgs a = eval_args(p, batch_offset, batch_stride, with_data);
+    if (with_data == 2) {       // likelihood only: no constraint rows, no prior constants, the all-zero prior table
+        a.n_cpoints = a.n_pos = a.n_neg = a.n_dir = 0;
+        a.const_prior = 0.0;
+        a.pri = p.pri + p.d;
+    }
     return logpost_any(p, a, w, m, out_lp, out_grad, lanes, (cudaStream_t)stream);
 }
 

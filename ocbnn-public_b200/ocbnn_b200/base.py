@@ -130,11 +130,10 @@ class BayesianNeuralNetwork:
         return lp.cpu()[0]
 
     def log_likelihood(self, batch_indices=None):
-        prob = self.engine_problem()
-        W = self._weights_matrix()
-        post, _ = prob.logpost_grad(W, batch_spec(batch_indices, self.N_train), True, want_grad=False)
-        prior, _ = prob.logpost_grad(W, (0, 1), False, want_grad=False)
-        return (post.double() - prior.double()).float().cpu()[0]
+        """log_likelihood of the task mixin (base.py:252-265, 432-444, 524-542), evaluated on its own by K1 (no prior table, no
+        constraint rows) rather than as posterior - prior."""
+        lp, _ = self.engine_problem().logpost_grad(self._weights_matrix(), batch_spec(batch_indices, self.N_train), "likelihood", want_grad=False)
+        return lp.cpu()[0]
 
     def isotropic_gaussian_prior(self, weights=None, mean=0, std=None):
         """Isotropic Gaussian prior (base.py:127-133) — host arithmetic, not on the sampler path."""

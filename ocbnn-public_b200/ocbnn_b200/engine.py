@@ -226,7 +226,8 @@ class DeviceProblem:
         M = W.shape[0]
         lp = (out_lp if out_lp is not None else torch.empty(M, device=W.device)) if want_lp else None
         g = (out_grad if out_grad is not None else torch.empty_like(W)) if want_grad else None
-        check(lib().ocbnn_logpost_grad(self._h, _ptr(W), M, int(batch[0]), int(batch[1]), int(bool(with_data)), _ptr(lp), _ptr(g),
+        mode = 2 if with_data == "likelihood" else int(bool(with_data))
+        check(lib().ocbnn_logpost_grad(self._h, _ptr(W), M, int(batch[0]), int(batch[1]), mode, _ptr(lp), _ptr(g),
                                        int(lanes), _stream()))
         return lp, g
 
