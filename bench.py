@@ -551,7 +551,7 @@ def bench_hmc(cx):
     peak_ffma2, peak_ffma, peak_mufu = engine.probe_peak(1), engine.probe_peak(0), engine.probe_peak(2)
     ker_s = ms_total * 1e-3 / K                      # one launch per step: the event brackets exactly that kernel
     ach_flops, ach_mufu = M * L * flop_step / ker_s, M * L * mufu_step / ker_s
-    traffic = ncu_traffic("r01_hmc_ncu.json", chains=M, leapfrog_l=L)
+    traffic = ncu_traffic("r02_hmc_ncu.json", chains=M, leapfrog_l=L)
     # The toy nets keep all state on chip: ~7 B of HBM traffic per chain-step, so neither the HBM nor the tensor roofline binds.
     # The binding pipe is the one with the larger fraction of its measured peak: MUFU (exp2/rcp, 16 op/clk/SM) vs fp32 FMA.
     mufu_frac, fp32_frac = ach_mufu / peak_mufu, ach_flops / peak_ffma2

@@ -152,11 +152,18 @@ static void flash_plan(long long n, long long n_rows, int dp, int* tiles, int* s
     const int nj = (int)((n + 63) / 64);
     const int t = (dp == 32 && n_rows > 128) ? 2 : 1;
     const long long row_blocks = (n_rows + 128 * t - 1) / (128 * t);
-    // as many column splits as fit ONE wave of 148 CTAs (a 149th CTA would double the kernel time).  A CTA walks all column blocks
-    // of its split; the accumulation chain limit is handled inside the kernel (accumulators drained every kFlashChainBlocks blocks).
-    long long want = 148 / row_blocks;
-    if (want < 1) want = 1;
-    int p = (int)((nj + want - 1) / want);
+    // Column splits: one CTA per SM, so the kernel time is (waves of 148 CTAs) x (column blocks per CTA).  Up to n = 4096 one wave
+    // is best (a 149th CTA would double the time); for more rows than SMs several waves of shorter CTAs waste less of the last wave
+    // (n = 32768: 128 row blocks x 8 splits = 7 waves x 64 blocks instead of 1 wave x 512 on 128 of the 148 SMs).  The accumulation
+    // chain limit is handled inside the kernel (accumulators drained every kFlashChainBlocks blocks).
+    int best_s = 1;
+    long long best_cost = -1;
+    for (int sp = 1; sp <= 32 && sp <= nj; ++sp) {
+        const long long waves = (row_blocks * sp + 147) / 148, per_cta = (nj + sp - 1) / sp;
+        const long long cost = waves * per_cta * 64 + sp;          // (+ sp: fewer partial outputs on ties)
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = sp; }
+    }
+    int p = (nj + best_s - 1) / best_s;
     if (p < 1) p = 1;
     *tiles = t;
     *per = p;
