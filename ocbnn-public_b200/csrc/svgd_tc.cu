@@ -160,7 +160,9 @@ static void flash_plan(long long n, long long n_rows, int dp, int* tiles, int* s
     long long best_cost = -1;
     for (int sp = 1; sp <= 32 && sp <= nj; ++sp) {
         const long long waves = (row_blocks * sp + 147) / 148, per_cta = (nj + sp - 1) / sp;
-        const long long cost = waves * per_cta * 64 + sp;          // (+ sp: fewer partial outputs on ties)
+        // a CTA costs ~5 column blocks on top of its own (TMEM allocation, the row tile's X into TMEM, the drain): measured at
+        // n = 16384 (16 splits, 7 waves: 313 us against 280 us for 2 splits in one wave) and n = 32768 (8 splits: 966 against 1025 us)
+        const long long cost = waves * (per_cta + 5) * 64 + sp;    // (+ sp: fewer partial outputs on ties)
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = sp; }
     }
     int p = (nj + best_s - 1) / best_s;
