@@ -346,7 +346,7 @@ extern "C" OCBNN_API int ocbnn_hmc_iterate(ocbnn_problem* h, float* q, const flo
     const float e = (float)eps, eh = (float)(eps / 2);
     if (small_net_supported(p)) {
         int pts = (a.with_data ? (int)a.n_train : 0) + a.n_cpoints;
-        if (lanes <= 0) lanes = choose_lanes(p, m, pts);
+        if (lanes <= 0) lanes = choose_lanes_hmc(p, m, pts);
         return launch_hmc_small(p, a, q, p0, u, m, n_it, e, eh, leapfrog_l, restore_on_reject, out_accept, out_h, out_flags, out_samples,
                                 thin, lanes, st);
     }

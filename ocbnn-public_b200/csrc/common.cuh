@@ -107,6 +107,7 @@ int try_launch_logpost_gen_tc(const Problem& p, const EvalArgs& a, const float* 
                               cudaStream_t st, int* rc);
 
 int choose_lanes(const Problem& p, long long m, int points);
+int choose_lanes_hmc(const Problem& p, long long m, int points);
 
 // abi.cu: evaluation arguments of a (minibatch, with_data) pair and K1 on whichever kernel family serves the net
 EvalArgs eval_args(const Problem& p, int offset, int stride, int with_data);

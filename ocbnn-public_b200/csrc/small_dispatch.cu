@@ -1,4 +1,5 @@
 // small_dispatch.cu — routes a problem to the register-resident kernels of its net shape (if instantiated).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace ocbnn {
@@ -45,6 +46,16 @@ int choose_lanes(const Problem& p, long long m, int points) {
     const long long want = (long long)p.sm_count * 6 * 32;      // measured: 4096 chains run best with 8 lanes (6.1e8 vs 5.5e8 at 16)
     int g = 1;
     while (g < 32 && m * g < want && 2 * g <= (points > 0 ? points : 1)) g *= 2;
+    return g;
+}
+
+// HMC: nets served by the slot-ownership kernel (k_hmc_own: one input, one output, rbf, <= 16 slots) run 16 lanes where the rule above
+// says 8 (measured, W2, 4096 chains: 0.89 G steps/s at 16 lanes with ownership, 0.83 G at 8 lanes replicated, 0.72 G at 16 replicated)
+int choose_lanes_hmc(const Problem& p, long long m, int points) {
+    int g = choose_lanes(p, m, points);
+    const SmallEntry* e = find_small(p);
+    static const bool want_own = [] { const char* v = getenv("OCBNN_HMC_OWN"); return v ? atoi(v) != 0 : true; }();
+    if (want_own && g == 8 && e && e->s0 == 1 && e->sk == 1 && e->act == OCBNN_ACT_RBF && e->h <= 10 && points >= 32) g = 16;
     return g;
 }
 

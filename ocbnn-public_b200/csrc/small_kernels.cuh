@@ -174,6 +174,195 @@ k_hmc_small(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, 
     }
 }
 
+// ---- K2, few chains: 16 / 32 lanes per chain with slot ownership ---------------------------------------------------------------------
+// With a few thousand chains the one-lane and 8-lane kernels above leave < 2 warps per scheduler and run at the latency of one
+// leapfrog step.  More lanes per chain hide that latency, but k_hmc_small replicates the whole leapfrog update, the prior and the
+// gradient butterfly (log2 G x NS float2 shuffles) on every lane - at 16 / 32 lanes that costs more than it hides (measured:
+// 0.72 / 0.47 G steps/s against 0.88 G at 8 lanes).  Here lane r of a chain's 16-lane group OWNS slot r (one float2 of q, p, g):
+//   * the gradient partials of the lanes meet by a recursive-halving REDUCE-SCATTER (8 + 4 + 2 + 1 float2 exchanges instead of
+//     4 x 16), after which each lane holds the total of its own slot;
+//   * moments -> gradient, prior and the leapfrog update touch the own slot only (one extra exchange brings the neighbouring
+//     moment the transform needs);
+//   * the evaluation copy of all weights is rebuilt by an all-gather of the owned slots (16 float2 shuffles) each step;
+//   * q and p live in registers (no shared-memory columns); 32 lanes = two 16-lane groups that split the points and first add
+//     their partials.
+// Single-input single-output rbf nets (the moment form of the gradient, use_moments<N>) with <= 16 slots: the [1,10,1] repro nets.
+template <class N, int G, int MB, int U>
+__global__ void __launch_bounds__(kSmallThreads, MB)
+k_hmc_own(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, const double* __restrict__ u, long long m, int n_it,
+          float eps, float eps_half, int L, int restore, uint8_t* __restrict__ out_acc, float* __restrict__ out_h,
+          int* __restrict__ out_flags, float* __restrict__ out_samples, int thin, int tile_cap) {
+    static_assert(use_moments<N>() && N::NS <= 16 && (G == 16 || G == 32), "slot-ownership HMC: moment-form nets with <= 16 slots, 16 or 32 lanes");
+    constexpr unsigned kFull = 0xffffffffu;
+    extern __shared__ __align__(16) float smem[];
+    float4* pri_s = reinterpret_cast<float4*>(smem);
+    float* tab = smem + kSmemFixedFloats(N::NS);
+    EvalCtx c = make_ctx(a, tab, pri_s, tile_cap);
+    load_pri_slots<N>(pri_s, a);
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x % G;
+    const int own = lane & 15;                                   // the slot this lane owns
+    const bool active = gid < m;
+    const long long chain = active ? gid : m - 1;
+    const bool owner = active && lane < 16 && own < N::NS;       // writes its slot; lane 0 also writes the per-chain scalars
+    const bool multi = c.npts > c.tile_cap;
+    const int i0 = own < N::NS ? N::cidx(own, 0) : -1, i1 = own < N::NS ? N::cidx(own, 1) : -1;
+    const int hp = own % N::HP;
+
+    auto load_own = [&](const float* __restrict__ src) { return make_float2(i0 >= 0 ? __ldg(src + i0) : 0.f, i1 >= 0 ? __ldg(src + i1) : 0.f); };
+    auto store_own = [&](float2 v, float* __restrict__ dst) {
+        if (i0 >= 0) dst[i0] = v.x;
+        if (i1 >= 0) dst[i1] = v.y;
+    };
+    auto sum16 = [&](double v) {                                  // over the 16 lanes of the group (every lane gets the same bits)
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+        return v;
+    };
+
+    float2 q_own = load_own(q_io + chain * N::D), p_own = f2(0.f), g_own = f2(0.f), q0_own = q_own;
+    float lp = 0.f, U0 = 0.f, K0 = 0.f;
+    int nan_flag = 0, it = 0, l = 0;
+    bool first = true;
+    __syncthreads();                                              // pri_s
+
+    // value and gradient at q: the gradient of the OWN slot in g_own, the value on every lane
+    auto evaluate_own = [&]() {
+        float2 w[N::NS], g[N::NS];
+#pragma unroll
+        for (int s = 0; s < N::NS; ++s) {                         // all-gather of the owned slots -> evaluation copy (W1, b1 scaled)
+            const float2 v = make_float2(__shfl_sync(kFull, q_own.x, s, 16), __shfl_sync(kFull, q_own.y, s, 16));
+            w[s] = (s < N::SW2 && act_in_scale<N::ACT>() != 1.f) ? __fmul2_rn(v, f2(act_in_scale<N::ACT>())) : v;
+            g[s] = f2(0.f);
+        }
+        double lpd = 0.0;
+        eval_points<N, G, U>(a, c, first, RegW<N::NS>{w}, g, lpd, lane);
+        float2 r[16];
+#pragma unroll
+        for (int s = 0; s < 16; ++s) r[s] = s < N::NS ? g[s] : f2(0.f);
+        if (G == 32) {
+#pragma unroll
+            for (int s = 0; s < 16; ++s) {
+                r[s].x += __shfl_xor_sync(kFull, r[s].x, 16);
+                r[s].y += __shfl_xor_sync(kFull, r[s].y, 16);
+            }
+        }
+        // recursive halving: after the stage with offset o the lane keeps the slots whose index agrees with its own in bit o
+        float2 r8[8], r4[4], r2[2], acc;
+        {
+            const bool up = (lane & 8) != 0;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const float2 send = up ? r[s] : r[s + 8], keep = up ? r[s + 8] : r[s];
+                r8[s] = make_float2(keep.x + __shfl_xor_sync(kFull, send.x, 8), keep.y + __shfl_xor_sync(kFull, send.y, 8));
+            }
+        }
+        {
+            const bool up = (lane & 4) != 0;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const float2 send = up ? r8[s] : r8[s + 4], keep = up ? r8[s + 4] : r8[s];
+                r4[s] = make_float2(keep.x + __shfl_xor_sync(kFull, send.x, 4), keep.y + __shfl_xor_sync(kFull, send.y, 4));
+            }
+        }
+        {
+            const bool up = (lane & 2) != 0;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const float2 send = up ? r4[s] : r4[s + 2], keep = up ? r4[s + 2] : r4[s];
+                r2[s] = make_float2(keep.x + __shfl_xor_sync(kFull, send.x, 2), keep.y + __shfl_xor_sync(kFull, send.y, 2));
+            }
+        }
+        {
+            const bool up = (lane & 1) != 0;
+            const float2 send = up ? r2[0] : r2[1], keep = up ? r2[1] : r2[0];
+            acc = make_float2(keep.x + __shfl_xor_sync(kFull, send.x, 1), keep.y + __shfl_xor_sync(kFull, send.y, 1));
+        }
+        // moments -> gradient (see evaluate()): the W1 slot needs A1 of the b1 slot, the b1 slot A0 of the W2 slot - both HP lanes up
+        const float2 other = make_float2(__shfl_sync(kFull, acc.x, (own + N::HP) & 15, 16), __shfl_sync(kFull, acc.y, (own + N::HP) & 15, 16));
+        float2 w1s = f2(0.f), b1s = f2(0.f), w2s = f2(0.f);
+#pragma unroll
+        for (int h = 0; h < N::HP; ++h)
+            if (hp == h) {
+                w1s = w[N::SW1 + h];
+                b1s = w[N::SB1 + h];
+                w2s = w[N::SW2 + h];
+            }
+        float2 gm = acc;
+        if (own < N::SW2) gm = __ffma2_rn(w1s, acc, __fmul2_rn(b1s, other));
+        // Gaussian prior on the own slot, rescaling of the data gradient (evaluate())
+        float pr = 0.f;
+        if (own < N::NS) {
+            const float4 mv = c.pri[own];
+            const float2 diff = __fadd2_rn(q_own, make_float2(-mv.x, -mv.y));
+            const float2 t = __fmul2_rn(diff, make_float2(mv.z, mv.w));
+            if (own < N::SW2) gm = __ffma2_rn(gm, __fmul2_rn(w2s, f2(grad_scale_for<N::ACT, true>())), make_float2(-t.x, -t.y));
+            else gm = __fadd2_rn(gm, make_float2(-t.x, -t.y));
+            const float2 e = __fmul2_rn(diff, t);
+            pr = e.x + e.y;
+        }
+        if (i0 < 0) gm.x = 0.f;
+        if (i1 < 0) gm.y = 0.f;
+        g_own = gm;
+        if (lane < 16) lpd -= 0.5 * (double)pr;
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) lpd += __shfl_xor_sync(kFull, lpd, off);
+        lp = (float)(lpd + c.lp_const);
+    };
+
+    auto begin_iteration = [&]() {
+        const float2 pv = load_own(p0 + ((long long)it * m + chain) * N::D);
+        U0 = -lp;
+        q0_own = q_own;                                           // for restore-on-reject
+        const float2 e = __fmul2_rn(pv, pv);
+        K0 = 0.5f * (float)sum16((double)e.x + (double)e.y);
+        p_own = __fadd2_rn(pv, __fmul2_rn(f2(eps_half), g_own));
+    };
+
+    for (;;) {
+        if (l >= 1) q_own = __fadd2_rn(q_own, __fmul2_rn(f2(eps), p_own));
+        evaluate_own();
+        first = false;
+        if (l == 0) {
+            begin_iteration();
+            l = 1;
+            continue;
+        }
+        p_own = __fadd2_rn(p_own, __fmul2_rn(f2((l < L) ? eps : eps_half), g_own));
+        if (l < L) {
+            ++l;
+            continue;
+        }
+        // end of the trajectory: Metropolis-Hastings (same arithmetic as k_hmc_small)
+        const bool isn = __any_sync(kFull, isnan(q_own.x) | isnan(q_own.y));       // (a 32-lane warp holds one or two chains: a NaN in
+        nan_flag |= isn ? 1 : 0;                                                    //  either flags both - diagnostics only)
+        const float2 e = __fmul2_rn(p_own, p_own);
+        const float U1 = -lp;
+        const float K1 = 0.5f * (float)sum16((double)e.x + (double)e.y);
+        const float dH = __fsub_rn(__fadd_rn(__fsub_rn(U0, U1), K0), K1);
+        const double alpha = (double)expf(dH);
+        const double ui = __ldg(u + (long long)it * m + chain);
+        const bool acc = ui < alpha;
+        if (active && lane == 0) {
+            if (out_acc) out_acc[(long long)it * m + chain] = acc ? 1 : 0;
+            if (out_h) reinterpret_cast<float4*>(out_h)[(long long)it * m + chain] = make_float4(U0, K0, U1, K1);
+        }
+        const bool need_eval = restore && !acc;
+        if (need_eval) q_own = q0_own;
+        if (out_samples && thin > 0 && ((it + 1) % thin == 0) && owner) store_own(q_own, out_samples + ((long long)((it + 1) / thin - 1) * m + chain) * N::D);
+        if (++it == n_it) break;
+        const bool again = multi ? (__syncthreads_or(need_eval ? 1 : 0) != 0) : (__any_sync(kFull, need_eval) != 0);
+        if (again) {
+            l = 0;
+            continue;
+        }
+        begin_iteration();
+        l = 1;
+    }
+    if (owner) store_own(q_own, q_io + chain * N::D);
+    if (active && lane == 0 && out_flags) out_flags[chain] = nan_flag;
+}
+
 // ---- K4 ------------------------------------------------------------------------------------------------
 // SGLD (bnn/inference.py:304-340): upd = (grad log prior + grad log lik) * (eps_t/2) + noise_t ; w += upd.
 template <class N, int G>
@@ -269,6 +458,22 @@ struct SmallLaunch {
         OCBNN_LAUNCH_CHECK();
         return OCBNN_OK;
     }
+    template <int G, int MB, int U>
+    static int hmc_own(const Problem& p, const EvalArgs& a, float* q, const float* p0, const double* u, long long m, int n_it, float eps,
+                       float eps_half, int L, int restore, uint8_t* acc, float* h, int* flags, float* samples, int thin, cudaStream_t st) {
+        if constexpr (use_moments<N>() && N::NS <= 16 && (G == 16 || G == 32)) {
+            int tile_cap;
+            size_t sm = smem_bytes(p, npts(a), tile_cap);
+            auto k = k_hmc_own<N, G, MB, U>;
+            OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            long long blocks = (m * G + kSmallThreads - 1) / kSmallThreads;
+            k<<<(unsigned)blocks, kSmallThreads, sm, st>>>(a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, tile_cap);
+            OCBNN_LAUNCH_CHECK();
+            return OCBNN_OK;
+        } else {
+            return OCBNN_EUNSUPPORTED;
+        }
+    }
     // One chain per thread (G = 1, the large-M case) has tuning variants selected by OCBNN_HMC_MB (resident CTAs per SM
     // the kernel is compiled for: register cap 65536 / (128 MB)) and OCBNN_HMC_U (points in flight per thread); measured
     // defaults in kDefaultHmc*.  Lane-split chains (G > 1, few chains) use one configuration.
@@ -302,6 +507,15 @@ struct SmallLaunch {
             if (auto_cfg && N::NS <= 18 && a.n_cpoints >= 64) OCBNN_HMC_GO(3, 4);
             OCBNN_HMC_GO(4, 2);
 #undef OCBNN_HMC_GO
+        }
+        if constexpr ((G == 16 || G == 32) && use_moments<N>() && N::NS <= 16) {
+            // 16 / 32 lanes per chain: slot ownership (k_hmc_own).  OCBNN_HMC_OWN=0 selects the replicated k_hmc_small; OCBNN_HMC_GU the points in flight
+            static const bool want_own = [] { const char* e = getenv("OCBNN_HMC_OWN"); return e ? atoi(e) != 0 : true; }();
+            static const int gu = [] { const char* e = getenv("OCBNN_HMC_GU"); return e ? atoi(e) : 0; }();
+            if (want_own) {
+                if (gu == 4) return hmc_own<G, 3, 4>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
+                return hmc_own<G, 4, 2>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
+            }
         }
         if constexpr (G > 1 && G <= 8 && N::NS <= 18) {
             // few chains, 2-8 lanes per chain: four points in flight per lane at 3 CTAs/SM, as on the one-lane path (4096 chains x 8 lanes on

@@ -111,7 +111,7 @@ def test_k2_hmc_trajectory(name):
             args = (g[tag + "_p0"][it][None, None], g[tag + "_u"][it][None, None], cfg["hmc_epsilon"], L)
             q32, a32, H32 = orc.hmc_iterate(spec, q_start, *args, with_data=wd)
             q64, a64, H64 = orc.hmc_iterate(spec, q_start, *args, with_data=wd, dtype=np.float64)
-            for lanes in ((1, 4, 32) if name in SMALL_NETS else (0,)):
+            for lanes in ((1, 4, 16, 32) if name in SMALL_NETS else (0,)):
                 q = t2d(q_start)
                 acc, H, flags = prob.hmc_iterate(q, t2d(args[0]), t2d(args[1], torch.float64), cfg["hmc_epsilon"], L, wd, want_h=True, lanes=lanes)
                 assert int(flags[0]) == 0
@@ -146,7 +146,7 @@ def test_k2_chains_are_independent_and_restore_works():
     p0 = np.repeat(g["hmc_p0"][:n_it, None, :], M, 1)
     u = np.repeat(g["hmc_u"][:n_it, None], M, 1)
     u[u == np.inf] = 0.5
-    for lanes in (1, 8, 32):
+    for lanes in (1, 8, 16, 32):
         q = t2d(q0)
         acc, H, _ = prob.hmc_iterate(q, t2d(p0), t2d(u, torch.float64), cfg["hmc_epsilon"], L, True, want_h=True, lanes=lanes)
         qc = q.cpu().numpy()
