@@ -10,6 +10,7 @@ constexpr int kSmallThreads = 128;
 constexpr int kPointUnroll = OCBNN_POINT_UNROLL;
 // measured on B200 (W2, 262144 chains, G chain-leapfrog-steps/s): (MB,U) = (4,2) 2.03, (3,4) 2.06, (4,4) 2.05, (5,2) 1.98, (5,1) 1.93,
 // (3,6) 1.95.  (4,2) is the default: within 1.5 % of the best and it keeps short point segments (6 training points) in full groups.
+constexpr int kDefaultHmcOwn = 1;                    // 16 / 32 lanes per chain: k_hmc_own with shuffle (1) or shared-memory (2) exchanges
 constexpr int kDefaultHmcMb = 4, kDefaultHmcU = 2;   // points in flight per thread in K1 / K4
 
 __host__ __device__ constexpr int kSmemFixedFloats(int ns) { return 4 * ns; }   // float4 prior table per slot
@@ -187,7 +188,10 @@ k_hmc_small(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, 
 //   * q and p live in registers (no shared-memory columns); 32 lanes = two 16-lane groups that split the points and first add
 //     their partials.
 // Single-input single-output rbf nets (the moment form of the gradient, use_moments<N>) with <= 16 slots: the [1,10,1] repro nets.
-template <class N, int G, int MB, int U>
+// XS = true: the reduce-scatter and the all-gather go through shared memory (one STS.64 per slot and lane, then each lane sums its own
+// slot over the 16 lanes: 16 LDS.64 at an odd slot stride, conflict-free per half-warp) instead of shuffles + selects.
+constexpr int kOwnXsFloat2PerWarp = 16 * 33 + 2 * 16;      // exchange buffer of one warp: [16 slots][33] partials + [2 groups][16] weights
+template <class N, int G, int MB, int U, bool XS>
 __global__ void __launch_bounds__(kSmallThreads, MB)
 k_hmc_own(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, const double* __restrict__ u, long long m, int n_it,
           float eps, float eps_half, int L, int restore, uint8_t* __restrict__ out_acc, float* __restrict__ out_h,
@@ -196,11 +200,13 @@ k_hmc_own(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, co
     constexpr unsigned kFull = 0xffffffffu;
     extern __shared__ __align__(16) float smem[];
     float4* pri_s = reinterpret_cast<float4*>(smem);
-    float* tab = smem + kSmemFixedFloats(N::NS);
+    float2* xs = reinterpret_cast<float2*>(smem + kSmemFixedFloats(N::NS)) + (threadIdx.x >> 5) * kOwnXsFloat2PerWarp;   // this warp's exchange buffer
+    float* tab = smem + kSmemFixedFloats(N::NS) + (XS ? 2 * kOwnXsFloat2PerWarp * (kSmallThreads / 32) : 0);
     EvalCtx c = make_ctx(a, tab, pri_s, tile_cap);
     load_pri_slots<N>(pri_s, a);
     const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int lane = threadIdx.x % G;
+    const int wl = threadIdx.x & 31;                             // lane of the warp (a warp holds two 16-lane groups when G = 16)
     const int own = lane & 15;                                   // the slot this lane owns
     const bool active = gid < m;
     const long long chain = active ? gid : m - 1;
@@ -229,65 +235,98 @@ k_hmc_own(EvalArgs a, float* __restrict__ q_io, const float* __restrict__ p0, co
     // value and gradient at q: the gradient of the OWN slot in g_own, the value on every lane
     auto evaluate_own = [&]() {
         float2 w[N::NS], g[N::NS];
+        float2* wbuf = xs + 16 * 33 + (wl & 16);                  // this group's 16 evaluation weights
+        if (XS) {
+            // all-gather through shared memory: the owner stores its slot in evaluation units, everyone reads the 16 slots
+            __syncwarp();
+            wbuf[own] = (own < N::SW2 && act_in_scale<N::ACT>() != 1.f) ? __fmul2_rn(q_own, f2(act_in_scale<N::ACT>())) : q_own;
+            __syncwarp();
 #pragma unroll
-        for (int s = 0; s < N::NS; ++s) {                         // all-gather of the owned slots -> evaluation copy (W1, b1 scaled)
-            const float2 v = make_float2(__shfl_sync(kFull, q_own.x, s, 16), __shfl_sync(kFull, q_own.y, s, 16));
-            w[s] = (s < N::SW2 && act_in_scale<N::ACT>() != 1.f) ? __fmul2_rn(v, f2(act_in_scale<N::ACT>())) : v;
-            g[s] = f2(0.f);
+            for (int s = 0; s < N::NS; ++s) {
+                w[s] = wbuf[s];
+                g[s] = f2(0.f);
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < N::NS; ++s) {                     // all-gather of the owned slots -> evaluation copy (W1, b1 scaled)
+                const float2 v = make_float2(__shfl_sync(kFull, q_own.x, s, 16), __shfl_sync(kFull, q_own.y, s, 16));
+                w[s] = (s < N::SW2 && act_in_scale<N::ACT>() != 1.f) ? __fmul2_rn(v, f2(act_in_scale<N::ACT>())) : v;
+                g[s] = f2(0.f);
+            }
         }
         double lpd = 0.0;
         eval_points<N, G, U>(a, c, first, RegW<N::NS>{w}, g, lpd, lane);
-        float2 r[16];
+        float2 acc, w1s = f2(0.f), b1s = f2(0.f), w2s = f2(0.f);
+        if (XS) {
+            // reduce-scatter through shared memory: slot s of warp lane L at xs[s * 33 + L] (odd slot stride: the 16 lanes of a
+            // half-warp read 16 different bank pairs); lane r then sums slot r over the lanes of its chain
+            __syncwarp();
 #pragma unroll
-        for (int s = 0; s < 16; ++s) r[s] = s < N::NS ? g[s] : f2(0.f);
-        if (G == 32) {
+            for (int s = 0; s < N::NS; ++s) xs[s * 33 + wl] = g[s];
+            __syncwarp();
+            const float2* col = xs + (own < N::NS ? own : 0) * 33 + (G == 32 ? 0 : (wl & 16));
+            float2 t0 = f2(0.f), t1 = f2(0.f);
 #pragma unroll
-            for (int s = 0; s < 16; ++s) {
-                r[s].x += __shfl_xor_sync(kFull, r[s].x, 16);
-                r[s].y += __shfl_xor_sync(kFull, r[s].y, 16);
+            for (int j = 0; j < (G == 32 ? 32 : 16); j += 2) {
+                t0 = __fadd2_rn(t0, col[j]);
+                t1 = __fadd2_rn(t1, col[j + 1]);
             }
-        }
-        // recursive halving: after the stage with offset o the lane keeps the slots whose index agrees with its own in bit o
-        float2 r8[8], r4[4], r2[2], acc;
-        {
-            const bool up = (lane & 8) != 0;
+            acc = __fadd2_rn(t0, t1);
+            w1s = wbuf[N::SW1 + hp];                              // this slot's hidden pair: evaluation weights as stored by their owners
+            b1s = wbuf[N::SB1 + hp];
+            w2s = wbuf[N::SW2 + hp];
+        } else {
+            float2 r[16];
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                const float2 send = up ? r[s] : r[s + 8], keep = up ? r[s + 8] : r[s];
-                r8[s] = make_float2(keep.x + __shfl_xor_sync(kFull, send.x, 8), keep.y + __shfl_xor_sync(kFull, send.y, 8));
-            }
-        }
-        {
-            const bool up = (lane & 4) != 0;
+            for (int s = 0; s < 16; ++s) r[s] = s < N::NS ? g[s] : f2(0.f);
+            if (G == 32) {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const float2 send = up ? r8[s] : r8[s + 4], keep = up ? r8[s + 4] : r8[s];
-                r4[s] = make_float2(keep.x + __shfl_xor_sync(kFull, send.x, 4), keep.y + __shfl_xor_sync(kFull, send.y, 4));
+                for (int s = 0; s < 16; ++s) {
+                    r[s].x += __shfl_xor_sync(kFull, r[s].x, 16);
+                    r[s].y += __shfl_xor_sync(kFull, r[s].y, 16);
+                }
             }
-        }
-        {
-            const bool up = (lane & 2) != 0;
+            // recursive halving: after the stage with offset o the lane keeps the slots whose index agrees with its own in bit o
+            float2 r8[8], r4[4], r2[2];
+            {
+                const bool up = (lane & 8) != 0;
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const float2 send = up ? r4[s] : r4[s + 2], keep = up ? r4[s + 2] : r4[s];
-                r2[s] = make_float2(keep.x + __shfl_xor_sync(kFull, send.x, 2), keep.y + __shfl_xor_sync(kFull, send.y, 2));
+                for (int s = 0; s < 8; ++s) {
+                    const float2 send = up ? r[s] : r[s + 8], keep = up ? r[s + 8] : r[s];
+                    r8[s] = make_float2(keep.x + __shfl_xor_sync(kFull, send.x, 8), keep.y + __shfl_xor_sync(kFull, send.y, 8));
+                }
             }
-        }
-        {
-            const bool up = (lane & 1) != 0;
-            const float2 send = up ? r2[0] : r2[1], keep = up ? r2[1] : r2[0];
-            acc = make_float2(keep.x + __shfl_xor_sync(kFull, send.x, 1), keep.y + __shfl_xor_sync(kFull, send.y, 1));
+            {
+                const bool up = (lane & 4) != 0;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const float2 send = up ? r8[s] : r8[s + 4], keep = up ? r8[s + 4] : r8[s];
+                    r4[s] = make_float2(keep.x + __shfl_xor_sync(kFull, send.x, 4), keep.y + __shfl_xor_sync(kFull, send.y, 4));
+                }
+            }
+            {
+                const bool up = (lane & 2) != 0;
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const float2 send = up ? r4[s] : r4[s + 2], keep = up ? r4[s + 2] : r4[s];
+                    r2[s] = make_float2(keep.x + __shfl_xor_sync(kFull, send.x, 2), keep.y + __shfl_xor_sync(kFull, send.y, 2));
+                }
+            }
+            {
+                const bool up = (lane & 1) != 0;
+                const float2 send = up ? r2[0] : r2[1], keep = up ? r2[1] : r2[0];
+                acc = make_float2(keep.x + __shfl_xor_sync(kFull, send.x, 1), keep.y + __shfl_xor_sync(kFull, send.y, 1));
+            }
+#pragma unroll
+            for (int h = 0; h < N::HP; ++h)
+                if (hp == h) {
+                    w1s = w[N::SW1 + h];
+                    b1s = w[N::SB1 + h];
+                    w2s = w[N::SW2 + h];
+                }
         }
         // moments -> gradient (see evaluate()): the W1 slot needs A1 of the b1 slot, the b1 slot A0 of the W2 slot - both HP lanes up
         const float2 other = make_float2(__shfl_sync(kFull, acc.x, (own + N::HP) & 15, 16), __shfl_sync(kFull, acc.y, (own + N::HP) & 15, 16));
-        float2 w1s = f2(0.f), b1s = f2(0.f), w2s = f2(0.f);
-#pragma unroll
-        for (int h = 0; h < N::HP; ++h)
-            if (hp == h) {
-                w1s = w[N::SW1 + h];
-                b1s = w[N::SB1 + h];
-                w2s = w[N::SW2 + h];
-            }
         float2 gm = acc;
         if (own < N::SW2) gm = __ffma2_rn(w1s, acc, __fmul2_rn(b1s, other));
         // Gaussian prior on the own slot, rescaling of the data gradient (evaluate())
@@ -458,13 +497,14 @@ struct SmallLaunch {
         OCBNN_LAUNCH_CHECK();
         return OCBNN_OK;
     }
-    template <int G, int MB, int U>
+    template <int G, int MB, int U, bool XS = false>
     static int hmc_own(const Problem& p, const EvalArgs& a, float* q, const float* p0, const double* u, long long m, int n_it, float eps,
                        float eps_half, int L, int restore, uint8_t* acc, float* h, int* flags, float* samples, int thin, cudaStream_t st) {
         if constexpr (use_moments<N>() && N::NS <= 16 && (G == 16 || G == 32)) {
             int tile_cap;
-            size_t sm = smem_bytes(p, npts(a), tile_cap);
-            auto k = k_hmc_own<N, G, MB, U>;
+            const size_t extra = XS ? sizeof(float2) * kOwnXsFloat2PerWarp * (kSmallThreads / 32) : 0;     // per-warp exchange buffers
+            size_t sm = smem_bytes(p, npts(a), tile_cap, extra) + extra;
+            auto k = k_hmc_own<N, G, MB, U, XS>;
             OCBNN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             long long blocks = (m * G + kSmallThreads - 1) / kSmallThreads;
             k<<<(unsigned)blocks, kSmallThreads, sm, st>>>(a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, tile_cap);
@@ -510,9 +550,11 @@ struct SmallLaunch {
         }
         if constexpr ((G == 16 || G == 32) && use_moments<N>() && N::NS <= 16) {
             // 16 / 32 lanes per chain: slot ownership (k_hmc_own).  OCBNN_HMC_OWN=0 selects the replicated k_hmc_small; OCBNN_HMC_GU the points in flight
-            static const bool want_own = [] { const char* e = getenv("OCBNN_HMC_OWN"); return e ? atoi(e) != 0 : true; }();
+            // OCBNN_HMC_OWN: 0 replicated kernel, 1 ownership with shuffle exchanges, 2 ownership with shared-memory exchanges
+            static const int own_mode = [] { const char* e = getenv("OCBNN_HMC_OWN"); return e ? atoi(e) : kDefaultHmcOwn; }();
             static const int gu = [] { const char* e = getenv("OCBNN_HMC_GU"); return e ? atoi(e) : 0; }();
-            if (want_own) {
+            if (own_mode == 2) return hmc_own<G, 4, 2, true>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
+            if (own_mode) {
                 if (gu == 4) return hmc_own<G, 3, 4>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
                 return hmc_own<G, 4, 2>(p, a, q, p0, u, m, n_it, eps, eps_half, L, restore, acc, h, flags, samples, thin, st);
             }
