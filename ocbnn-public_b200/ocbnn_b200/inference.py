@@ -31,6 +31,46 @@ def _name(self, sampler):
     return f"{sampler}_{'ocbnn' if self.use_ocbnn else 'baseline'}"
 
 
+class H2DPipe:
+    """Host draws -> device, two deep: the copy of the next step's host tensor runs on a copy stream under the kernels of the current
+    step.  put() stages a host tensor (through a pinned buffer unless it is pinned already) and returns a slot; take() makes the
+    compute stream wait for that slot's copy and hands out the device tensor; done() marks it reusable."""
+
+    def __init__(self, shape, dev, dtype=torch.float32):
+        self.dev = dev
+        self.stream = torch.cuda.Stream(device=dev)
+        self.dbuf = [torch.empty(shape, dtype=dtype, device=dev) for _ in range(2)]
+        self.hbuf = [None, None]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [None, None]
+        self.i = 0
+
+    def put(self, host):
+        i = self.i
+        self.i ^= 1
+        if not host.is_pinned():
+            if self.hbuf[i] is None:
+                self.hbuf[i] = torch.empty(host.shape, dtype=host.dtype).pin_memory()
+            self.ready[i].synchronize()                   # the previous copy out of this pinned buffer has finished
+            self.hbuf[i].copy_(host)
+            host = self.hbuf[i]
+        if self.consumed[i] is not None:
+            self.stream.wait_event(self.consumed[i])      # the step that read this device buffer two steps ago
+        with torch.cuda.stream(self.stream):
+            self.dbuf[i].copy_(host, non_blocking=True)
+            self.ready[i].record(self.stream)
+        return i
+
+    def take(self, i):
+        torch.cuda.current_stream().wait_event(self.ready[i])
+        return self.dbuf[i]
+
+    def done(self, i):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.consumed[i] = ev
+
+
 def _batch_for(self, t):
     """(offset, stride) of torch.arange(t % nbatches, N_train, nbatches) (inference.py:180,276,334)."""
     nb = int(getattr(self, "nbatches", 0) or 0)
@@ -412,14 +452,24 @@ class BBBMixin:
             gen = torch.Generator(device=dev)
             gen.manual_seed(int(torch.initial_seed()) + 7919 * (D.rank() + 1))
         elbos, state = [], {}
+
+        def host_draw():                        # inference.py:138; rank 0's stream, so that N ranks reproduce one rank
+            eps_all = torch.randn(k, self.nweights)
+            D.broadcast_(eps_all)
+            return eps_all[lo:hi]
+
+        # host draws go to the device two deep (H2DPipe): the draw and the copy of epoch e + 1 run under the kernels of epoch e
+        pipe = None if device_rng or self.bbb_epochs < 1 else H2DPipe((hi - lo, self.nweights), dev)
+        slot = pipe.put(host_draw()) if pipe else None
         for epoch in range(1, self.bbb_epochs + 1):
             if device_rng:
                 eps = torch.randn(hi - lo, self.nweights, device=dev, generator=gen)
-            else:                               # inference.py:138; rank 0's stream, so that N ranks reproduce one rank
-                eps_all = torch.randn(k, self.nweights)
-                D.broadcast_(eps_all)
-                eps = eps_all[lo:hi].to(dev).contiguous()
+            else:
+                cur, slot = slot, (pipe.put(host_draw()) if epoch < self.bbb_epochs else None)
+                eps = pipe.take(cur)
             elbos.append(self.bbb_epoch(qp, acc, eps, epoch, with_data, k_total=k, state=state))
+            if pipe:
+                pipe.done(cur)
             if verbose and epoch % 100 == 0:
                 logging.info(f"  Epoch {epoch}: {float(elbos[-1]):.2f}")
         self.elbos = [float(e) for e in torch.cat(elbos).cpu()] if elbos else []
