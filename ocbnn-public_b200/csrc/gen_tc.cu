@@ -163,7 +163,9 @@ __device__ __forceinline__ float head_switch(int sk, int kind, const float (&z)[
     }
 }
 
-template <int kTP, int ACT>
+// kWLoad: weights (and prior entries) a thread has in flight while it loads a weight vector - 8 where a weight vector meets only a tile or
+// two of points (recid minibatches: the load is a quarter of the chain's time), 4 otherwise
+template <int kTP, int ACT, int kWLoad>
 __global__ void __launch_bounds__(kThreads, 1)
 k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __restrict__ w, long long m, float* __restrict__ out_lp,
                  float* __restrict__ out_grad) {
@@ -239,11 +241,11 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
                 const int n = threadIdx.x & (nn - 1), k0 = threadIdx.x >> sh;
                 if (n < L.n && k0 < rpp) {
                     const int coloff = (n >> 3) * L.w_cg + (n & 7) * 2;
-                    for (int kb = k0; kb < L.kin; kb += 4 * rpp) {
-                        float v[4];
-                        float2 mv[4];
+                    for (int kb = k0; kb < L.kin; kb += kWLoad * rpp) {
+                        float v[kWLoad];
+                        float2 mv[kWLoad];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < kWLoad; ++u) {
                             const int k = kb + u * rpp;
                             if (k < L.kin) {
                                 v[u] = __ldg(wc + L.coff + k * L.n + n);
@@ -251,7 +253,7 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
                             }
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < kWLoad; ++u) {
                             const int k = kb + u * rpp;
                             if (k >= L.kin) break;
                             const float diff = v[u] - mv[u].x, t = diff * mv[u].y;
@@ -645,10 +647,13 @@ int try_launch_logpost_gen_tc(const Problem& p, const EvalArgs& a, const float* 
     auto launch = [&]() -> int {
         void (*kern)(EvalArgs, const gtc::Layout, const float*, long long, float*, float*) = nullptr;
         const int act = p.desc.activation;
-        if (Y.tp == 128) kern = act == OCBNN_ACT_RBF ? gtc::k_logpost_gen_tc<128, OCBNN_ACT_RBF> : act == OCBNN_ACT_RELU ? gtc::k_logpost_gen_tc<128, OCBNN_ACT_RELU>
-                                                                                                                        : gtc::k_logpost_gen_tc<128, OCBNN_ACT_IDENTITY>;
-        else kern = act == OCBNN_ACT_RBF ? gtc::k_logpost_gen_tc<64, OCBNN_ACT_RBF> : act == OCBNN_ACT_RELU ? gtc::k_logpost_gen_tc<64, OCBNN_ACT_RELU>
-                                                                                                        : gtc::k_logpost_gen_tc<64, OCBNN_ACT_IDENTITY>;
+        const bool deep = npts <= 2 * Y.tp;              // few point tiles per weight vector: load it with more requests in flight
+#define OCBNN_GTC_PICK(TP, WL)                                                                                                     \
+    (act == OCBNN_ACT_RBF ? gtc::k_logpost_gen_tc<TP, OCBNN_ACT_RBF, WL>                                                            \
+                          : act == OCBNN_ACT_RELU ? gtc::k_logpost_gen_tc<TP, OCBNN_ACT_RELU, WL> : gtc::k_logpost_gen_tc<TP, OCBNN_ACT_IDENTITY, WL>)
+        if (Y.tp == 128) kern = deep ? OCBNN_GTC_PICK(128, 8) : OCBNN_GTC_PICK(128, 4);
+        else kern = deep ? OCBNN_GTC_PICK(64, 8) : OCBNN_GTC_PICK(64, 4);
+#undef OCBNN_GTC_PICK
         OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Y.smem_bytes));
         const long long grid = m < (long long)p.sm_count ? m : (long long)p.sm_count;
         kern<<<(unsigned)grid, gtc::kThreads, Y.smem_bytes, st>>>(a, Y, w, m, out_lp, out_grad);
