@@ -548,6 +548,25 @@ __device__ __forceinline__ void sel_final_body(const DistSrc dist, const float* 
     if (pairs != hdr->zeros) {
         unsigned prefix = 0;
         unsigned long long r = ok ? __ldcg(&hdr->resid) : rank;
+        if (ok && n2 <= 512u) {
+            // short list (the usual case: ~n^2 / 270 000 candidates in the hit bin): the value of rank r by direct counting - one pass
+            // instead of three radix passes.  Squared distances are positive floats: their order is the order of the bit patterns.
+            for (unsigned i = t; i < n2; i += NT) sh[i] = __float_as_uint(__ldcg(list2 + i));
+            if (t == 0) *s_res = 0ull;
+            __syncthreads();
+            for (unsigned i = t; i < n2; i += NT) {
+                const unsigned v = sh[i];
+                unsigned lt = 0, le = 0;
+                for (unsigned j = 0; j < n2; ++j) {
+                    const unsigned x = sh[j];
+                    lt += x < v ? 1u : 0u;
+                    le += x <= v ? 1u : 0u;
+                }
+                if ((unsigned long long)lt <= r && r < (unsigned long long)le) *s_res = (unsigned long long)v;     // (ties write the same value)
+            }
+            __syncthreads();
+            prefix = (unsigned)*s_res;
+        } else
         for (int pass = 0; pass < 3; ++pass) {
             __syncthreads();
             for (int i = t; i < 2048; i += NT) sh[i] = 0u;
