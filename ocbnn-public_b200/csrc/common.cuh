@@ -105,6 +105,7 @@ int launch_forward_generic(const Problem& p, const float* w, long long m, const 
 // not fit it and the caller should use generic_net.cu's kernels.
 int try_launch_logpost_gen_tc(const Problem& p, const EvalArgs& a, const float* w, long long m, float* out_lp, float* out_grad,
                               cudaStream_t st, int* rc);
+int try_launch_forward_gen_tc(const Problem& p, const float* w, long long m, const float* x, long long npts, float* out, cudaStream_t st, int* rc);
 
 int choose_lanes(const Problem& p, long long m, int points);
 int choose_lanes_hmc(const Problem& p, long long m, int points);

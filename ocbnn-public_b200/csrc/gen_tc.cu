@@ -525,6 +525,166 @@ k_logpost_gen_tc(EvalArgs a, const __grid_constant__ Layout Yp, const float* __r
     if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)Y.tmem_cols);
 }
 
+// ---- forward only (predict / forward, base.py:89-104, 267-277): the forward half of the kernel above -------------------------------
+// out[chain][point][k] = f(x_point; w_chain).  Same operand arrays, GEMM1 and epilogues; the points come straight from x (npts x s_0,
+// row-major) and the rows of the output layer's accumulator go to global memory.  One CTA per weight vector at a time.
+template <int kTP, int ACT>
+__global__ void __launch_bounds__(kThreads, 1)
+k_forward_gen_tc(const __grid_constant__ Layout Yp, const float* __restrict__ w, long long m, const float* __restrict__ x, long long npts,
+                 float* __restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    __shared__ Layout Y;
+    for (int i = threadIdx.x; i < (int)(sizeof(Layout) / 4); i += kThreads) reinterpret_cast<int*>(&Y)[i] = reinterpret_cast<const int*>(&Yp)[i];
+    __syncthreads();
+    float* rec0 = reinterpret_cast<float*>(sm + Y.rec_off);
+    const uint32_t bar = smem_u32(sm + Y.bar_off);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + Y.bar_off + 8);
+    const uint32_t sm_base = smem_u32(sm);
+    const int warp = tc::warp_idx_sync(), lane = threadIdx.x & 31;
+    const int q = warp & 3, part = warp >> 2;
+    constexpr int kActCG = (kTP / 8) * kRG;
+    const int pt = kTP == 128 ? q * 32 + lane : q * 16 + (lane & 15);
+    const bool has_pt = kTP == 128 || lane < 16;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int nl = Y.nl, sk = Y.sk, s0 = Y.s0;
+
+    for (int i = threadIdx.x; i < Y.zero_bytes / 16; i += kThreads) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        tc::mbar_init(bar, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) tc::tmem_alloc(smem_u32(tmem_slot), (uint32_t)Y.tmem_cols);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    uint32_t phase = 0;
+    const int rec_floats = Y.rec_bytes >> 2;
+    // rows [begin, begin + count) of x -> buffer `buf`: contiguous in memory, copied 4 bytes at a time (s_0 is not a multiple of 4 in general)
+    auto prefetch_x = [&](long long begin, int buf) {
+        const int count = (int)min((long long)kTP, npts - begin);
+        const uint32_t dst0 = smem_u32(rec0 + buf * rec_floats);
+        const float* src = x + begin * s0;
+        for (int i = threadIdx.x; i < count * s0; i += kThreads) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst0 + (uint32_t)(i * 4)), "l"(src + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    for (long long chain = blockIdx.x; chain < m; chain += gridDim.x) {
+        const float* wc = w + chain * Y.d;
+        __syncthreads();                                  // the previous weight vector's last GEMM has been waited for by every thread
+        for (int l = 1; l <= nl; ++l) {
+            const Layer& L = Y.L[l];
+            uint8_t* wp = sm + L.w_off;
+            int nn = 8;
+            while (nn < L.n) nn <<= 1;
+            const int sh = __ffs(nn) - 1, rpp = max(1, kThreads >> sh);
+            const int n = threadIdx.x & (nn - 1), k0 = threadIdx.x >> sh;
+            if (n < L.n && k0 < rpp) {
+                const int coloff = (n >> 3) * L.w_cg + (n & 7) * 2;
+                for (int k = k0; k < L.kin; k += rpp) {
+                    const float v = __ldg(wc + L.coff + k * L.n + n);
+                    __nv_bfloat16 b0 = __float2bfloat16_rn(v);
+                    float r = v - __bfloat162float(b0);
+                    __nv_bfloat16 b1 = __float2bfloat16_rn(r);
+                    r -= __bfloat162float(b1);
+                    __nv_bfloat16 b2 = __float2bfloat16_rn(r);
+                    const int off = coloff + (k >> 3) * kRG + (k & 7) * 16;
+                    *reinterpret_cast<__nv_bfloat16*>(wp + off) = b0;
+                    *reinterpret_cast<__nv_bfloat16*>(wp + L.w_part + off) = b1;
+                    *reinterpret_cast<__nv_bfloat16*>(wp + 2 * L.w_part + off) = b2;
+                }
+            }
+        }
+        int buf = 0;
+        if (npts > 0) prefetch_x(0, 0);
+        for (long long begin = 0; begin < npts; begin += kTP, buf ^= 1) {
+            const int count = (int)min((long long)kTP, npts - begin);
+            const float* rec = rec0 + buf * rec_floats;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            if (begin + kTP < npts) prefetch_x(begin + kTP, buf ^ 1);
+            {
+                const Layer& L1 = Y.L[1];
+                const int nch = L1.kp >> 3, per = (nch + kParts - 1) / kParts;
+                const float* r = rec + pt * s0;
+                const int a_off = L1.a_off, a_part = L1.a_part;
+                for (int ch = part * per; ch < min(nch, (part + 1) * per); ++ch) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int f = ch * 8 + i;
+                        v[i] = f < s0 ? (pt < count ? r[f] : 0.f) : (f == s0 ? 1.f : 0.f);
+                    }
+                    if (has_pt) store_chunk(sm + a_off, a_part, act_chunk_off<kTP>(pt, ch), v);
+                }
+            }
+            fence_async_smem();
+            __syncthreads();
+            for (int l = 1; l <= nl; ++l) {
+                const Layer& L = Y.L[l];
+                const uint32_t zc = l < nl ? (uint32_t)L.z_col : (uint32_t)Y.da_col;
+                if (warp == 0) {
+                    if (tc::elect_one_sync()) {
+                        tc::tc_fence_after();
+                        const uint32_t idesc = idesc_bf16(kTP, L.np, 0, 1);
+                        const uint64_t da = desc_noswz(sm_base + L.a_off, kActCG, kRG);
+                        const uint64_t db = desc_noswz(sm_base + L.w_off, kRG, L.w_cg);
+                        for (int ks = 0; ks < (L.kp >> 4); ++ks)
+                            umma_x3(tmem + zc, da + (uint64_t)((ks * 2 * kActCG) >> 4), db + (uint64_t)((ks * 2 * kRG) >> 4), L.a_part >> 4,
+                                    L.w_part >> 4, idesc, ks != 0);
+                        tc::umma_commit(bar);
+                    }
+                    __syncwarp();
+                }
+                tc::mbar_wait(bar, phase);
+                phase ^= 1;
+                tc::tc_fence_after();
+                if (l < nl) {
+                    const Layer& N = Y.L[l + 1];
+                    const int nch = N.kp >> 3, per = (nch + kParts - 1) / kParts;
+                    const int c_lo = part * per, c_hi = min(nch, (part + 1) * per);
+                    const int n_real = L.n, np = L.np, a_off = N.a_off, a_part = N.a_part;
+                    constexpr int act = ACT;
+                    for (int c0 = c_lo; c0 < c_hi; c0 += kBatch) {
+                        uint32_t raw[kBatch][8];
+#pragma unroll
+                        for (int j = 0; j < kBatch; ++j)
+                            if (c0 + j < c_hi && (c0 + j) * 8 < np) tmem_ld8_nowait(tmem + lane_base + zc + (uint32_t)((c0 + j) * 8), raw[j]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < kBatch; ++j) {
+                            if (c0 + j >= c_hi) break;
+                            const int f0 = (c0 + j) * 8;
+                            float v[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = f0 + i < n_real ? act_f(act, __uint_as_float(raw[j][i])) : (f0 + i == n_real ? 1.f : 0.f);
+                            if (has_pt) store_chunk(sm + a_off, a_part, act_chunk_off<kTP>(pt, c0 + j), v);
+                        }
+                    }
+                } else if (part == 0) {
+                    uint32_t raw[2][8];
+                    tmem_ld8_nowait(tmem + lane_base + zc, raw[0]);
+                    tmem_ld8_nowait(tmem + lane_base + zc + 8, raw[1]);
+                    tmem_ld_wait();
+                    if (has_pt && pt < count) {
+                        float* o = out + ((long long)chain * npts + begin + pt) * sk;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k)
+                            if (k < sk) o[k] = __uint_as_float(raw[k >> 3][k & 7]);
+                    }
+                }
+                tc::tc_fence_before();
+                fence_async_smem();
+                __syncthreads();
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)Y.tmem_cols);
+}
+
+
 // ---- host side --------------------------------------------------------------------------------------------------------------------
 static bool make_layout(const Problem& p, Layout& Y, bool overlap, int tp) {
     Y = Layout{};
@@ -657,6 +817,37 @@ int try_launch_logpost_gen_tc(const Problem& p, const EvalArgs& a, const float* 
         OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Y.smem_bytes));
         const long long grid = m < (long long)p.sm_count ? m : (long long)p.sm_count;
         kern<<<(unsigned)grid, gtc::kThreads, Y.smem_bytes, st>>>(a, Y, w, m, out_lp, out_grad);
+        OCBNN_LAUNCH_CHECK();
+        return OCBNN_OK;
+    };
+    *rc_out = launch();
+    return 1;
+}
+
+// forward / predict of the application nets on the same tcgen05 machinery; 1 = launched, 0 = use generic_net.cu's SIMT forward
+int try_launch_forward_gen_tc(const Problem& p, const float* w, long long m, const float* x, long long npts, float* out, cudaStream_t st, int* rc_out) {
+    static const bool enabled = [] { const char* e = getenv("OCBNN_GEN_TC"); return e ? atoi(e) != 0 : true; }();
+    *rc_out = OCBNN_OK;
+    if (!enabled || npts < 32) return 0;                  // a handful of points: the SIMT kernel has no tile to fill
+    gtc::Layout Y;
+    bool ok = false;
+    Problem q = p;
+    q.rs = p.desc.layer_sizes[0];                         // the staged "records" are the rows of x
+    for (int tp : {128, 64}) {
+        if (tp == 128 && npts <= 64) continue;
+        ok = gtc::make_layout(q, Y, false, tp) && Y.smem_bytes + 2048 <= p.max_smem_optin;
+        if (ok) break;
+    }
+    if (!ok) return 0;
+    auto launch = [&]() -> int {
+        void (*kern)(const gtc::Layout, const float*, long long, const float*, long long, float*) = nullptr;
+        const int act = p.desc.activation;
+#define OCBNN_GTC_FWD(TP) (act == OCBNN_ACT_RBF ? gtc::k_forward_gen_tc<TP, OCBNN_ACT_RBF> : act == OCBNN_ACT_RELU ? gtc::k_forward_gen_tc<TP, OCBNN_ACT_RELU> : gtc::k_forward_gen_tc<TP, OCBNN_ACT_IDENTITY>)
+        kern = Y.tp == 128 ? OCBNN_GTC_FWD(128) : OCBNN_GTC_FWD(64);
+#undef OCBNN_GTC_FWD
+        OCBNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Y.smem_bytes));
+        const long long grid = m < (long long)p.sm_count ? m : (long long)p.sm_count;
+        kern<<<(unsigned)grid, gtc::kThreads, Y.smem_bytes, st>>>(Y, w, m, x, npts, out);
         OCBNN_LAUNCH_CHECK();
         return OCBNN_OK;
     };

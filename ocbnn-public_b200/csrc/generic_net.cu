@@ -762,6 +762,10 @@ int launch_logpost_generic(const Problem& p, const EvalArgs& a, const float* w, 
 }
 
 int launch_forward_generic(const Problem& p, const float* w, long long m, const float* x, long long npts, float* out, cudaStream_t st) {
+    {   // tcgen05 forward (gen_tc.cu) where the net fits it and there are enough points for a tile
+        int rc = OCBNN_OK;
+        if (try_launch_forward_gen_tc(p, w, m, x, npts, out, st, &rc)) return rc;
+    }
     GenLayout L;
     int sm = pick_tp(p, L, false);
     OCBNN_REQUIRE(sm > 0, OCBNN_EUNSUPPORTED, "network with %d weights does not fit the shared-memory resident kernel", p.d);
