@@ -47,6 +47,11 @@ def test_k1_application_shape_full_size(wl, full_rows):
         assert np.isfinite(lp64).all()
         hold("k1_fullsize", wl, tag + "/grad", rel_err(gr.cpu().numpy(), g64), 1e-5, 2 * rel_err(g32, g64))
         hold("k1_fullsize", wl, tag + "/value", np.abs(lp.cpu().numpy() - lp64) / np.abs(lp64), 1e-5, 2 * np.abs(lp32 - lp64) / np.abs(lp64))
+    # forward / predict on the same machinery (k_forward_gen_tc): 3000 points, 24 tiles of 128 (47 of 64)
+    Xf = m.X_train[:3000]
+    F = prob.forward(Wd, Xf.cuda().contiguous()).cpu().numpy()
+    F64 = orc.forward(spec, W.astype(np.float64), Xf.numpy().astype(np.float64), dtype=np.float64)
+    hold("k1_fullsize", wl, "forward", np.abs(F - F64).max() / max(1.0, np.abs(F64).max()), 1e-5)
     lp, gr = prob.logpost_grad(Wd, (0, 1), False)                 # prior only: no points
     lp64, g64 = orc.log_posterior(spec, W, None, False, dtype=np.float64)
     hold("k1_fullsize", wl, "prior/grad", rel_err(gr.cpu().numpy(), g64), 1e-5)
