@@ -38,7 +38,7 @@ extern "C" {
 #define OCBNN_API
 #endif
 
-#define OCBNN_ABI_VERSION 2
+#define OCBNN_ABI_VERSION 3 /* 3: ocbnn_predict, ocbnn_violation_flags, with_data = 2 (likelihood only) in ocbnn_logpost_grad */
 #define OCBNN_MAX_LAYERS 8
 
 /* error codes */

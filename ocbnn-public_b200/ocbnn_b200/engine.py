@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libocbnn_b200.so")
 
-OCBNN_ABI_VERSION = 2
+OCBNN_ABI_VERSION = 3
 OCBNN_MAX_LAYERS = 8
 ACT_IDENTITY, ACT_RBF, ACT_RELU = 0, 1, 2
 HEAD_LIK_GAUSS, HEAD_NEG_EXP, HEAD_POS_GAUSS, HEAD_DIRICHLET, HEAD_LIK_SOFTMAX, HEAD_LIK_BERNOULLI = range(6)
